@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- SDF train pts/s of the fused MISO hot path on N B200s (driver contract in the task).
+
+Workload (BASELINE.json configs[1], `build_submaps`): one ScanNet-submap-shaped GridNet per GPU
+(bound [[-10,10],[-5,5],[-10,10]], 2 levels: coarse (1,4,40,20,40), fine (1,4,200,100,200), decoder
+8->64->64->1 fixed), 2^20 synthetic RGB-D-sampled points per iteration.  A "step" is one mapping
+iteration of the reference's hot loop (grid_opt/trainer.py:209-217): loss.compute (L1 sdf + 0.1
+free-space + 0.5 second-order eikonal) -> backward -> Adam.step over both grid levels.
+N GPUs = N independent submaps (weak scaling, no data-path collective).
+
+  value     device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e       same step through miso_b200.trainer with HOST (pinned) buffers: H2D of the batch and a D2H
+            read of the loss every step, inside the timed region
+  roofline  fused mapping kernel: algorithmic bytes/launch over its measured duration vs the measured
+            HBM peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle port of the reference's torch CPU path (the reference is
+            Python and /root/reference is absent on the GPU box) on a bounded sample, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+N_POINTS = 1 << 20
+NUM_KF = 49
+NUM_HOST_BATCHES = 4
+LOSS_CFG = dict(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                grad_method="autograd", eik_trunc_dist=None)
+# algorithmic bytes per point of the fused step (DESIGN.md "bytes per unit"): coords 12 + frame id 8 + sdf 4 +
+# valid 1 + sign 4 + weight 4 + corner gather 2 levels x 8 x 16 B + gradient scatter 2 x 8 x 16 B
+BYTES_PER_POINT = 12 + 8 + 4 + 1 + 4 + 4 + 256 + 256
+SURVEY_BYTES_PER_POINT = 1068   # SURVEY.md section 8d two-pass figure (fwd + bwd re-gather + eikonal scatter)
+FLOPS_PER_POINT = 2 * (2 * (8 * 64 + 64 * 64) + 64)  # MLP forward + Jacobian backward, FMA = 2 flops
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_host_batches(seed0):
+    from miso_b200 import synth
+    batches = []
+    poses = synth.keyframe_poses(NUM_KF, synth.SCANNET_SUBMAP_BOUND, seed=55 + seed0)
+    for b in range(NUM_HOST_BATCHES):
+        mi, gt, _ = synth.rgbd_batch(N_POINTS, num_kf=NUM_KF, seed=1000 * seed0 + b, poses=poses)
+        mi = {k: v.pin_memory() for k, v in mi.items()}
+        gt = {k: v.pin_memory() for k, v in gt.items()}
+        batches.append((mi, gt))
+    return batches, poses
+
+
+def build_model(device, poses, seed):
+    from miso_b200 import synth
+    from miso_b200.models import GridNet
+    cfg = synth.model_cfg(synth.SCANNET_SUBMAP_BOUND, num_poses=NUM_KF)
+    net = GridNet(cfg, device=device)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for lvl in net.features:
+            lvl.feature.copy_((torch.randn(lvl.feature.shape, generator=g) * 1e-2).to(device))
+    net.decoder.load_state_dict(synth.decoder_weights(8, seed=0))
+    R, t = poses
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    return net
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from miso_b200 import _lib, loss as mloss
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    batches, poses = make_host_batches(rank)
+    net = build_model(device, poses, seed=rank)
+    L = MisoLossMapping(**LOSS_CFG)
+    trainer = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net, L, lambda e: batches[e % NUM_HOST_BATCHES],
+                          device=device)
+    dev_batches = [({k: v.to(device) for k, v in mi.items()}, {k: v.to(device) for k, v in gt.items()})
+                   for mi, gt in batches]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident value ----------------
+    for i in range(args.warmup):
+        trainer.train_step(*dev_batches[i % NUM_HOST_BATCHES])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    mloss.PROFILE_EVENTS = []
+    launches0 = _lib.LAUNCHES["total"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        last = trainer.train_step(*dev_batches[i % NUM_HOST_BATCHES])
+    e1.record()
+    barrier()
+    launches = _lib.LAUNCHES["total"] - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    kern_ms = [a.elapsed_time(b) for a, b in mloss.PROFILE_EVENTS]
+    mloss.PROFILE_EVENTS = None
+    clocks = sampler.stop() if sampler else None
+    final_loss = [float(v) for v in last.tolist()]
+
+    # ---------------- end-to-end through the trainer API with host buffers ----------------
+    copy_stream = torch.cuda.Stream(device)
+    loss_host = torch.zeros(args.steps + args.warmup, 4).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for d in batches[0] for v in d.values())
+
+    def stage(i):
+        mi, gt = batches[i % NUM_HOST_BATCHES]
+        with torch.cuda.stream(copy_stream):
+            dmi = {k: v.to(device, non_blocking=True) for k, v in mi.items()}
+            dgt = {k: v.to(device, non_blocking=True) for k, v in gt.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dmi, dgt, ev
+
+    def e2e_loop(n, offset):
+        cur = torch.cuda.current_stream(device)
+        nxt = stage(offset)
+        for i in range(n):
+            dmi, dgt, ev = nxt
+            if i + 1 < n:
+                nxt = stage(offset + i + 1)      # H2D of batch i+1 overlaps step i
+            cur.wait_event(ev)
+            for d in (dmi, dgt):
+                for v in d.values():
+                    v.record_stream(cur)
+            terms = trainer.train_step(dmi, dgt)
+            loss_host[offset + i].copy_(terms, non_blocking=True)   # D2H read of the step's loss
+
+    e2e_loop(args.warmup, 0)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(args.steps, args.warmup)
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the e2e run"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    ms_step = ms_total / args.steps
+    value = world * N_POINTS / (ms_step * 1e-3)
+    kms = float(np.mean(kern_ms))
+    achieved = BYTES_PER_POINT * N_POINTS / (kms * 1e-3) / 1e9
+    line = {
+        "metric": "SDF train pts/s (grid+MLP fwd/bwd/eikonal)", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "build_submaps: 1 ScanNet-submap GridNet per GPU, 2 levels (40x20x40, 200x100x200) x C4, "
+                               "decoder 8-64-64-1 fixed, 2^20 RGB-D-sampled pts/iter, L1 sdf + 0.1 free-space + 0.5 "
+                               "second-order eikonal, Adam joint",
+                   "points_per_step_per_gpu": N_POINTS, "submaps": world, "parallelism": f"submap-per-gpu x{world}",
+                   "l2_policy": f"{NUM_HOST_BATCHES} distinct batches cycled; grids+grads+Adam state+batch "
+                                "(~360 MB/step touched) exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * N_POINTS / (e2e_ms / args.steps * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "mapping_step_kernel<2,4> (+finalize)", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "bytes_per_point": BYTES_PER_POINT, "survey_bytes_per_point": SURVEY_BYTES_PER_POINT,
+                     "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
+                     "fp32_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12},
+        "final_loss_terms": final_loss,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_arm(steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_arm(steps, warmup, sample_points=1 << 18):
+    """The reference's CPU path for the SAME step (oracle port: identical torch ops to
+    grid_opt/loss.py:754-813 + torch.optim.Adam; the second-order eikonal goes through the gather
+    restatement because F.grid_sample has no double backward on CPU), on a bounded
+    sample of the workload: full-size grids, `sample_points` of the 2^20 points per step."""
+    from miso_b200 import synth
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count())
+    shapes = O.level_shapes(synth.SCANNET_SUBMAP_BOUND, 0.5, 5, 2, 4)
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(s, generator=g) * 1e-2 for s in shapes]
+    dec = O.make_decoder(8)
+    dec.load_state_dict({k.replace("network.", ""): v for k, v in synth.decoder_weights(8).items()})
+    model = O.OracleGridNet(synth.SCANNET_SUBMAP_BOUND, feats, dec, second_order=True)
+    mi, gt, (R, t) = synth.rgbd_batch(sample_points, num_kf=NUM_KF, seed=0)
+    poses = {k: (R[k], t[k]) for k in range(R.shape[0])}
+    opt = torch.optim.Adam(list(model.features.parameters()), lr=1e-3)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        ld = O.mapping_loss(model, mi, gt, poses, LOSS_CFG["loss_type"], LOSS_CFG["weight_sdf"], LOSS_CFG["weight_eik"],
+                            LOSS_CFG["weight_fs"], LOSS_CFG["trunc_dist"], grad_method="autograd", eik_trunc_dist=None)
+        sum(ld.values()).backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": sample_points / sec, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sample_points} of the 2^20 points/step on the full-size grids, {steps} timed steps "
+                      f"(+{warmup} warm-up), loss+backward+Adam; Adam sweeps the full dense grids as in the reference",
+            "sec_per_step": sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    cb = cpu_reference_arm(steps=steps, warmup=warm)
+    line = {"impl": "reference", "metric": "SDF train pts/s (grid+MLP fwd/bwd/eikonal)", "value": cb["value"],
+            "unit": "points/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+            "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "build_submaps (same step as the product arm) on the reference's torch CPU path "
+                                   "(oracle port), bounded sample"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

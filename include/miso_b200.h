@@ -1,0 +1,227 @@
+/*
+ * miso_b200.h -- C-ABI of the B200-native (sm_100a) MISO hot path.
+ *
+ * Plain C: raw device pointers, sizes, element strides, a cudaStream_t (passed as void*), int
+ * return code (0 = ok, <0 = error; text via miso_last_error_string()).  No torch types, no
+ * exceptions, no allocation: the caller owns every buffer.  Scatter targets ("grad" buffers)
+ * are ACCUMULATED into (the caller pre-zeroes them or lets gradients accumulate), which removes
+ * the grid-sized zeros_like the reference performs on every call
+ * (third_party/cuda_gridsample_grad2/gridsample_cuda.cu:620-622).
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ */
+#ifndef MISO_B200_H_
+#define MISO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MISO_ABI_VERSION 1
+#define MISO_MAX_LEVELS 4          /* grid.n_levels; shipped configs use 2 (configs/rgbd/scannet.yaml:24) */
+#define MISO_MAX_POSES 1024
+
+/* error codes */
+#define MISO_OK 0
+#define MISO_ERR_INVALID_ARG (-1)
+#define MISO_ERR_UNSUPPORTED (-2)
+#define MISO_ERR_CUDA (-3)
+
+/* dtype codes for the generic grid_sample entry points */
+#define MISO_F32 0
+#define MISO_F64 1
+
+/* padding_mode codes -- same indices as cuda_gridsample.py:87 (['zeros','border'].index) */
+#define MISO_PAD_ZEROS 0
+#define MISO_PAD_BORDER 1
+
+typedef void* miso_stream_t; /* cudaStream_t */
+
+/* Return text of the last error raised on the calling thread ("" if none). */
+const char* miso_last_error_string(void);
+int miso_abi_version(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int miso_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Generic trilinear grid_sample (the reference's plugin point).
+ *
+ * Replaces cu.grid_sample_3d / _GridSample3dForward / _GridSample3dBackward
+ * (third_party/cuda_gridsample_grad2/cuda_gridsample.py:17-19,76-126) selected by
+ * FeatureGrid.grid_sample_func (grid_opt/models/grid_modules.py:63-69), i.e.
+ *   fwd      = ATen grid_sampler_3d                (mode bilinear)
+ *   bwd      = aten::grid_sampler_3d_backward      (cuda_gridsample.py:102-107)
+ *   bwd_bwd  = grid_sampler_3d_grad2_kernel        (gridsample_cuda.cu:212-533)
+ *
+ * input  : (B,C,D,H,W) with arbitrary element strides in_strides[5] (NCDHW or channels_last_3d;
+ *          the 128-bit vector path is taken when stride_C==1, C%4==0 and the base is 16B aligned)
+ * grid   : (B,P,3) contiguous, normalised coords in [-1,1], last dim (x,y,z)->(W,H,D)
+ * output : (B,C,P) addressed with out_strides[3] = (sB,sC,sP)
+ * ------------------------------------------------------------------------------------------ */
+int miso_grid_sample3d_fwd(int dtype, const void* input, const int64_t in_sizes[5], const int64_t in_strides[5],
+                           const void* grid, int64_t P, void* output, const int64_t out_strides[3],
+                           int padding_mode, int align_corners, miso_stream_t stream);
+
+/* grad_input (same sizes as input, element strides gi_strides or, when NULL, input's; accumulated)
+ * and grad_grid ((B,P,3) contiguous, overwritten) are each optional (NULL) -- mirrors output_mask of
+ * aten::grid_sampler_3d_backward. */
+int miso_grid_sample3d_bwd(int dtype, const void* grad_output, const int64_t go_strides[3], const void* input,
+                           const int64_t in_sizes[5], const int64_t in_strides[5], const void* grid, int64_t P,
+                           void* grad_input, const int64_t gi_strides[5], void* grad_grid, int padding_mode,
+                           int align_corners, miso_stream_t stream);
+
+/* Double backward.  Inputs gg_input (grid-shaped, strides ggi_strides) and gg_grid ((B,P,3)) are
+ * optional (NULL == zeros).  Outputs gg_output ((B,C,P), ggo_strides, overwritten), g_input
+ * (input-shaped, gi_strides or input's when NULL, accumulated), g_grid ((B,P,3), overwritten) are optional. */
+int miso_grid_sample3d_bwd_bwd(int dtype, const void* gg_input, const int64_t ggi_strides[5], const void* gg_grid,
+                               const void* grad_output, const int64_t go_strides[3], const void* input,
+                               const int64_t in_sizes[5], const int64_t in_strides[5], const void* grid, int64_t P,
+                               void* gg_output, const int64_t ggo_strides[3], void* g_input,
+                               const int64_t gi_strides[5], void* g_grid, int padding_mode, int align_corners,
+                               miso_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Fused multiresolution field: L dense levels over one bound + ReLU MLP decoder.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct miso_level {
+  const float* feat; /* level tensor base, logical (1,C,Z,Y,X) (grid_modules.py:55-57) */
+  float* grad;       /* same layout, accumulated into; may be NULL when no grid gradient is wanted */
+  int32_t X, Y, Z, C;
+  int64_t sC, sZ, sY, sX; /* element strides; fused kernels require sC==1 (channels_last_3d) */
+} miso_level_t;
+
+typedef struct miso_field {
+  int32_t num_levels;
+  uint32_t ignore_mask; /* bit l set: level l contributes zeros (GridNet.ignore_level_, utils.py:159-163) */
+  float bound[6];       /* xmin,xmax,ymin,ymax,zmin,zmax  (BaseNet.bound, base_net.py:31-36) */
+  miso_level_t level[MISO_MAX_LEVELS];
+} miso_field_t;
+
+/* MLPNet(input_dim=F, 1, hidden_dim=H, hidden_layers=1, bias=True) (grid_opt/models/modules.py:11-32);
+ * nn.Linear layout: W row-major [out][in]. */
+typedef struct miso_decoder {
+  const float *W1, *b1, *W2, *b2, *W3, *b3;
+  int32_t in_dim, hidden_dim;
+} miso_decoder_t;
+
+/* Optional frame->world transform fused in front of the field (loss.py:764-774):
+ * x_world = R[id] x + t[id].  ids int64 (N), R (K,3,3) row-major, t (K,3).  All NULL = identity. */
+typedef struct miso_frames {
+  const int64_t* ids;
+  const float* R;
+  const float* t;
+  int32_t num_frames;
+} miso_frames_t;
+
+/* grid_interp_regular (grid_opt/utils/utils.py:143-164): feats (N, sum_l C_l) row-major. */
+int miso_field_features(const miso_field_t* field, const float* x, int64_t N, float* feats, miso_stream_t stream);
+
+/* GridNet.forward (grid_net.py:306-325) + analytic first-order quantities, one kernel:
+ *   sdf (N)      = MLP(concat_l interp_l(x))
+ *   jac (N,F)    = d sdf / d feat                          (optional, NULL to skip)
+ *   gradx (N,3)  = d sdf / d x  == gradient3d(...,'autograd')   (diff.py:27-33; optional)
+ *   xw (N,3)     = transformed coordinates when frames given (optional) */
+int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                     const float* x, int64_t N, float* sdf, float* jac, float* gradx, float* xw,
+                     miso_stream_t stream);
+
+/* Backward of the above w.r.t. the grids, a single scatter:
+ *   grad_l[corner] += (a*w_c + v . dw_c/dx) * jac_l      a = dL/dsdf (N, optional), v = dL/dgradx (N,3, optional)
+ * The v-term is the fused double-backward of the eikonal loss (replaces gridsample_cuda.cu:450-481).
+ * hv (N,3) optional output: d/dx of (v . gradx) with jac held fixed (mixed second derivatives,
+ * gridsample_cuda.cu:484-531) -- the coordinate cotangent of the eikonal double-backward. */
+int miso_sdf_backward(const miso_field_t* field, const float* xw, int64_t N, const float* jac, const float* a,
+                      const float* v, float* hv, miso_stream_t stream);
+
+/* Whole mapping step (MisoLossMappingBase.compute loss.py:754-813 + backward), one kernel:
+ *   sdf term  (miso_loss_regression loss.py:594-635), L1 or L2, valid mask, weights, mean over N
+ *   fs  term  (miso_loss_free_space loss.py:668-700)
+ *   eik term  (miso_loss_eikonal loss.py:638-665), analytic gradient, optional |gt|<eik_trunc filter
+ * and scatters d(total)/d(grid) into level[].grad.  total = w_sdf*sdf + w_fs*fs + w_eik*eik. */
+typedef struct miso_mapping_cfg {
+  int32_t loss_type;      /* 0 = L1, 1 = L2 */
+  float weight_sdf, weight_fs, weight_eik;
+  float trunc_dist;       /* free-space lower bound */
+  float eik_trunc_dist;   /* <0: no filter (None) */
+  int32_t eik_mode;       /* 0 = off, 1 = analytic (autograd second-order equivalent) */
+  float grad_scale;       /* upstream d(total) (normally 1) */
+} miso_mapping_cfg_t;
+
+/* gt arrays are (N) float; valid is uint8/bool (N).  eik_count: device int32 counter holding the
+ * number of eikonal samples (written by miso_mapping_count; read by the step when the filter is on).
+ * partials: device float[(grid_blocks)*4] workspace, loss_out: device float[4] =
+ * {sdf_term, fs_term, eik_term, total} (unweighted terms, weighted total).
+ * sdf_out (N) optional.  Returns the number of blocks needed for partials via miso_mapping_workspace. */
+int64_t miso_mapping_workspace_floats(void);
+int miso_mapping_count(const float* gt_sdf, int64_t N, float eik_trunc_dist, int32_t* eik_count, miso_stream_t stream);
+int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                      const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                      const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                      const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                      miso_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Latent-space submap alignment (pairwise_loss_latent, grid_opt/align/miso.py:116-211),
+ *    batched over all submap pairs of one iteration of generic_align_multiple_submaps
+ *    (grid_opt/align/base.py:127-159) in ONE launch.
+ *
+ * For pair i and each src sample p (M,3):  u = A1 p + b1 (src->world), q = A2 u + b2 (world->dst)
+ * (transform_points_to / transfrom_points_from, utils_geometry.py:214-240; A1=R_s, b1=t_s,
+ * A2=R_d^T, b2=-R_d^T t_d are composed by the caller exactly as the reference does, so autograd
+ * can finish through so3_exp_map), inclusive in-bound test against the dst bound
+ * (coords_in_bound :11-27), r = f_src(p)[0:K] - f_dst(q)[0:K], K = C*(levels_used).
+ * Reductions (float64) into out[i*MISO_ALIGN_OUT + ...]:
+ *   [0] S = sum r^2   [1] count of valid points   [2..4] G0 = sum gamma   [5..13] G1 = sum gamma u^T
+ *   [14..22] G2 = sum gamma p^T (row-major 3x3),  gamma = dS/dq           [23] sum_i |r_i|_2
+ *   [24..29] Jtr, [30..65] JtJ: Gauss-Newton normal equations of r wrt a left-multiplied dst-frame
+ *   twist (tracker.py:179-197 conventions), accumulated only when want_gn != 0.
+ * ------------------------------------------------------------------------------------------ */
+#define MISO_ALIGN_OUT 72
+typedef struct miso_align_pair {
+  int32_t src, dst;        /* indices into fields[] */
+  int32_t levels_used;     /* level+1: channels [0, C*levels_used) enter the residual (miso.py:133-134) */
+  int32_t reserved;
+  const float* p;          /* (M,3) src-frame samples: GridAtlas.coordinates_for_alignment (grid_atlas.py:581-587) */
+  int64_t M;
+  const float* fsrc;       /* optional (M,K) cached f_src(p): constant across iterations */
+  uint8_t* mask_out;       /* optional (M): bit-exact in-bound mask (1 = valid) */
+  const int32_t* enabled;  /* optional device flag (e.g. intersection test result); NULL = enabled */
+  float src_grad_scale;    /* when fields[src].level[].grad != NULL: grad += src_grad_scale * dS/dfeat */
+  float dst_grad_scale;
+} miso_align_pair_t;
+
+/* fields, pairs, poses ((num_pairs,24) floats: A1 row-major, b1, A2 row-major, b2) and out are
+ * DEVICE pointers; out is overwritten. */
+int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
+                     int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t want_gn,
+                     miso_stream_t stream);
+
+/* check_submap_intersection (grid_atlas.py:405-420) for all pairs in one launch: for pair i counts
+ * the src vertices (pairs[i].p, M) that land inside fields[dst].bound; enabled_out[i] =
+ * (count / M > overlap_thresh).  counts_out (num_pairs) int64 optional. */
+int miso_align_intersections(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
+                             int32_t num_pairs, int64_t max_M, const float* poses, float overlap_thresh,
+                             int32_t* enabled_out, unsigned long long* counts_out, miso_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Helpers around the path.
+ * ------------------------------------------------------------------------------------------ */
+/* 30-bit (10 bits/axis) Morton key of each point inside bound, for L2-local batch ordering. */
+int miso_morton_keys(const float* x, int64_t N, const float bound[6], uint32_t* keys, miso_stream_t stream);
+
+/* x_world = R[id] x + t[id]  (loss.py:764-774 without the per-keyframe host loop). */
+int miso_transform_points(const float* x, const int64_t* ids, const float* R, const float* t, int32_t num_frames,
+                          int64_t N, float* y, miso_stream_t stream);
+
+/* torch.optim.Adam (no amsgrad, no weight decay) single-tensor step; optionally zeroes g in the
+ * same pass so the next scatter starts from a clean buffer (trainer.py:216-217 + zero_grad). */
+int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int32_t step, int32_t zero_grad, miso_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISO_B200_H_ */

@@ -1,0 +1,355 @@
+"""Latent-space submap alignment on the B200 path.  Same names / arguments as the reference:
+
+    pairwise_loss_latent                  grid_opt/align/miso.py:116-211
+    generic_align_multiple_submaps        grid_opt/align/base.py:89-163
+    align_multiple_submaps_hierarchical   grid_opt/align/miso.py:217-322
+
+`pairwise_loss_latent` keeps its per-pair signature (it is a batch of one).  The multi-pair loop
+evaluates EVERY pair of an iteration in one launch (miso_align_batch): transform, inclusive
+in-bound mask, both interpolations, residual and the reductions that autograd needs
+(sum r^2, count, sum gamma, sum gamma u^T, sum gamma p^T), then finishes through the same tiny
+torch ops as the reference (R0 @ so3_exp_map(w), R^T, -R^T t), so `dL/dw`, `dL/dtau` and the Adam
+update follow the reference's path.  The per-pair intersection test (grid_atlas.py:405-420) is one
+more launch and stays on the device (the reference syncs the host once per pair per iteration).
+
+Deliberate deviation: the reference also back-propagates into both submaps' dense feature grids
+(they are left requires_grad=True by Mapper.mapping, mapper.py:72) although no optimizer reads
+them; here that scatter is opt-in (`feature_grads=True`).
+"""
+import ctypes as C
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from . import _lib
+from . import field as _field
+from . import geometry as utils_geometry
+from .models import GridAtlas
+
+
+def _structs_to_device(structs, device) -> torch.Tensor:
+    raw = b"".join(bytes(s) for s in structs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+class AlignBatch:
+    """Device-side description of one alignment problem: all submaps' fields + a list of
+    (src, dst) pairs at one level.  Built once per level; reused by every iteration."""
+
+    def __init__(self, grid_atlas: GridAtlas, pairs: Sequence[Tuple[int, int]], level: int, fdim: int = 4,
+                 subsample_points: Optional[int] = None, cache_src_features: bool = True, want_masks: bool = False,
+                 check_intersection: bool = True):
+        self.atlas = grid_atlas
+        self.pairs = list(pairs)
+        self.level = level
+        self.device = torch.device(grid_atlas.device)
+        self.levels_used = level + 1
+        S = grid_atlas.num_submaps
+        for s in range(S):
+            sm = grid_atlas.get_submap(s)
+            if sm.fdim != 4 or fdim != 4:
+                raise NotImplementedError("fused alignment kernel is built for fdim=4 (miso.py:122 default)")
+        self._keep = []
+        fields = []
+        for s in range(S):
+            sm = grid_atlas.get_submap(s)
+            mask = sum((1 << l) for l in range(sm.num_levels) if sm.ignore_level_[l])
+            fields.append(_field.make_field(sm.level_tensors(), sm._bound_host, None, mask))
+        self.fields_dev = _structs_to_device(fields, self.device)
+        self.num_fields = S
+        P = len(self.pairs)
+        self.enabled = torch.ones(max(P, 1), dtype=torch.int32, device=self.device)
+        self.counts = torch.zeros(max(P, 1), dtype=torch.int64, device=self.device)
+        self.masks: List[Optional[torch.Tensor]] = [None] * P
+        K = 4 * self.levels_used
+        # per-src caches
+        self._coords, self._fsrc, self._verts = {}, {}, {}
+        pair_structs, isect_structs = [], []
+        self.max_M, self.max_V = 0, 0
+        for i, (src, dst) in enumerate(self.pairs):
+            assert src < S and dst < S
+            if src not in self._coords:
+                p = grid_atlas.coordinates_for_alignment(src, level)
+                if subsample_points is not None:
+                    n = min(subsample_points, p.shape[0])
+                    idx = np.random.choice(p.shape[0], n, replace=False)  # miso.py:146-149
+                    p = p[torch.from_numpy(idx).to(p.device), :]
+                p = p.detach().contiguous().float()
+                self._coords[src] = p
+                if cache_src_features and p.shape[0] > 0:
+                    sm = grid_atlas.get_submap(src)
+                    with torch.no_grad():
+                        f = sm.query_feature(p)[:, :K].contiguous()
+                    self._fsrc[src] = f
+            p = self._coords[src]
+            M = p.shape[0]
+            self.max_M = max(self.max_M, M)
+            ap = _lib.AlignPair()
+            ap.src, ap.dst, ap.levels_used = src, dst, self.levels_used
+            ap.p, ap.M = p.data_ptr() if M > 0 else None, M
+            ap.fsrc = self._fsrc[src].data_ptr() if src in self._fsrc else None
+            if want_masks:
+                self.masks[i] = torch.zeros(M, dtype=torch.uint8, device=self.device)
+                ap.mask_out = self.masks[i].data_ptr() if M > 0 else None
+            ap.enabled = self.enabled.data_ptr() + 4 * i if check_intersection else None
+            ap.src_grad_scale = 0.0
+            ap.dst_grad_scale = 0.0
+            pair_structs.append(ap)
+            if check_intersection:
+                if src not in self._verts:
+                    sm = grid_atlas.get_submap(src)
+                    self._verts[src] = sm.features[-1].vertex_positions().to(self.device).contiguous().float()
+                v = self._verts[src]
+                self.max_V = max(self.max_V, v.shape[0])
+                ip = _lib.AlignPair()
+                ip.src, ip.dst, ip.levels_used = src, dst, 0
+                ip.p, ip.M = v.data_ptr(), v.shape[0]
+                isect_structs.append(ip)
+        self.check_intersection = check_intersection
+        self.pairs_dev = _structs_to_device(pair_structs, self.device) if P else None
+        self.isect_dev = _structs_to_device(isect_structs, self.device) if (P and check_intersection) else None
+        self.src_idx = torch.tensor([s for s, _ in self.pairs], dtype=torch.long, device=self.device)
+        self.dst_idx = torch.tensor([d for _, d in self.pairs], dtype=torch.long, device=self.device)
+        self.K = K
+
+    # ---- poses ------------------------------------------------------------------------------------
+    def submap_poses(self):
+        """Batched GridAtlas.updated_submap_pose (grid_atlas.py:250-268) for all submaps."""
+        a = self.atlas
+        R0 = torch.stack(list(a.R_world_submap_list), 0)
+        t0 = torch.stack(list(a.t_world_submap_list), 0)
+        w = torch.cat(list(a.rotation_corrections), 0)
+        tau = torch.stack(list(a.translation_corrections), 0)
+        R = torch.matmul(R0, utils_geometry.so3_exp_map(w))
+        t = t0 + tau
+        return R, t
+
+    def pair_poses(self):
+        """(P,24): A1=R_s, b1=t_s, A2=R_d^T, b2=-R_d^T t_d (utils_geometry.py:214-240)."""
+        R, t = self.submap_poses()
+        A1 = R[self.src_idx]
+        b1 = t[self.src_idx]
+        A2 = R[self.dst_idx].transpose(1, 2)
+        b2 = -torch.matmul(A2, t[self.dst_idx])
+        return torch.cat([A1.reshape(-1, 9), b1.reshape(-1, 3), A2.reshape(-1, 9), b2.reshape(-1, 3)], 1)
+
+    # ---- launches -----------------------------------------------------------------------------------
+    def update_intersections(self, poses24: torch.Tensor, overlap_thresh: float = 1e-2):
+        if not self.check_intersection or not self.pairs:
+            return
+        lib = _lib.load()
+        p = poses24.detach().contiguous().float()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.miso_align_intersections(
+                self.fields_dev.data_ptr(), self.num_fields, self.isect_dev.data_ptr(), len(self.pairs), self.max_V,
+                p.data_ptr(), float(overlap_thresh), self.enabled.data_ptr(), self.counts.data_ptr(),
+                _lib.stream_ptr(self.device)), "align_intersections")
+
+    def launch(self, poses24: torch.Tensor, want_gn: bool = False) -> torch.Tensor:
+        lib = _lib.load()
+        P = len(self.pairs)
+        out = torch.empty((P, _lib.MISO_ALIGN_OUT), dtype=torch.float64, device=self.device)
+        if P == 0:
+            return out
+        p = poses24.detach().contiguous().float()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.miso_align_batch(
+                self.fields_dev.data_ptr(), self.num_fields, self.pairs_dev.data_ptr(), P, self.max_M, p.data_ptr(),
+                out.data_ptr(), int(want_gn), _lib.stream_ptr(self.device)), "align_batch")
+        return out
+
+    def losses(self, align_weight: float = 3000.0, poses24: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(P,) L2 alignment losses, differentiable w.r.t. the submap pose corrections."""
+        if poses24 is None:
+            poses24 = self.pair_poses()
+        return _AlignBatchFn.apply(poses24, self, float(align_weight))
+
+
+class _AlignBatchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, poses24, batch: AlignBatch, align_weight: float):
+        out = batch.launch(poses24)
+        S, cnt = out[:, 0], out[:, 1]
+        denom = cnt * batch.K
+        # mean((f_s - f_d)^2) * weight over M_valid x K elements; 0 when nothing is valid (miso.py:180-182,200-201)
+        scale = torch.where(cnt > 0, align_weight / denom.clamp(min=1.0), torch.zeros_like(denom))
+        loss = (S * scale).to(torch.float32)
+        ctx.save_for_backward(poses24, out, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        poses24, out, scale = ctx.saved_tensors
+        P = out.shape[0]
+        s = (scale * g.to(torch.float64)).view(P, 1, 1)
+        G0 = out[:, 2:5].reshape(P, 3, 1)
+        G1 = out[:, 5:14].reshape(P, 3, 3)
+        G2 = out[:, 14:23].reshape(P, 3, 3)
+        A2 = poses24[:, 12:21].reshape(P, 3, 3).to(torch.float64)
+        A2t = A2.transpose(1, 2)
+        dA1 = torch.matmul(A2t, G2) * s
+        db1 = torch.matmul(A2t, G0) * s
+        dA2 = G1 * s
+        db2 = G0 * s
+        grad = torch.cat([dA1.reshape(P, 9), db1.reshape(P, 3), dA2.reshape(P, 9), db2.reshape(P, 3)], 1)
+        return grad.to(poses24.dtype), None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-named entry points
+# ------------------------------------------------------------------------------------------------
+def pairwise_loss_latent(grid_atlas: GridAtlas, data_loader, src_id: int, dst_id: int, level: int, fdim=4,
+                         align_weight=3000, align_loss="L2", use_bound=True, stability_thresh=0,
+                         covariance_thresh=None, subsample_points=None, trunc_factor=None, device="cuda:0"):
+    """miso.py:116-211 for one pair.  L2 / use_bound=True (the shipped configuration,
+    configs/rgbd/scannet.yaml:56-63) runs the fused kernel; other variants are rejected loudly."""
+    loss_key = f"align_latent_level{level}_{src_id}_{dst_id}"
+    assert src_id < grid_atlas.num_submaps
+    assert dst_id < grid_atlas.num_submaps
+    if covariance_thresh is not None:
+        raise NotImplementedError
+    if align_loss != "L2" or not use_bound or stability_thresh > 0 or trunc_factor is not None:
+        raise NotImplementedError("miso_b200.pairwise_loss_latent implements align_loss='L2', use_bound=True, "
+                                  "no stability / truncation pruning (the shipped configs)")
+    batch = AlignBatch(grid_atlas, [(src_id, dst_id)], level, fdim=fdim, subsample_points=subsample_points,
+                       cache_src_features=False, check_intersection=False)
+    return {loss_key: batch.losses(align_weight)[0]}
+
+
+def relative_param_change(params_curr, params_prev=None):
+    """utils.py:507-516 without the per-iteration .item() host sync: returns a 0-dim tensor (inf first)."""
+    if params_prev is None:
+        return None
+    num_sq = 0
+    den_sq = 0
+    for c, p in zip(params_curr, params_prev):
+        num_sq = num_sq + torch.sum((c - p) ** 2)
+        den_sq = den_sq + torch.sum(p ** 2)
+    return torch.sqrt(num_sq / den_sq)
+
+
+def grid_atlas_pose_trust_region_loss(model: GridAtlas, thresh_rad, thresh_m, weight=1e3):
+    """base.py:20-27."""
+    loss_dict = {}
+    for submap_id in range(model.num_submaps):
+        rot_norm = torch.linalg.norm(model.rotation_corrections[submap_id])
+        loss_dict[f"submap{submap_id}_trust_region_R"] = weight * torch.nn.functional.relu(rot_norm - thresh_rad)
+        tran_norm = torch.linalg.norm(model.translation_corrections[submap_id])
+        loss_dict[f"submap{submap_id}_trust_region_t"] = weight * torch.nn.functional.relu(tran_norm - thresh_m)
+    return loss_dict
+
+
+def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise_loss_tuple=None, num_iters=10,
+                                   lr=1e-2, rel_change_thresh=0, submap_pairs=None, check_intersection=True,
+                                   pose_reg_weight=0, pose_thresh_rad=1.0, pose_thresh_m=1.0, verbose=True,
+                                   save_iterations=False, *, level: int = 0, align_weight=3000.0,
+                                   subsample_points=None, pair_filter=None, allreduce=None):
+    """base.py:89-163 with the pair loop replaced by one batched launch per iteration.
+
+    `pairwise_loss_tuple` is accepted for signature compatibility; the loss is the latent L2 loss at
+    `level`.  `pair_filter` / `allreduce` are the multi-GPU hooks (miso_b200.dist): a rank evaluates
+    only its share of the pairs and the per-submap pose gradients are summed across ranks before Adam.
+    Runs `num_iters + 1` iterations like the reference (`while iter <= num_iters`, base.py:127)."""
+    def pose_params():
+        params = []
+        for submap_id in range(1, grid_atlas.num_submaps):  # submap 0 stays fixed (base.py:104-108)
+            params += list(grid_atlas.params_for_submap_pose(submap_id))
+        return params
+
+    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr)
+    if submap_pairs is None:
+        submap_pairs = [(s, d) for s in range(grid_atlas.num_submaps) for d in range(s + 1, grid_atlas.num_submaps)]
+    my_pairs = list(submap_pairs) if pair_filter is None else [p for i, p in enumerate(submap_pairs) if pair_filter(i, p)]
+    batch = AlignBatch(grid_atlas, my_pairs, level, subsample_points=subsample_points,
+                       check_intersection=check_intersection)
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    iteration_results = dict()
+    params_prev = None
+    losses_hist = []
+    it = 0
+    while it <= num_iters:
+        if save_iterations:
+            R, t = batch.submap_poses()
+            T = torch.eye(4, device=R.device).repeat(R.shape[0], 1, 1)
+            T[:, :3, :3] = R.detach()
+            T[:, :3, 3:] = t.detach()
+            iteration_results[it] = T
+        optimizer.zero_grad()
+        poses24 = batch.pair_poses()
+        if check_intersection:
+            batch.update_intersections(poses24)
+        pair_losses = torch.nan_to_num(batch.losses(align_weight, poses24))  # base.py:139-141
+        total_loss = pair_losses.sum()
+        if pose_reg_weight > 0:
+            reg = grid_atlas_pose_trust_region_loss(grid_atlas, thresh_rad=pose_thresh_rad, thresh_m=pose_thresh_m,
+                                                    weight=pose_reg_weight)
+            total_loss = total_loss + sum(reg.values())
+        total_loss.backward()
+        if allreduce is not None:
+            allreduce([p.grad for p in pose_params() if p.grad is not None])
+        optimizer.step()
+        losses_hist.append(total_loss.detach())
+        params_curr = [p.clone().detach() for p in pose_params()]
+        relchange = relative_param_change(params_curr, params_prev)
+        params_prev = params_curr
+        if rel_change_thresh > 0 and relchange is not None and float(relchange) < rel_change_thresh:
+            break
+        it += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    info = {"cpu_time_sec": time.perf_counter() - t0, "gpu_time_sec": ev0.elapsed_time(ev1) / 1e3,
+            "iteration_results": iteration_results, "losses": torch.stack(losses_hist).cpu() if losses_hist else None,
+            "iterations": it if it <= num_iters else num_iters + 1}
+    return info
+
+
+def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, level_iters=10, finetune_iters=10,
+                                        level_thresh=0.0, lr=1e-2, align_weight=3000, align_loss="L2",
+                                        use_bound=True, stability_thresh=0, subsample_points=None,
+                                        latent_levels=None, skip_finetune=False, submap_pairs=None,
+                                        pose_reg_weight=0, pose_thresh_m=1.0, pose_thresh_rad=1.0, gm_scale_sdf=0.1,
+                                        device="cuda:0", verbose=True, save_iterations=False, pair_filter=None,
+                                        allreduce=None):
+    """miso.py:217-322.  The SDF-space fine-tune (pairwise_loss_sdf) is off in the shipped configs
+    (skip_finetune: True, scannet.yaml:63) and is not part of this path."""
+    if align_loss != "L2" or not use_bound or stability_thresh > 0:
+        raise NotImplementedError("fused alignment implements align_loss='L2', use_bound=True, stability_thresh=0")
+    if not skip_finetune:
+        raise NotImplementedError("SDF-space fine-tune (pairwise_loss_sdf) is outside the fused path; "
+                                  "pass skip_finetune=True as the shipped configs do")
+    grid_atlas.precompute_coordinates_for_alignment()
+    info = dict()
+    cpu_total, gpu_total = 0.0, 0.0
+    if latent_levels is None:
+        latent_levels = range(grid_atlas.num_levels)
+    for curr_level in latent_levels:
+        loss_name = f"hier_latent_level{curr_level}_{align_loss}"
+        level_dict = generic_align_multiple_submaps(
+            grid_atlas, dataset, (loss_name, None), num_iters=level_iters, rel_change_thresh=level_thresh, lr=lr,
+            submap_pairs=submap_pairs, pose_reg_weight=pose_reg_weight, pose_thresh_m=pose_thresh_m,
+            pose_thresh_rad=pose_thresh_rad, verbose=verbose, save_iterations=save_iterations, level=curr_level,
+            align_weight=align_weight, subsample_points=subsample_points, pair_filter=pair_filter,
+            allreduce=allreduce)
+        cpu_total += level_dict["cpu_time_sec"]
+        gpu_total += level_dict["gpu_time_sec"]
+        info[loss_name] = level_dict
+    info["cpu_time_sec"] = cpu_total
+    info["gpu_time_sec"] = gpu_total
+    return info
+
+
+def gauss_newton_dst_step(batch: AlignBatch, lm_lambda: float = 1e-4):
+    """Explicit 6-DoF normal equations of the latent residual w.r.t. a right-multiplied twist of each
+    pair's DST pose (conventions of Tracker.lm_step, grid_opt/slam/tracker.py:179-197):
+    H = J^T J + lambda I, g = J^T r, delta = solve(H, -g).  Returns (delta (P,6), H (P,6,6), g (P,6))."""
+    out = batch.launch(batch.pair_poses(), want_gn=True)
+    P = out.shape[0]
+    g = out[:, 24:30]
+    Hm = out[:, 30:66].reshape(P, 6, 6) + lm_lambda * torch.eye(6, dtype=out.dtype, device=out.device)
+    delta = torch.linalg.solve(Hm, -g.unsqueeze(-1)).squeeze(-1)
+    return delta, Hm, g

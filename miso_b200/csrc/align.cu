@@ -1,0 +1,348 @@
+// Latent-space submap alignment: transform + in-bound mask + dual interpolation + residual +
+// pose-gradient / Gauss-Newton reductions, batched over every submap pair of an iteration.
+//
+// Replaces the body of pairwise_loss_latent (grid_opt/align/miso.py:116-211) and its autograd
+// backward, called per pair per iteration from generic_align_multiple_submaps
+// (grid_opt/align/base.py:127-159), plus check_submap_intersection (grid_opt/models/grid_atlas.py:405-420).
+//
+// The reference materialises coords_world, coords_to, the mask, nonzero indices, two (M,8) feature
+// matrices and their autograd graph per pair (>=20 launches and ~1 KB/point of HBM traffic); here a
+// point costs 12 B of coordinates + its corner fetches, and everything else stays in registers until
+// the block-level reduction (float partials -> float64 atomics, 24 or 51 values per pair).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace miso {
+
+constexpr int kAlignAcc = 24;       // S, count, G0(3), G1(9), G2(9), sum|r|
+constexpr int kGnAcc = 27;          // Jtr(6) + upper triangle of JtJ(21)
+
+struct Pose24 {
+  float A1[9], b1[3], A2[9], b2[3];
+};
+
+__device__ __forceinline__ void load_pose(const float* __restrict__ poses, int pair, Pose24& P) {
+  const float* s = poses + (int64_t)pair * 24;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P.A1[i] = s[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P.b1[i] = s[9 + i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P.A2[i] = s[12 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P.b2[i] = s[21 + i];
+}
+
+// y = x A^T + b^T evaluated like torch's (N,3)@(3,3) + (1,3): products summed left to right
+__device__ __forceinline__ void xform(const float (&A)[9], const float (&b)[3], const float (&x)[3], float (&y)[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float s = __fmul_rn(x[0], A[3 * j]);
+    s = __fmaf_rn(x[1], A[3 * j + 1], s);
+    s = __fmaf_rn(x[2], A[3 * j + 2], s);
+    y[j] = __fadd_rn(s, b[j]);
+  }
+}
+
+__device__ __forceinline__ bool in_bound(const float (&q)[3], const float* bound) {
+  // coords_in_bound (utils_geometry.py:21-23): inclusive on both sides
+  return q[0] >= bound[0] && q[0] <= bound[1] && q[1] >= bound[2] && q[1] <= bound[3] && q[2] >= bound[4] &&
+         q[2] <= bound[5];
+}
+
+template <int C>
+__device__ __forceinline__ void gather4(const miso_level_t& lv, const Cell& c, float* f, float* dx, float* dy,
+                                        float* dz, bool deriv) {
+  float w[8], wdx[8], wdy[8], wdz[8];
+  long long off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float wx, wy, wz;
+    axis_w(c, k, wx, wy, wz);
+    bool ok = (c.valid >> k) & 1u;
+    float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
+    w[k] = ok ? (wx * wy) * wz : 0.f;
+    wdx[k] = ok ? sx * wy * wz : 0.f;
+    wdy[k] = ok ? wx * sy * wz : 0.f;
+    wdz[k] = ok ? wx * wy * sz : 0.f;
+    off[k] = ok ? corner_off(lv, c, k) : 0;
+  }
+#pragma unroll
+  for (int ch = 0; ch < C; ch += 4) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ldg_f4(lv.feat + off[k] + ch);
+    float a[4] = {0, 0, 0, 0}, ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float vv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a[e] = fmaf(vv[e], w[k], a[e]);
+        if (deriv) {
+          ax[e] = fmaf(vv[e], wdx[k], ax[e]);
+          ay[e] = fmaf(vv[e], wdy[k], ay[e]);
+          az[e] = fmaf(vv[e], wdz[k], az[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[ch + e] = a[e];
+      if (deriv) dx[ch + e] = ax[e], dy[ch + e] = ay[e], dz[ch + e] = az[e];
+    }
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void scatter4(const miso_level_t& lv, const Cell& c, float coef, const float* r) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (!((c.valid >> k) & 1u)) continue;
+    float wx, wy, wz;
+    axis_w(c, k, wx, wy, wz);
+    float w = coef * ((wx * wy) * wz);
+    float* dst = lv.grad + corner_off(lv, c, k);
+#pragma unroll
+    for (int ch = 0; ch < C; ch += 4) red_add_f4(dst + ch, w * r[ch], w * r[ch + 1], w * r[ch + 2], w * r[ch + 3]);
+  }
+}
+
+template <int C, bool kGN>
+__global__ void __launch_bounds__(kThreads)
+    align_batch_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
+                       const float* __restrict__ poses, double* __restrict__ out) {
+  constexpr int NACC = kAlignAcc + (kGN ? kGnAcc : 0);
+  __shared__ float red[NACC][kThreads / 32];
+  const int pi = blockIdx.y;
+  const miso_align_pair_t pr = pairs[pi];
+  if (pr.enabled && *pr.enabled == 0) return;
+  if (pr.M <= 0) return;
+  const miso_field_t& src = fields[pr.src];
+  const miso_field_t& dst = fields[pr.dst];
+  Pose24 P;
+  load_pose(poses, pi, P);
+  float dbound[6], sbmin[3], sbmax[3], dbmin[3], dbmax[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dbound[i] = dst.bound[i];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    sbmin[d] = src.bound[2 * d], sbmax[d] = src.bound[2 * d + 1];
+    dbmin[d] = dst.bound[2 * d], dbmax[d] = dst.bound[2 * d + 1];
+  }
+  const int LU = pr.levels_used;
+  const int K = LU * C;
+
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < pr.M; n += (int64_t)gridDim.x * blockDim.x) {
+    float p[3] = {pr.p[3 * n], pr.p[3 * n + 1], pr.p[3 * n + 2]};
+    float u[3], q[3];
+    xform(P.A1, P.b1, p, u);
+    xform(P.A2, P.b2, u, q);
+    const bool ok = in_bound(q, dbound);
+    if (pr.mask_out) pr.mask_out[n] = ok ? 1 : 0;
+    if (!ok) continue;
+    float pn[3], qn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      pn[d] = normalize_coord(p[d], sbmin[d], sbmax[d]);
+      qn[d] = normalize_coord(q[d], dbmin[d], dbmax[d]);
+    }
+    float gam[3] = {0.f, 0.f, 0.f};
+    float rr = 0.f;
+    for (int l = 0; l < LU; ++l) {
+      float fs[C], fd[C], dx[C], dy[C], dz[C];
+      const miso_level_t& sl = src.level[l];
+      const miso_level_t& dl = dst.level[l];
+      Cell cs;
+      const bool src_ignored = (src.ignore_mask >> l) & 1u;
+      const bool dst_ignored = (dst.ignore_mask >> l) & 1u;
+      if (pr.fsrc) {
+#pragma unroll
+        for (int ch = 0; ch < C; ch += 4) {
+          float4 t = *reinterpret_cast<const float4*>(pr.fsrc + n * K + l * C + ch);
+          fs[ch] = t.x, fs[ch + 1] = t.y, fs[ch + 2] = t.z, fs[ch + 3] = t.w;
+        }
+        if (sl.grad) cs = make_cell(unnormalize_nc(pn[0], sl.X), unnormalize_nc(pn[1], sl.Y), unnormalize_nc(pn[2], sl.Z), sl);
+      } else if (src_ignored) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) fs[ch] = 0.f;
+      } else {
+        cs = make_cell(unnormalize_nc(pn[0], sl.X), unnormalize_nc(pn[1], sl.Y), unnormalize_nc(pn[2], sl.Z), sl);
+        gather4<C>(sl, cs, fs, nullptr, nullptr, nullptr, false);
+      }
+      Cell cd = make_cell(unnormalize_nc(qn[0], dl.X), unnormalize_nc(qn[1], dl.Y), unnormalize_nc(qn[2], dl.Z), dl);
+      if (dst_ignored) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) fd[ch] = dx[ch] = dy[ch] = dz[ch] = 0.f;
+      } else {
+        gather4<C>(dl, cd, fd, dx, dy, dz, true);
+      }
+      const float kx = (float)dl.X / (dbmax[0] - dbmin[0]), ky = (float)dl.Y / (dbmax[1] - dbmin[1]),
+                  kz = (float)dl.Z / (dbmax[2] - dbmin[2]);
+      float r[C];
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        r[ch] = fs[ch] - fd[ch];
+        rr = fmaf(r[ch], r[ch], rr);
+        const float gx = dx[ch] * kx, gy = dy[ch] * ky, gz = dz[ch] * kz;  // grad_q f_d,ch
+        gam[0] = fmaf(-2.f * r[ch], gx, gam[0]);
+        gam[1] = fmaf(-2.f * r[ch], gy, gam[1]);
+        gam[2] = fmaf(-2.f * r[ch], gz, gam[2]);
+        if constexpr (kGN) {
+          // J row (1x6) of r_ch wrt a right-multiplied dst twist: [ (q x g)^T , (R_d g)^T ],  R_d = A2^T
+          float Jr[6];
+          Jr[0] = q[1] * gz - q[2] * gy;
+          Jr[1] = q[2] * gx - q[0] * gz;
+          Jr[2] = q[0] * gy - q[1] * gx;
+          Jr[3] = P.A2[0] * gx + P.A2[3] * gy + P.A2[6] * gz;
+          Jr[4] = P.A2[1] * gx + P.A2[4] * gy + P.A2[7] * gz;
+          Jr[5] = P.A2[2] * gx + P.A2[5] * gy + P.A2[8] * gz;
+          int t = kAlignAcc + 6;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            acc[kAlignAcc + a] = fmaf(Jr[a], r[ch], acc[kAlignAcc + a]);
+#pragma unroll
+            for (int b = a; b < 6; ++b) {
+              acc[t] = fmaf(Jr[a], Jr[b], acc[t]);
+              ++t;
+            }
+          }
+        }
+      }
+      // optional dS/dfeature scatter (the reference back-propagates into both submaps' grids)
+      if (sl.grad && !src_ignored && pr.src_grad_scale != 0.f) scatter4<C>(sl, cs, 2.f * pr.src_grad_scale, r);
+      if (dl.grad && !dst_ignored && pr.dst_grad_scale != 0.f) scatter4<C>(dl, cd, -2.f * pr.dst_grad_scale, r);
+    }
+    acc[0] += rr;
+    acc[1] += 1.f;
+    acc[23] += sqrtf(rr);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      acc[2 + i] += gam[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc[5 + 3 * i + j] = fmaf(gam[i], u[j], acc[5 + 3 * i + j]);
+        acc[14 + 3 * i + j] = fmaf(gam[i], p[j], acc[14 + 3 * i + j]);
+      }
+    }
+  }
+  // block reduction, then one float64 atomic per value per block
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[i][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) s += (double)red[threadIdx.x][k];
+    double* o = out + (int64_t)pi * MISO_ALIGN_OUT;
+    int idx = threadIdx.x;
+    if (idx < kAlignAcc) {
+      if (s != 0.0) atomicAdd(o + idx, s);
+    } else if (idx < kAlignAcc + 6) {
+      if (s != 0.0) atomicAdd(o + idx, s);  // Jtr at [24..29]
+    } else {
+      // upper-triangle entry t -> (a,b); mirror into the full 6x6 at [30..65]
+      int t = idx - (kAlignAcc + 6), a = 0;
+      while (t >= 6 - a) {
+        t -= 6 - a;
+        ++a;
+      }
+      int b = a + t;
+      if (s != 0.0) {
+        atomicAdd(o + 30 + a * 6 + b, s);
+        if (a != b) atomicAdd(o + 30 + b * 6 + a, s);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    align_intersection_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
+                              const float* __restrict__ poses, unsigned long long* __restrict__ counts) {
+  const int pi = blockIdx.y;
+  const miso_align_pair_t pr = pairs[pi];
+  if (pr.M <= 0) return;
+  const miso_field_t& dst = fields[pr.dst];
+  Pose24 P;
+  load_pose(poses, pi, P);
+  float dbound[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dbound[i] = dst.bound[i];
+  unsigned cnt = 0;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < pr.M; n += (int64_t)gridDim.x * blockDim.x) {
+    float p[3] = {pr.p[3 * n], pr.p[3 * n + 1], pr.p[3 * n + 2]};
+    float u[3], q[3];
+    xform(P.A1, P.b1, p, u);
+    xform(P.A2, P.b2, u, q);
+    cnt += in_bound(q, dbound) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(counts + pi, (unsigned long long)cnt);
+}
+
+__global__ void align_intersection_finalize(const miso_align_pair_t* __restrict__ pairs, int num_pairs,
+                                            const unsigned long long* __restrict__ counts, float thresh,
+                                            int32_t* __restrict__ enabled) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_pairs) return;
+  // overlap_percentage = num_valid / num_all (float32 division of int64 tensors in torch) > thresh
+  const int64_t M = pairs[i].M;
+  float frac = M > 0 ? (float)counts[i] / (float)M : 0.f;
+  enabled[i] = frac > thresh ? 1 : 0;
+}
+
+}  // namespace miso
+
+using namespace miso;
+
+extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
+                                int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t want_gn,
+                                miso_stream_t stream) {
+  MISO_REQUIRE(fields && pairs && poses && out, "align_batch: null argument");
+  MISO_REQUIRE(num_fields > 0 && num_pairs >= 0, "align_batch: bad counts");
+  if (num_pairs == 0) return MISO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double) * MISO_ALIGN_OUT * num_pairs, s);
+  if (max_M <= 0) return check_launch("align_batch(memset)");
+  MISO_REQUIRE(num_pairs <= 65535, "align_batch: too many pairs (%d)", num_pairs);
+  // channel count is read on the host from nothing (fields live on the device): the ABI fixes C=4
+  // per level for alignment (fdim=4, miso.py:122); other widths go through the generic path.
+  int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_pairs, sm_count() * 8))));
+  dim3 grid(bx, num_pairs);
+  if (want_gn)
+    align_batch_kernel<4, true><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+  else
+    align_batch_kernel<4, false><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+  return check_launch("align_batch");
+}
+
+extern "C" int miso_align_intersections(const miso_field_t* fields, int32_t num_fields,
+                                        const miso_align_pair_t* pairs, int32_t num_pairs, int64_t max_M,
+                                        const float* poses, float overlap_thresh, int32_t* enabled_out,
+                                        unsigned long long* counts_out, miso_stream_t stream) {
+  MISO_REQUIRE(fields && pairs && poses && enabled_out && counts_out, "align_intersections: null argument");
+  MISO_REQUIRE(num_fields > 0 && num_pairs >= 0 && num_pairs <= 65535, "align_intersections: bad counts");
+  if (num_pairs == 0) return MISO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(counts_out, 0, sizeof(unsigned long long) * num_pairs, s);
+  if (max_M > 0) {
+    int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_pairs, sm_count() * 8))));
+    dim3 grid(bx, num_pairs);
+    align_intersection_kernel<<<grid, kThreads, 0, s>>>(fields, pairs, poses, counts_out);
+  }
+  align_intersection_finalize<<<(num_pairs + 127) / 128, 128, 0, s>>>(pairs, num_pairs, counts_out, overlap_thresh,
+                                                                       enabled_out);
+  return check_launch("align_intersections");
+}

@@ -1,0 +1,772 @@
+// Fused multiresolution-grid + MLP-decoder kernels: per-point features never touch HBM.
+//
+// Replaces the chain
+//   normalize_coordinates (utils.py:22-51) -> FeatureGrid.interpolate per level (grid_modules.py:72-95)
+//   -> torch.cat (utils.py:164) -> MLPNet.forward (modules.py:31-32) -> gradient3d (diff.py:14-38)
+//   -> miso_loss_regression / miso_loss_free_space / miso_loss_eikonal (loss.py:594-700)
+//   -> autograd backward through aten::grid_sampler_3d_backward and grid_sampler_3d_grad2_kernel.
+//
+// Math: with J = d sdf/d feat = W3 D2 W2 D1 W1 (ReLU masks D), and because
+// d2relu = 0 a.e., both the first-order loss gradient and the eikonal double-backward reduce to ONE
+// scatter per corner:   grad_l[corner] += (a * w_c + v . dw_c/dx) * J_l
+// with a = dL/dsdf and v = dL/d(grad_x sdf).
+//
+// SIMT design for sm_100a: one thread per point, decoder weights staged once per CTA in shared
+// memory and read as warp-uniform 128-bit broadcasts, all MLP math as packed FFMA2 (fma.rn.f32x2),
+// corner fetches as 128-bit read-only loads from the channels-last grid, scatter as 128-bit
+// red.global.add.v4.f32.  Persistent CTAs (grid = SMs x occupancy) loop over 256-point tiles.
+#include "common.cuh"
+
+namespace miso {
+
+constexpr int H = 64;  // decoder hidden_dim (configs/rgbd/scannet.yaml:12, configs/lidar/ncd_quad.yaml:11)
+
+template <int F>
+struct DecoderSmem {
+  float W1[H * F];  // [k][i]
+  float W2[H * H];  // [j][k]
+  float b1[H];
+  float b2[H];
+  float W3[H];
+  float b3[4];
+};
+
+template <int F>
+__device__ __forceinline__ void load_decoder(DecoderSmem<F>* s, const miso_decoder_t& d) {
+  for (int i = threadIdx.x; i < H * F; i += blockDim.x) s->W1[i] = d.W1[i];
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) s->W2[i] = d.W2[i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    s->b1[i] = d.b1[i];
+    s->b2[i] = d.b2[i];
+    s->W3[i] = d.W3[i];
+  }
+  if (threadIdx.x == 0) s->b3[0] = d.b3[0];
+  __syncthreads();
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// MLP forward + Jacobian wrt input.  f: F inputs.  Returns sdf; J[F] = d sdf / d f.
+template <int F, bool kJac>
+__device__ __forceinline__ float mlp_eval(const DecoderSmem<F>* s, const float (&f)[F], float (&J)[F]) {
+  static_assert(F % 4 == 0, "F must be a multiple of 4");
+  float2 fp[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) fp[i] = make_float2(f[2 * i], f[2 * i + 1]);
+
+  // ---- layer 1: h1 = relu(W1 f + b1), kept as 32 packed pairs --------------------------------
+  float2 h1[H / 2];
+  unsigned m1lo = 0, m1hi = 0;
+#pragma unroll
+  for (int kp = 0; kp < H / 2; ++kp) {
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+    const float4* r0 = reinterpret_cast<const float4*>(s->W1 + (2 * kp) * F);
+    const float4* r1 = reinterpret_cast<const float4*>(s->W1 + (2 * kp + 1) * F);
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      float4 w0 = r0[q], w1 = r1[q];
+      a0 = ffma2(make_float2(w0.x, w0.y), fp[2 * q], a0);
+      a0 = ffma2(make_float2(w0.z, w0.w), fp[2 * q + 1], a0);
+      a1 = ffma2(make_float2(w1.x, w1.y), fp[2 * q], a1);
+      a1 = ffma2(make_float2(w1.z, w1.w), fp[2 * q + 1], a1);
+    }
+    float2 bb = *reinterpret_cast<const float2*>(s->b1 + 2 * kp);
+    float x0 = (a0.x + a0.y) + bb.x, x1 = (a1.x + a1.y) + bb.y;
+    unsigned p0 = x0 > 0.f, p1 = x1 > 0.f;
+    if (kp < 16) m1lo |= (p0 << (2 * kp)) | (p1 << (2 * kp + 1));
+    else m1hi |= (p0 << (2 * kp - 32)) | (p1 << (2 * kp - 31));
+    h1[kp] = make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  }
+
+  // ---- layer 2 + 3 forward: sdf = W3 relu(W2 h1 + b2) + b3 ------------------------------------
+  float sdf = s->b3[0];
+  unsigned m2lo = 0, m2hi = 0;
+#pragma unroll 1
+  for (int j = 0; j < H; j += 4) {
+    float2 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < H / 4; ++q) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float4 w = reinterpret_cast<const float4*>(s->W2 + (j + r) * H)[q];
+        acc[r] = ffma2(make_float2(w.x, w.y), h1[2 * q], acc[r]);
+        acc[r] = ffma2(make_float2(w.z, w.w), h1[2 * q + 1], acc[r]);
+      }
+    }
+    float4 b2v = *reinterpret_cast<const float4*>(s->b2 + j);
+    float4 w3v = *reinterpret_cast<const float4*>(s->W3 + j);
+    float hb[4] = {b2v.x, b2v.y, b2v.z, b2v.w};
+    float hw[4] = {w3v.x, w3v.y, w3v.z, w3v.w};
+    unsigned bits = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float h2 = (acc[r].x + acc[r].y) + hb[r];
+      bits |= (h2 > 0.f ? 1u : 0u) << r;
+      sdf = fmaf(hw[r], fmaxf(h2, 0.f), sdf);
+    }
+    if (j < 32) m2lo |= bits << j;
+    else m2hi |= bits << (j - 32);
+  }
+  if constexpr (!kJac) return sdf;
+
+  // ---- backward for J: g1 = D1 W2^T D2 W3^T ; J = W1^T g1 -------------------------------------
+  float2 g1[H / 2];
+#pragma unroll
+  for (int kp = 0; kp < H / 2; ++kp) g1[kp] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int j = 0; j < H; j += 2) {
+    unsigned word = (j < 32) ? m2lo : m2hi;
+    unsigned sh = j & 31;
+    float2 w3 = *reinterpret_cast<const float2*>(s->W3 + j);
+    float t0 = ((word >> sh) & 1u) ? w3.x : 0.f;
+    float t1 = ((word >> (sh + 1)) & 1u) ? w3.y : 0.f;
+    float2 tt0 = make_float2(t0, t0), tt1 = make_float2(t1, t1);
+#pragma unroll
+    for (int q = 0; q < H / 4; ++q) {
+      float4 w0 = reinterpret_cast<const float4*>(s->W2 + j * H)[q];
+      float4 w1 = reinterpret_cast<const float4*>(s->W2 + (j + 1) * H)[q];
+      g1[2 * q] = ffma2(make_float2(w0.x, w0.y), tt0, g1[2 * q]);
+      g1[2 * q + 1] = ffma2(make_float2(w0.z, w0.w), tt0, g1[2 * q + 1]);
+      g1[2 * q] = ffma2(make_float2(w1.x, w1.y), tt1, g1[2 * q]);
+      g1[2 * q + 1] = ffma2(make_float2(w1.z, w1.w), tt1, g1[2 * q + 1]);
+    }
+  }
+  // compiler barrier: without it nvcc CSEs these W1 reads with layer 1's and keeps 64*F weights
+  // alive across the whole MLP (2.5 KB of local-memory spills per thread)
+  asm volatile("" ::: "memory");
+  float2 Jp[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) Jp[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int kp = 0; kp < H / 2; ++kp) {
+    unsigned word = (kp < 16) ? m1lo : m1hi;
+    unsigned sh = (2 * kp) & 31;
+    float e0 = ((word >> sh) & 1u) ? g1[kp].x : 0.f;
+    float e1 = ((word >> (sh + 1)) & 1u) ? g1[kp].y : 0.f;
+    float2 ee0 = make_float2(e0, e0), ee1 = make_float2(e1, e1);
+    const float4* r0 = reinterpret_cast<const float4*>(s->W1 + (2 * kp) * F);
+    const float4* r1 = reinterpret_cast<const float4*>(s->W1 + (2 * kp + 1) * F);
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      float4 w0 = r0[q], w1 = r1[q];
+      Jp[2 * q] = ffma2(make_float2(w0.x, w0.y), ee0, Jp[2 * q]);
+      Jp[2 * q + 1] = ffma2(make_float2(w0.z, w0.w), ee0, Jp[2 * q + 1]);
+      Jp[2 * q] = ffma2(make_float2(w1.x, w1.y), ee1, Jp[2 * q]);
+      Jp[2 * q + 1] = ffma2(make_float2(w1.z, w1.w), ee1, Jp[2 * q + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) {
+    J[2 * i] = Jp[i].x;
+    J[2 * i + 1] = Jp[i].y;
+  }
+  return sdf;
+}
+
+// ---- per-point geometry -------------------------------------------------------------------------
+struct FieldGeom {
+  float bmin[3], bmax[3];
+  float inv_len[3];  // 1/(bmax-bmin)
+};
+
+__device__ __forceinline__ FieldGeom field_geom(const miso_field_t& fl) {
+  FieldGeom g;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    g.bmin[d] = fl.bound[2 * d];
+    g.bmax[d] = fl.bound[2 * d + 1];
+    g.inv_len[d] = 1.0f / (g.bmax[d] - g.bmin[d]);
+  }
+  return g;
+}
+
+__device__ __forceinline__ void load_point(const float* __restrict__ x, const miso_frames_t& fr, int64_t n,
+                                           float (&p)[3]) {
+  float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
+  if (fr.ids) {
+    // transform_points_to (utils_geometry.py:214-225): x R^T + t^T, pose picked per sample (loss.py:764-774)
+    int64_t id = fr.ids[n];
+    if (id < 0 || id >= fr.num_frames) id = 0;
+    const float* R = fr.R + id * 9;
+    const float* t = fr.t + id * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p[j] = fmaf(c, R[3 * j + 2], fmaf(b, R[3 * j + 1], a * R[3 * j])) + t[j];
+  } else {
+    p[0] = a, p[1] = b, p[2] = c;
+  }
+}
+
+__device__ __forceinline__ Cell level_cell(const miso_level_t& lv, const float (&xn)[3]) {
+  return make_cell(unnormalize_nc(xn[0], lv.X), unnormalize_nc(xn[1], lv.Y), unnormalize_nc(xn[2], lv.Z), lv);
+}
+
+// Gather C channels of one level: features f[C] and index-space derivatives d[3][C].
+template <int C, bool kDeriv>
+__device__ __forceinline__ void gather_level(const miso_level_t& lv, const Cell& c, float* __restrict__ f,
+                                             float* __restrict__ dfx, float* __restrict__ dfy,
+                                             float* __restrict__ dfz) {
+  float w[8];
+  long long off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float wx, wy, wz;
+    axis_w(c, k, wx, wy, wz);
+    bool ok = (c.valid >> k) & 1u;
+    w[k] = ok ? (wx * wy) * wz : 0.f;
+    off[k] = ok ? corner_off(lv, c, k) : 0;
+  }
+#pragma unroll
+  for (int ch = 0; ch < C; ch += 4) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ldg_f4(lv.feat + off[k] + ch);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc.x = fmaf(v[k].x, w[k], acc.x);
+      acc.y = fmaf(v[k].y, w[k], acc.y);
+      acc.z = fmaf(v[k].z, w[k], acc.z);
+      acc.w = fmaf(v[k].w, w[k], acc.w);
+    }
+    f[ch] = acc.x, f[ch + 1] = acc.y, f[ch + 2] = acc.z, f[ch + 3] = acc.w;
+    if constexpr (kDeriv) {
+      float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ay = ax, az = ax;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float wx, wy, wz;
+        axis_w(c, k, wx, wy, wz);
+        bool ok = (c.valid >> k) & 1u;
+        float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
+        float wdx = ok ? sx * wy * wz : 0.f, wdy = ok ? wx * sy * wz : 0.f, wdz = ok ? wx * wy * sz : 0.f;
+        ax.x = fmaf(v[k].x, wdx, ax.x), ax.y = fmaf(v[k].y, wdx, ax.y), ax.z = fmaf(v[k].z, wdx, ax.z), ax.w = fmaf(v[k].w, wdx, ax.w);
+        ay.x = fmaf(v[k].x, wdy, ay.x), ay.y = fmaf(v[k].y, wdy, ay.y), ay.z = fmaf(v[k].z, wdy, ay.z), ay.w = fmaf(v[k].w, wdy, ay.w);
+        az.x = fmaf(v[k].x, wdz, az.x), az.y = fmaf(v[k].y, wdz, az.y), az.z = fmaf(v[k].z, wdz, az.z), az.w = fmaf(v[k].w, wdz, az.w);
+      }
+      dfx[ch] = ax.x, dfx[ch + 1] = ax.y, dfx[ch + 2] = ax.z, dfx[ch + 3] = ax.w;
+      dfy[ch] = ay.x, dfy[ch + 1] = ay.y, dfy[ch + 2] = ay.z, dfy[ch + 3] = ay.w;
+      dfz[ch] = az.x, dfz[ch + 1] = az.y, dfz[ch + 2] = az.z, dfz[ch + 3] = az.w;
+    }
+  }
+}
+
+// Scatter (a*w_c + vi . dw_c/di) * J into one level's gradient buffer; vi is in index space.
+template <int C>
+__device__ __forceinline__ void scatter_level(const miso_level_t& lv, const Cell& c, float a, float vix, float viy,
+                                              float viz, const float* __restrict__ J) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (!((c.valid >> k) & 1u)) continue;
+    float wx, wy, wz;
+    axis_w(c, k, wx, wy, wz);
+    float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
+    float coef = a * ((wx * wy) * wz) + vix * (sx * wy * wz) + viy * (wx * sy * wz) + viz * (wx * wy * sz);
+    float* dst = lv.grad + corner_off(lv, c, k);
+#pragma unroll
+    for (int ch = 0; ch < C; ch += 4)
+      red_add_f4(dst + ch, coef * J[ch], coef * J[ch + 1], coef * J[ch + 2], coef * J[ch + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: features only (grid_interp_regular)
+// ---------------------------------------------------------------------------------------------
+template <int L, int C>
+__global__ void __launch_bounds__(kThreads) field_features_kernel(const __grid_constant__ miso_field_t fl,
+                                                                  const float* __restrict__ x, int64_t N,
+                                                                  float* __restrict__ feats) {
+  const FieldGeom g = field_geom(fl);
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float xn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(x[3 * n + d], g.bmin[d], g.bmax[d]);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      float f[C];
+      if ((fl.ignore_mask >> l) & 1u) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[i] = 0.f;
+      } else {
+        Cell c = level_cell(fl.level[l], xn);
+        gather_level<C, false>(fl.level[l], c, f, nullptr, nullptr, nullptr);
+      }
+#pragma unroll
+      for (int ch = 0; ch < C; ch += 4)
+        *reinterpret_cast<float4*>(feats + n * (L * C) + l * C + ch) = make_float4(f[ch], f[ch + 1], f[ch + 2], f[ch + 3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: fused forward (sdf, jac, gradx)
+// ---------------------------------------------------------------------------------------------
+template <int L, int C, bool kJac>
+__global__ void __launch_bounds__(kThreads)
+    sdf_forward_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
+                       const __grid_constant__ miso_frames_t fr, const float* __restrict__ x, int64_t N,
+                       float* __restrict__ sdf, float* __restrict__ jac, float* __restrict__ gradx,
+                       float* __restrict__ xw) {
+  constexpr int F = L * C;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecoderSmem<F>* s = reinterpret_cast<DecoderSmem<F>*>(smem_raw);
+  load_decoder<F>(s, dec);
+  const FieldGeom g = field_geom(fl);
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float p[3], xn[3];
+    load_point(x, fr, n, p);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
+    float f[F], dfx[F], dfy[F], dfz[F];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if ((fl.ignore_mask >> l) & 1u) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
+      } else {
+        Cell c = level_cell(fl.level[l], xn);
+        gather_level<C, kJac>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+        if constexpr (kJac) {
+          // chain d(index)/dx = S/len (ATen gi*_mult = S/2 times normalize's 2/len)
+          float kx = (float)fl.level[l].X * g.inv_len[0], ky = (float)fl.level[l].Y * g.inv_len[1],
+                kz = (float)fl.level[l].Z * g.inv_len[2];
+#pragma unroll
+          for (int i = 0; i < C; ++i) dfx[l * C + i] *= kx, dfy[l * C + i] *= ky, dfz[l * C + i] *= kz;
+        }
+      }
+    }
+    float J[F];
+    float val = mlp_eval<F, kJac>(s, f, J);
+    sdf[n] = val;
+    if (xw) xw[3 * n] = p[0], xw[3 * n + 1] = p[1], xw[3 * n + 2] = p[2];
+    if constexpr (kJac) {
+      if (jac) {
+#pragma unroll
+        for (int i = 0; i < F; i += 4) *reinterpret_cast<float4*>(jac + n * F + i) = make_float4(J[i], J[i + 1], J[i + 2], J[i + 3]);
+      }
+      if (gradx) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int i = 0; i < F; ++i) gx = fmaf(J[i], dfx[i], gx), gy = fmaf(J[i], dfy[i], gy), gz = fmaf(J[i], dfz[i], gz);
+        gradx[3 * n] = gx, gradx[3 * n + 1] = gy, gradx[3 * n + 2] = gz;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: scatter backward given per-point J, a, v  (+ optional Hessian-vector product wrt x)
+// ---------------------------------------------------------------------------------------------
+template <int L, int C>
+__global__ void __launch_bounds__(kThreads)
+    sdf_backward_kernel(const __grid_constant__ miso_field_t fl, const float* __restrict__ xw, int64_t N,
+                        const float* __restrict__ jac, const float* __restrict__ a, const float* __restrict__ v,
+                        float* __restrict__ hv) {
+  constexpr int F = L * C;
+  const FieldGeom g = field_geom(fl);
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float av = a ? a[n] : 0.f;
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    if (v) vx = v[3 * n], vy = v[3 * n + 1], vz = v[3 * n + 2];
+    const bool nothing = av == 0.f && vx == 0.f && vy == 0.f && vz == 0.f;
+    if (nothing) {
+      if (hv) hv[3 * n] = 0.f, hv[3 * n + 1] = 0.f, hv[3 * n + 2] = 0.f;
+      continue;
+    }
+    float xn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(xw[3 * n + d], g.bmin[d], g.bmax[d]);
+    float J[F];
+#pragma unroll
+    for (int i = 0; i < F; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(jac + n * F + i);
+      J[i] = t.x, J[i + 1] = t.y, J[i + 2] = t.z, J[i + 3] = t.w;
+    }
+    float hx = 0.f, hy = 0.f, hz = 0.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if ((fl.ignore_mask >> l) & 1u) continue;
+      const miso_level_t& lv = fl.level[l];
+      Cell c = level_cell(lv, xn);
+      float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
+      const float ux = vx * kx, uy = vy * ky, uz = vz * kz;
+      if (lv.grad) scatter_level<C>(lv, c, av, ux, uy, uz, J + l * C);
+      if (hv) {
+        // d/dx of (v . grad_x sdf) with J held fixed: mixed second derivatives of the trilinear
+        // weights (dxy, dxz, dyz of gridsample_cuda.cu:484-526); the diagonal is zero.
+        float dxy = 0.f, dxz = 0.f, dyz = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (!((c.valid >> k) & 1u)) continue;
+          float wx, wy, wz;
+          axis_w(c, k, wx, wy, wz);
+          float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
+          float sc = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < C; ch += 4) {
+            float4 val = ldg_f4(lv.feat + corner_off(lv, c, k) + ch);
+            sc = fmaf(val.x, J[l * C + ch], sc);
+            sc = fmaf(val.y, J[l * C + ch + 1], sc);
+            sc = fmaf(val.z, J[l * C + ch + 2], sc);
+            sc = fmaf(val.w, J[l * C + ch + 3], sc);
+          }
+          dxy = fmaf(sc, sx * sy * wz, dxy);
+          dxz = fmaf(sc, sx * wy * sz, dxz);
+          dyz = fmaf(sc, wx * sy * sz, dyz);
+        }
+        hx = fmaf(kx, uy * dxy + uz * dxz, hx);
+        hy = fmaf(ky, ux * dxy + uz * dyz, hy);
+        hz = fmaf(kz, ux * dxz + uy * dyz, hz);
+      }
+    }
+    if (hv) hv[3 * n] = hx, hv[3 * n + 1] = hy, hv[3 * n + 2] = hz;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: whole mapping step (forward + losses + backward scatter) -- the headline kernel
+// ---------------------------------------------------------------------------------------------
+struct MapArgs {
+  const float* x;
+  int64_t N;
+  const float* gt_sdf;
+  const uint8_t* gt_valid;
+  const float* gt_sign;
+  const float* weights;
+  miso_mapping_cfg_t cfg;
+  const int32_t* eik_count;
+  float* partials;
+  float* sdf_out;
+};
+
+template <int L, int C>
+__global__ void __launch_bounds__(kThreads)
+    mapping_step_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
+                        const __grid_constant__ miso_frames_t fr, const __grid_constant__ MapArgs m) {
+  constexpr int F = L * C;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecoderSmem<F>* s = reinterpret_cast<DecoderSmem<F>*>(smem_raw);
+  __shared__ float red[32];
+  load_decoder<F>(s, dec);
+  const FieldGeom g = field_geom(fl);
+  const bool eik_on = m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f;
+  const bool eik_filter = m.cfg.eik_trunc_dist >= 0.f;
+  const float invN = 1.0f / (float)m.N;
+  float n_eik = (float)m.N;
+  if (eik_on && eik_filter) n_eik = (float)(*m.eik_count);
+  const float inv_neik = 1.0f / n_eik;
+
+  float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < m.N; n += (int64_t)gridDim.x * blockDim.x) {
+    float p[3], xn[3];
+    load_point(m.x, fr, n, p);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
+    float f[F], dfx[F], dfy[F], dfz[F];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if ((fl.ignore_mask >> l) & 1u) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
+      } else {
+        Cell c = level_cell(fl.level[l], xn);
+        gather_level<C, true>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+      }
+    }
+    float J[F];
+    const float pred = mlp_eval<F, true>(s, f, J);
+    if (m.sdf_out) m.sdf_out[n] = pred;
+
+    const float gt = m.gt_sdf[n];
+    // --- regression term (loss.py:594-635): where(valid==1, rho(pred-gt), 0) * weight, mean over N
+    float a = 0.f;
+    if (m.gt_valid[n]) {
+      const float w = m.weights ? m.weights[n] : 1.f;
+      const float e = pred - gt;
+      if (m.cfg.loss_type == 0) {
+        acc_sdf += w * fabsf(e);
+        a += m.cfg.weight_sdf * w * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
+      } else {
+        acc_sdf += w * e * e;
+        a += m.cfg.weight_sdf * w * 2.f * e;
+      }
+    }
+    // --- free-space term (loss.py:668-700): max(relu(pred-gt), relu(trunc-pred)) where sign==1
+    if (m.cfg.weight_fs != 0.f && m.gt_sign[n] == 1.f) {
+      const float up = fmaxf(pred - gt, 0.f), lo = fmaxf(m.cfg.trunc_dist - pred, 0.f);
+      acc_fs += fmaxf(up, lo);
+      if (up > lo) a += m.cfg.weight_fs;
+      else if (lo > up) a -= m.cfg.weight_fs;
+    }
+    a *= invN * m.cfg.grad_scale;
+    // --- eikonal term (loss.py:638-665): mean((|grad_x sdf| - 1)^2) over the filtered samples
+    float v[3] = {0.f, 0.f, 0.f};
+    if (eik_on && (!eik_filter || fabsf(gt) < m.cfg.eik_trunc_dist)) {
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          sx = fmaf(J[l * C + i], dfx[l * C + i], sx);
+          sy = fmaf(J[l * C + i], dfy[l * C + i], sy);
+          sz = fmaf(J[l * C + i], dfz[l * C + i], sz);
+        }
+        gx = fmaf(sx, (float)fl.level[l].X * g.inv_len[0], gx);
+        gy = fmaf(sy, (float)fl.level[l].Y * g.inv_len[1], gy);
+        gz = fmaf(sz, (float)fl.level[l].Z * g.inv_len[2], gz);
+      }
+      const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float e = nrm - 1.f;
+      acc_eik += e * e;
+      if (nrm > 0.f) {
+        const float k = m.cfg.weight_eik * m.cfg.grad_scale * 2.f * e * inv_neik / nrm;
+        v[0] = k * gx, v[1] = k * gy, v[2] = k * gz;
+      }
+    }
+    if (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        if (((fl.ignore_mask >> l) & 1u) || !fl.level[l].grad) continue;
+        const miso_level_t& lv = fl.level[l];
+        Cell c = level_cell(lv, xn);
+        float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
+        scatter_level<C>(lv, c, a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
+      }
+    }
+  }
+  float s0 = block_sum(acc_sdf, red);
+  float s1 = block_sum(acc_fs, red);
+  float s2 = block_sum(acc_eik, red);
+  if (threadIdx.x == 0) {
+    m.partials[blockIdx.x * 4 + 0] = s0;
+    m.partials[blockIdx.x * 4 + 1] = s1;
+    m.partials[blockIdx.x * 4 + 2] = s2;
+    m.partials[blockIdx.x * 4 + 3] = 0.f;
+  }
+}
+
+__global__ void mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
+                                        miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out) {
+  // fixed-order reduction => deterministic loss values
+  __shared__ double red[32];
+  double s[3] = {0, 0, 0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+    for (int k = 0; k < 3; ++k) s[k] += (double)partials[b * 4 + k];
+  double t[3];
+  for (int k = 0; k < 3; ++k) t[k] = block_sum(s[k], red);
+  if (threadIdx.x == 0) {
+    const bool eik_on = cfg.eik_mode != 0 && cfg.weight_eik != 0.f;
+    double neik = (double)N;
+    if (eik_on && cfg.eik_trunc_dist >= 0.f) neik = (double)(*eik_count);
+    float l_sdf = (float)(t[0] / (double)N);
+    float l_fs = cfg.weight_fs != 0.f ? (float)(t[1] / (double)N) : 0.f;
+    float l_eik = eik_on ? (float)(t[2] / neik) : 0.f;
+    out[0] = l_sdf;
+    out[1] = l_fs;
+    out[2] = l_eik;
+    out[3] = cfg.weight_sdf * l_sdf + cfg.weight_fs * l_fs + (eik_on ? cfg.weight_eik * l_eik : 0.f);
+  }
+}
+
+__global__ void mapping_count_kernel(const float* __restrict__ gt, int64_t N, float trunc, int32_t* out) {
+  int cnt = 0;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
+    cnt += fabsf(gt[n]) < trunc ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------
+static int validate_field(const miso_field_t* f, bool need_grad_layout) {
+  MISO_REQUIRE(f, "field: null");
+  MISO_REQUIRE(f->num_levels >= 1 && f->num_levels <= MISO_MAX_LEVELS, "field: num_levels %d not in [1,%d]",
+               f->num_levels, MISO_MAX_LEVELS);
+  const int C = f->level[0].C;
+  for (int l = 0; l < f->num_levels; ++l) {
+    const miso_level_t& lv = f->level[l];
+    MISO_REQUIRE(lv.feat, "field: level %d has null features", l);
+    MISO_REQUIRE(lv.C == C, "field: fused kernels need the same channel count on every level");
+    MISO_REQUIRE(lv.C % 4 == 0 && lv.C >= 4 && lv.C <= 16, "field: fused kernels need C in {4,8,12,16}, got %d", lv.C);
+    MISO_REQUIRE(lv.sC == 1, "field: level %d is not channels-last (stride_C=%lld); convert with channels_last_3d", l,
+                 (long long)lv.sC);
+    MISO_REQUIRE(lv.sX % 4 == 0 && lv.sY % 4 == 0 && lv.sZ % 4 == 0 && ((uintptr_t)lv.feat) % 16 == 0,
+                 "field: level %d not 16-byte aligned", l);
+    MISO_REQUIRE(!lv.grad || ((uintptr_t)lv.grad) % 16 == 0, "field: level %d grad not 16-byte aligned", l);
+    MISO_REQUIRE(lv.X > 0 && lv.Y > 0 && lv.Z > 0, "field: level %d has an empty dimension", l);
+  }
+  for (int d = 0; d < 3; ++d)
+    MISO_REQUIRE(f->bound[2 * d + 1] > f->bound[2 * d], "field: empty bound on axis %d", d);
+  (void)need_grad_layout;
+  return MISO_OK;
+}
+
+static int validate_decoder(const miso_decoder_t* d, int F) {
+  MISO_REQUIRE(d && d->W1 && d->b1 && d->W2 && d->b2 && d->W3 && d->b3, "decoder: null weights (bias=True required)");
+  MISO_REQUIRE(d->hidden_dim == H, "decoder: fused path supports hidden_dim=64, got %d", d->hidden_dim);
+  MISO_REQUIRE(d->in_dim == F, "decoder: in_dim %d != levels*channels %d", d->in_dim, F);
+  return MISO_OK;
+}
+
+template <typename K>
+static int blocks_for(K kernel, size_t smem, int64_t N) {
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
+  if (occ < 1) occ = 1;
+  return grid_for(N, kThreads, sm_count() * occ);
+}
+
+#define MISO_DISPATCH_LC(L_, C_, ...)                                              \
+  do {                                                                             \
+    const int key_ = (L_)*100 + (C_);                                              \
+    switch (key_) {                                                                \
+      case 104: { constexpr int L = 1, C = 4; __VA_ARGS__; } break;                \
+      case 204: { constexpr int L = 2, C = 4; __VA_ARGS__; } break;                \
+      case 304: { constexpr int L = 3, C = 4; __VA_ARGS__; } break;                \
+      case 404: { constexpr int L = 4, C = 4; __VA_ARGS__; } break;                \
+      case 108: { constexpr int L = 1, C = 8; __VA_ARGS__; } break;                \
+      case 208: { constexpr int L = 2, C = 8; __VA_ARGS__; } break;                \
+      case 116: { constexpr int L = 1, C = 16; __VA_ARGS__; } break;               \
+      default:                                                                     \
+        miso::set_error("fused path: unsupported (levels=%d, channels=%d)", (L_), (C_)); \
+        return MISO_ERR_UNSUPPORTED;                                               \
+    }                                                                              \
+  } while (0)
+
+// feature-only kernel has no decoder, allow more shapes
+#define MISO_DISPATCH_LC_FEAT(L_, C_, ...)                                         \
+  do {                                                                             \
+    const int key_ = (L_)*100 + (C_);                                              \
+    switch (key_) {                                                                \
+      case 104: { constexpr int L = 1, C = 4; __VA_ARGS__; } break;                \
+      case 204: { constexpr int L = 2, C = 4; __VA_ARGS__; } break;                \
+      case 304: { constexpr int L = 3, C = 4; __VA_ARGS__; } break;                \
+      case 404: { constexpr int L = 4, C = 4; __VA_ARGS__; } break;                \
+      case 108: { constexpr int L = 1, C = 8; __VA_ARGS__; } break;                \
+      case 208: { constexpr int L = 2, C = 8; __VA_ARGS__; } break;                \
+      case 308: { constexpr int L = 3, C = 8; __VA_ARGS__; } break;                \
+      case 408: { constexpr int L = 4, C = 8; __VA_ARGS__; } break;                \
+      case 116: { constexpr int L = 1, C = 16; __VA_ARGS__; } break;               \
+      case 216: { constexpr int L = 2, C = 16; __VA_ARGS__; } break;               \
+      case 316: { constexpr int L = 3, C = 16; __VA_ARGS__; } break;               \
+      case 416: { constexpr int L = 4, C = 16; __VA_ARGS__; } break;               \
+      default:                                                                     \
+        miso::set_error("features: unsupported (levels=%d, channels=%d)", (L_), (C_)); \
+        return MISO_ERR_UNSUPPORTED;                                               \
+    }                                                                              \
+  } while (0)
+
+static miso_frames_t frames_or_none(const miso_frames_t* fr) {
+  miso_frames_t z;
+  z.ids = nullptr, z.R = nullptr, z.t = nullptr, z.num_frames = 0;
+  return fr ? *fr : z;
+}
+
+static int validate_frames(const miso_frames_t* fr) {
+  if (!fr || !fr->ids) return MISO_OK;
+  MISO_REQUIRE(fr->R && fr->t && fr->num_frames > 0, "frames: ids given without poses");
+  return MISO_OK;
+}
+
+}  // namespace miso
+
+using namespace miso;
+
+extern "C" int miso_field_features(const miso_field_t* field, const float* x, int64_t N, float* feats,
+                                   miso_stream_t stream) {
+  if (int e = validate_field(field, false)) return e;
+  MISO_REQUIRE(N >= 0 && (N == 0 || (x && feats)), "field_features: null x/feats");
+  if (N == 0) return MISO_OK;
+  MISO_REQUIRE(((uintptr_t)feats) % 16 == 0, "field_features: feats not 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  MISO_DISPATCH_LC_FEAT(field->num_levels, field->level[0].C, {
+    auto k = field_features_kernel<L, C>;
+    k<<<blocks_for(k, 0, N), kThreads, 0, s>>>(*field, x, N, feats);
+  });
+  return check_launch("field_features");
+}
+
+extern "C" int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                                const float* x, int64_t N, float* sdf, float* jac, float* gradx, float* xw,
+                                miso_stream_t stream) {
+  if (int e = validate_field(field, false)) return e;
+  if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
+  if (int e = validate_frames(frames)) return e;
+  MISO_REQUIRE(N >= 0 && (N == 0 || (x && sdf)), "sdf_forward: null x/sdf");
+  if (N == 0) return MISO_OK;
+  MISO_REQUIRE(!jac || ((uintptr_t)jac) % 16 == 0, "sdf_forward: jac not 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const miso_frames_t fr = frames_or_none(frames);
+  const bool want_jac = jac || gradx;
+  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+    constexpr size_t smem = sizeof(DecoderSmem<L * C>);
+    if (want_jac) {
+      auto k = sdf_forward_kernel<L, C, true>;
+      k<<<blocks_for(k, smem, N), kThreads, smem, s>>>(*field, *dec, fr, x, N, sdf, jac, gradx, xw);
+    } else {
+      auto k = sdf_forward_kernel<L, C, false>;
+      k<<<blocks_for(k, smem, N), kThreads, smem, s>>>(*field, *dec, fr, x, N, sdf, jac, gradx, xw);
+    }
+  });
+  return check_launch("sdf_forward");
+}
+
+extern "C" int miso_sdf_backward(const miso_field_t* field, const float* xw, int64_t N, const float* jac,
+                                 const float* a, const float* v, float* hv, miso_stream_t stream) {
+  if (int e = validate_field(field, true)) return e;
+  MISO_REQUIRE(N >= 0 && (N == 0 || (xw && jac)), "sdf_backward: null xw/jac");
+  if (N == 0 || (!a && !v)) return MISO_OK;
+  MISO_REQUIRE(((uintptr_t)jac) % 16 == 0, "sdf_backward: jac not 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+    auto k = sdf_backward_kernel<L, C>;
+    k<<<blocks_for(k, 0, N), kThreads, 0, s>>>(*field, xw, N, jac, a, v, hv);
+  });
+  return check_launch("sdf_backward");
+}
+
+extern "C" int64_t miso_mapping_workspace_floats(void) { return (int64_t)sm_count() * 8 * 4; }
+
+extern "C" int miso_mapping_count(const float* gt_sdf, int64_t N, float eik_trunc_dist, int32_t* eik_count,
+                                  miso_stream_t stream) {
+  MISO_REQUIRE(eik_count && (N == 0 || gt_sdf), "mapping_count: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(eik_count, 0, sizeof(int32_t), s);
+  if (N > 0) mapping_count_kernel<<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, s>>>(gt_sdf, N, eik_trunc_dist, eik_count);
+  return check_launch("mapping_count");
+}
+
+extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                                 const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                                 const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                                 const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                                 miso_stream_t stream) {
+  if (int e = validate_field(field, true)) return e;
+  if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
+  if (int e = validate_frames(frames)) return e;
+  MISO_REQUIRE(cfg && partials && loss_out, "mapping_step: null cfg/partials/loss_out");
+  MISO_REQUIRE(N > 0 && x && gt_sdf && gt_valid && gt_sign, "mapping_step: null inputs or N == 0");
+  MISO_REQUIRE(cfg->loss_type == 0 || cfg->loss_type == 1, "mapping_step: loss_type must be 0 (L1) or 1 (L2)");
+  MISO_REQUIRE(cfg->eik_mode == 0 || cfg->eik_mode == 1, "mapping_step: eik_mode must be 0 or 1");
+  const bool eik_on = cfg->eik_mode != 0 && cfg->weight_eik != 0.f;
+  MISO_REQUIRE(!(eik_on && cfg->eik_trunc_dist >= 0.f) || eik_count, "mapping_step: eik filter needs eik_count");
+  cudaStream_t s = (cudaStream_t)stream;
+  const miso_frames_t fr = frames_or_none(frames);
+  MapArgs m;
+  m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
+  m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
+  int nblocks = 0;
+  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+    constexpr size_t smem = sizeof(DecoderSmem<L * C>);
+    auto k = mapping_step_kernel<L, C>;
+    nblocks = blocks_for(k, smem, N);
+    if ((int64_t)nblocks * 4 > miso_mapping_workspace_floats()) nblocks = (int)(miso_mapping_workspace_floats() / 4);
+    k<<<nblocks, kThreads, smem, s>>>(*field, *dec, fr, m);
+  });
+  if (int e = check_launch("mapping_step")) return e;
+  mapping_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nblocks, N, *cfg, eik_count, loss_out);
+  return check_launch("mapping_finalize");
+}

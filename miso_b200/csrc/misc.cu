@@ -1,0 +1,167 @@
+// Error plumbing + the small helpers around the hot path: Adam over dense grids (fused with the
+// gradient zero-fill), batched frame->world transform, Morton keys for L2-local batch ordering.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace miso {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error: %s", what, cudaGetErrorString(e));
+    return MISO_ERR_CUDA;
+  }
+  return MISO_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// torch.optim.Adam._single_tensor_adam (no amsgrad / weight decay / maximize):
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(kThreads)
+    adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
+                int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
+          va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ma[e] = ma[e] + (ga[e] - ma[e]) * (1.f - b1);  // torch: exp_avg.lerp_(grad, 1-beta1)
+      va[e] = va[e] * b2 + (1.f - b2) * ga[e] * ga[e];
+      float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] = pa[e] - step_size * (ma[e] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (zero) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // scalar tail
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+    if (zero) g[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    transform_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ R,
+                     const float* __restrict__ t, int num_frames, int64_t N, float* __restrict__ y) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
+    int64_t id = ids[n];
+    if (id < 0 || id >= num_frames) {
+      y[3 * n] = a, y[3 * n + 1] = b, y[3 * n + 2] = c;
+      continue;
+    }
+    const float* Rm = R + id * 9;
+    const float* tv = t + id * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) y[3 * n + j] = fmaf(c, Rm[3 * j + 2], fmaf(b, Rm[3 * j + 1], a * Rm[3 * j])) + tv[j];
+  }
+}
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    morton_kernel(const float* __restrict__ x, int64_t N, float bx0, float bx1, float by0, float by1, float bz0,
+                  float bz1, uint32_t* __restrict__ keys) {
+  const float sx = 1024.f / (bx1 - bx0), sy = 1024.f / (by1 - by0), sz = 1024.f / (bz1 - bz0);
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float fx = fminf(fmaxf((x[3 * n] - bx0) * sx, 0.f), 1023.f);
+    float fy = fminf(fmaxf((x[3 * n + 1] - by0) * sy, 0.f), 1023.f);
+    float fz = fminf(fmaxf((x[3 * n + 2] - bz0) * sz, 0.f), 1023.f);
+    keys[n] = spread10((uint32_t)fx) | (spread10((uint32_t)fy) << 1) | (spread10((uint32_t)fz) << 2);
+  }
+}
+
+}  // namespace miso
+
+using namespace miso;
+
+extern "C" const char* miso_last_error_string(void) { return g_err; }
+extern "C" int miso_abi_version(void) { return MISO_ABI_VERSION; }
+extern "C" int miso_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    set_error("device_sm_count: no CUDA device");
+    return MISO_ERR_CUDA;
+  }
+  return n;
+}
+
+extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                              float eps, int32_t step, int32_t zero_grad, miso_stream_t stream) {
+  MISO_REQUIRE(p && g && m && v, "adam_step: null tensor");
+  MISO_REQUIRE(n >= 0 && step >= 1, "adam_step: n >= 0 and step >= 1 required");
+  if (n == 0) return MISO_OK;
+  const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const int blocks = grid_for(n4 > 0 ? n4 : n, kThreads, sm_count() * 8);
+  adam_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, step_size,
+                                                             bc2_sqrt, zero_grad);
+  return check_launch("adam_step");
+}
+
+extern "C" int miso_transform_points(const float* x, const int64_t* ids, const float* R, const float* t,
+                                     int32_t num_frames, int64_t N, float* y, miso_stream_t stream) {
+  MISO_REQUIRE(N >= 0 && (N == 0 || (x && ids && R && t && y)), "transform_points: null argument");
+  MISO_REQUIRE(num_frames > 0, "transform_points: num_frames must be positive");
+  if (N == 0) return MISO_OK;
+  transform_kernel<<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, (cudaStream_t)stream>>>(x, ids, R, t, num_frames, N, y);
+  return check_launch("transform_points");
+}
+
+extern "C" int miso_morton_keys(const float* x, int64_t N, const float bound[6], uint32_t* keys, miso_stream_t stream) {
+  MISO_REQUIRE(N >= 0 && (N == 0 || (x && keys)) && bound, "morton_keys: null argument");
+  if (N == 0) return MISO_OK;
+  morton_kernel<<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, (cudaStream_t)stream>>>(
+      x, N, bound[0], bound[1], bound[2], bound[3], bound[4], bound[5], keys);
+  return check_launch("morton_keys");
+}

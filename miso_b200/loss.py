@@ -1,0 +1,315 @@
+"""Mapping losses of the hot path, same names and semantics as grid_opt/loss.py:
+`miso_loss_regression` (:594-635), `miso_loss_eikonal` (:638-665), `miso_loss_free_space`
+(:668-700), `MisoLossMappingBase.compute` / `MisoLossMapping` (:703-813, :847-853).
+
+Two execution paths, both on the GPU:
+  * fused   -- ONE kernel does frame->world transform, interpolation of every level, the MLP, its
+               analytic spatial gradient, the three loss terms and the scatter of d(total)/d(grid)
+               (miso_mapping_step).  Taken when the model exposes a fused spec (decoder fixed),
+               keyframe poses are locked, grad_method is 'autograd' (or the eikonal weight is 0).
+  * generic -- the reference's op sequence on torch tensors; the per-level interpolation is the
+               twice-differentiable miso_b200.cuda_gridsample op, the eikonal gradient comes from
+               miso_b200.diff.gradient3d.  Handles trainable decoders, unlocked poses, finite
+               differences, Cosine loss.
+
+Reference defect mirrored deliberately: the reference asserts on an
+attribute `use_clip` that is never set (loss.py:788), so `weight_eik > 0` raises there; here the
+eikonal term simply works.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from . import field as _field
+from .diff import gradient3d
+
+
+def miso_loss_regression(pred, targ, valid_mask=None, sample_weights=None, loss_type="L1"):
+    """loss.py:594-635."""
+    assert pred.shape == targ.shape
+    num_samples = pred.shape[0]
+    if valid_mask is None:
+        valid_mask = torch.ones((num_samples, 1)).to(pred)
+    if sample_weights is None:
+        sample_weights = torch.ones((num_samples, 1)).to(pred)
+    assert valid_mask.shape == (num_samples, 1)
+    assert sample_weights.shape == (num_samples, 1)
+    if loss_type == "L2":
+        loss_vec = torch.sum((pred - targ) ** 2, dim=1, keepdim=True)
+    elif loss_type == "L1":
+        loss_vec = torch.sum(torch.abs(pred - targ), dim=1, keepdim=True)
+    elif loss_type == "Cosine":
+        loss_vec = 1.0 - F.cosine_similarity(pred, targ, dim=1, eps=1e-8).unsqueeze(1)
+    else:
+        raise ValueError(f"Invalid loss type: {loss_type}")
+    loss_vec = torch.where(valid_mask == 1, loss_vec, torch.zeros_like(loss_vec))
+    return torch.mean(sample_weights * loss_vec)
+
+
+def miso_loss_eikonal(model, coords_world, gt_sdf, eik_trunc_dist, grad_method, finite_diff_eps):
+    """loss.py:638-665."""
+    if eik_trunc_dist is not None:
+        valid_mask = torch.abs(gt_sdf) < eik_trunc_dist
+        valid_indices = torch.nonzero(valid_mask, as_tuple=False)[:, 0]
+        x_eik = coords_world[valid_indices, :].clone()
+    else:
+        x_eik = coords_world.clone()
+    x_eik.requires_grad_(True)
+    gradient = gradient3d(x_eik, model, method=grad_method, finite_diff_eps=finite_diff_eps, create_graph=True)
+    grad_constraint = gradient.norm(dim=-1) - 1
+    return torch.mean(grad_constraint ** 2)
+
+
+def miso_loss_free_space(pred_sdf, gt_sdf, gt_sdf_sign, trunc_dist):
+    """loss.py:668-700."""
+    assert trunc_dist is not None
+    fs_upper = torch.where(gt_sdf_sign == 1, F.relu(pred_sdf - gt_sdf), torch.zeros_like(pred_sdf))
+    fs_lower = torch.where(gt_sdf_sign == 1, F.relu(trunc_dist - pred_sdf), torch.zeros_like(pred_sdf))
+    return torch.mean(torch.maximum(fs_upper, fs_lower))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused step
+# ------------------------------------------------------------------------------------------------
+# bench.py hook: when set to a list, (start, end) CUDA events are recorded around every fused step launch
+PROFILE_EVENTS = None
+
+
+class MappingWorkspace:
+    """Per-device scratch of the fused step (never allocated inside the kernel)."""
+    _cache = {}
+
+    def __init__(self, device):
+        lib = _lib.load()
+        self.partials = torch.zeros(int(lib.miso_mapping_workspace_floats()), dtype=torch.float32, device=device)
+        self.eik_count = torch.zeros(1, dtype=torch.int32, device=device)
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(device)
+        return cls._cache[key]
+
+
+def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
+                     weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None):
+    """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
+    terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped)."""
+    lib = _lib.load()
+    dev = x.device
+    N = x.shape[0]
+    ws = MappingWorkspace.get(dev)
+    cfg = _lib.MappingCfg()
+    cfg.loss_type = {"L1": 0, "L2": 1}[loss_type]
+    cfg.weight_sdf, cfg.weight_fs, cfg.weight_eik = float(weight_sdf), float(weight_fs), float(weight_eik)
+    cfg.trunc_dist = float(trunc_dist if trunc_dist is not None else 0.0)
+    cfg.eik_trunc_dist = float(eik_trunc_dist) if eik_trunc_dist is not None else -1.0
+    cfg.eik_mode = 1 if (eik_on and weight_eik > 0) else 0
+    cfg.grad_scale = float(grad_scale)
+    fld = _field.make_field(feats, spec.bound, grads, spec.ignore_mask)
+    dec = spec.decoder.struct()
+    fr = frames.struct() if frames is not None else None
+    loss_out = torch.empty(4, dtype=torch.float32, device=dev)
+    stream = _lib.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        if cfg.eik_mode == 1 and eik_trunc_dist is not None:
+            _lib.check(lib.miso_mapping_count(gt_sdf.data_ptr(), N, cfg.eik_trunc_dist, ws.eik_count.data_ptr(),
+                                              stream), "mapping_count")
+        if PROFILE_EVENTS is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
+        _lib.check(lib.miso_mapping_step(
+            C.byref(fld), C.byref(dec), C.byref(fr) if fr is not None else None, x.data_ptr(), N, gt_sdf.data_ptr(),
+            gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg), ws.eik_count.data_ptr(),
+            ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out), stream), "mapping_step")
+        if PROFILE_EVENTS is not None:
+            e1.record(torch.cuda.current_stream(dev))
+            PROFILE_EVENTS.append((e0, e1))
+    return loss_out
+
+
+def _flat_f32(t):
+    t = t.detach().reshape(-1)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _flat_u8(t):
+    t = t.detach().reshape(-1)
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    return (t != 0).to(torch.uint8).contiguous()
+
+
+class _FusedMappingLoss(torch.autograd.Function):
+    """Forward runs the whole step (including the gradient scatter); backward hands the stored
+    gradients to autograd scaled by the upstream cotangent.  Outputs are the three WEIGHTED terms so
+    the caller's `sum(loss_dict.values())` has unit cotangents; unequal cotangents poison the result
+    with NaN instead of returning a silently wrong gradient (a single kernel cannot un-mix them)."""
+
+    @staticmethod
+    def forward(ctx, x, gt_sdf, gt_valid, gt_sign, weights, spec, frames, cfg, *feats):
+        need = [f.requires_grad for f in feats]
+        grads = [torch.zeros_like(f) if n else None for f, n in zip(feats, need)]
+        out = mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, **cfg)
+        ctx.grads = grads
+        ctx.unit = cfg.get("_assume_unit", False)
+        w = out.new_tensor([cfg["weight_sdf"], cfg["weight_fs"], cfg["weight_eik"] if cfg["eik_on"] else 0.0])
+        terms = out[:3] * w
+        ctx.mark_non_differentiable(out)
+        return terms[0], terms[1], terms[2], out
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, _g_out):
+        grads = ctx.grads
+        ctx.grads = None
+        gs = [g for g in (g0, g1, g2) if g is not None]
+        if not gs:
+            return (None,) * (8 + len(grads))
+        s = gs[0]
+        for g in gs[1:]:
+            s = torch.where(g == s, s, torch.full_like(s, float("nan")))
+        outs = []
+        for G in grads:
+            outs.append(None if G is None else G.mul_(s))
+        return (None,) * 8 + tuple(outs)
+
+
+class MisoLossMappingBase:
+    """loss.py:703-813.  Same constructor arguments and `compute(model, model_input, gt) -> dict`."""
+
+    def __init__(self, loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0, trunc_dist=0,
+                 finite_diff_eps=1e-2, grad_method="autograd", eik_trunc_dist=0.1, use_stability=False,
+                 weight_clip=0):
+        self.loss_type = loss_type
+        self.trunc_dist = trunc_dist
+        self.weight_sdf = weight_sdf
+        self.weight_eik = weight_eik
+        self.weight_fs = weight_fs
+        self.finite_diff_eps = finite_diff_eps
+        self.grad_method = grad_method
+        self.eik_trunc_dist = eik_trunc_dist
+        self.use_stability = use_stability
+        self.weight_clip = weight_clip
+        if use_stability or weight_clip > 0:
+            raise NotImplementedError("stability / CLIP terms are outside the hot path (SURVEY.md section 8)")
+        self.last_terms = None
+
+    # -- pose table -------------------------------------------------------------------------------
+    def frame_table(self, model):
+        """(R (K,3,3), t (K,3,1), lut) with lut[global kf id] = row; replaces the per-keyframe
+        query_kf_pose loop + np.unique host sync of loss.py:764-774."""
+        raise NotImplementedError
+
+    def _fused_ok(self, model):
+        if getattr(model, "fused_spec", None) is None or model.fused_spec() is None:
+            return False
+        if self.loss_type not in ("L1", "L2"):
+            return False
+        if self.weight_eik > 0 and self.grad_method != "autograd":
+            return False
+        R, t, _ = self.frame_table(model)
+        return not (R.requires_grad or t.requires_grad)
+
+    def compute(self, model, model_input: dict, gt: dict) -> dict:
+        coords_frame = model_input["coords_frame"][0]
+        sample_frame_ids = model_input["sample_frame_ids"][0, :, 0]
+        sample_weights = model_input["weights"][0]
+        gt_sdf = gt["sdf"][0]
+        gt_sdf_valid = gt["sdf_valid"][0]
+        gt_sdf_sign = gt["sdf_signs"][0]
+        assert coords_frame.ndim == 2 and gt_sdf.ndim == 2
+        assert sample_weights.shape == gt_sdf.shape
+        if self._fused_ok(model):
+            return self._compute_fused(model, coords_frame, sample_frame_ids, sample_weights, gt_sdf, gt_sdf_valid,
+                                       gt_sdf_sign)
+        return self._compute_generic(model, coords_frame, sample_frame_ids, sample_weights, gt_sdf, gt_sdf_valid,
+                                     gt_sdf_sign)
+
+    def _step_cfg(self):
+        return dict(loss_type=self.loss_type, weight_sdf=self.weight_sdf, weight_fs=self.weight_fs,
+                    weight_eik=self.weight_eik, trunc_dist=self.trunc_dist, eik_trunc_dist=self.eik_trunc_dist,
+                    eik_on=self.weight_eik > 0)
+
+    def _frames(self, model, sample_frame_ids):
+        R, t, lut = self.frame_table(model)
+        ids = lut[sample_frame_ids.reshape(-1)] if lut is not None else sample_frame_ids.reshape(-1)
+        return _field.FramesSpec(ids, R, t)
+
+    def _compute_fused(self, model, coords_frame, ids, weights, gt_sdf, gt_valid, gt_sign):
+        spec = model.fused_spec()
+        frames = self._frames(model, ids)
+        x = _field._prep_x(coords_frame)
+        t_sdf, t_fs, t_eik, raw = _FusedMappingLoss.apply(
+            x, _flat_f32(gt_sdf), _flat_u8(gt_valid), _flat_f32(gt_sign), _flat_f32(weights), spec, frames,
+            self._step_cfg(), *model.level_tensors())
+        self.last_terms = raw
+        loss_dict = {f"sdf_{self.loss_type}": t_sdf}
+        if self.weight_eik > 0:
+            loss_dict["eik"] = t_eik
+        if self.weight_fs > 0:
+            loss_dict["free_space"] = t_fs
+        return loss_dict
+
+    def _compute_generic(self, model, coords_frame, ids, weights, gt_sdf, gt_valid, gt_sign):
+        R, t, lut = self.frame_table(model)
+        loc = lut[ids] if lut is not None else ids
+        coords_world = torch.einsum("nij,nj->ni", R[loc], coords_frame) + t[loc].squeeze(-1)
+        pred_sdf = model(coords_world)[:, [0]]
+        sdf_loss = miso_loss_regression(pred=pred_sdf, targ=gt_sdf, valid_mask=gt_valid, sample_weights=weights,
+                                        loss_type=self.loss_type)
+        loss_dict = {f"sdf_{self.loss_type}": self.weight_sdf * sdf_loss}
+        if self.weight_eik > 0:
+            eik_loss = miso_loss_eikonal(model=model, coords_world=coords_world, gt_sdf=gt_sdf,
+                                         eik_trunc_dist=self.eik_trunc_dist, grad_method=self.grad_method,
+                                         finite_diff_eps=self.finite_diff_eps)
+            loss_dict["eik"] = eik_loss * self.weight_eik
+        if self.weight_fs > 0:
+            fs_loss = miso_loss_free_space(pred_sdf=pred_sdf, gt_sdf=gt_sdf, gt_sdf_sign=gt_sign,
+                                           trunc_dist=self.trunc_dist)
+            loss_dict["free_space"] = fs_loss * self.weight_fs
+        return loss_dict
+
+    # -- autograd-free variant used by miso_b200.trainer (gradients go straight into param.grad) -----
+    def step_into_grads(self, model, model_input: dict, gt: dict, active_levels=None):
+        """Runs the fused step accumulating into `feature.grad` of the active levels.  Returns the (4,)
+        loss tensor [sdf, fs, eik, total]."""
+        if not self._fused_ok(model):
+            raise RuntimeError("step_into_grads needs the fused path (fixed decoder, locked poses, "
+                               "grad_method='autograd' when weight_eik > 0)")
+        coords_frame = model_input["coords_frame"][0]
+        ids = model_input["sample_frame_ids"][0, :, 0]
+        feats = model.level_tensors()
+        grads = []
+        for l, f in enumerate(feats):
+            active = f.requires_grad and (active_levels is None or l in active_levels)
+            if active and f.grad is None:
+                f.grad = torch.zeros_like(f)
+            grads.append(f.grad if active else None)
+        raw = mapping_step_raw(feats, grads, model.fused_spec(), self._frames(model, ids),
+                               _field._prep_x(coords_frame), _flat_f32(gt["sdf"][0]), _flat_u8(gt["sdf_valid"][0]),
+                               _flat_f32(gt["sdf_signs"][0]), _flat_f32(model_input["weights"][0]), **self._step_cfg())
+        self.last_terms = raw
+        return raw
+
+
+class MisoLossMapping(MisoLossMappingBase):
+    """loss.py:847-853: mapping within a single submap (GridNet); keyframe k is addressed by the key
+    f'KF{k}' (grid_net.py:232-235)."""
+
+    def frame_table(self, model):
+        R, t = model.all_kf_poses()
+        keys = model._pose_key_to_id
+        cache = getattr(model, "_miso_lut", None)
+        if cache is None or cache[0] != len(keys) or cache[1].device != R.device:
+            n = 1 + max([int(k[2:]) for k in keys], default=-1)
+            lut = torch.zeros(max(n, 1), dtype=torch.int64)
+            for k, v in keys.items():
+                lut[int(k[2:])] = v
+            cache = (len(keys), lut.to(R.device))
+            model._miso_lut = cache
+        return R, t, cache[1]

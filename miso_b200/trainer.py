@@ -1,0 +1,188 @@
+"""Mapping loop of the hot path: `GridTrainer` mirrors grid_opt/trainer.py:370-491 (per-level Adam
+optimisers, 'coordinate' / 'coordinate+joint' / 'joint' schedule, level switching every
+`max_epochs_in_level` epochs or on relative-change convergence) with `train_epoch` =
+prepare_batch -> loss -> backward -> step (trainer.py:196-228), and `Mapper.mapping` mirrors
+grid_opt/slam/mapper.py:65-98.
+
+One epoch is one batch (reference datasets have `__len__ == 1`, sdf_rgbd.py:86-87).  On the fused
+path an epoch is 3 launches: eikonal-sample count, the fused mapping step (scatter straight into
+`feature.grad`), and one fused Adam(+zero) pass per active level.  Host buffers are staged through
+pinned memory on a copy stream (`HostBatchStager`) so the H2D copy of batch i+1 overlaps step i.
+"""
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .loss import MisoLossMapping
+from .models import GridNet
+from .optim import FusedAdam
+
+Batch = Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]
+
+
+def prepare_batch(model_input, gt, device="cuda:0"):
+    """utils.py:500-505 (+ sanitize :487-493): move to the device, nan_to_num float tensors."""
+    def mv(v):
+        v = v.to(device, non_blocking=True)
+        return torch.nan_to_num(v) if v.is_floating_point() else v
+    return {k: mv(v) for k, v in model_input.items()}, {k: mv(v) for k, v in gt.items()}
+
+
+class HostBatchStager:
+    """Double-buffered pinned-host -> device staging of (model_input, gt) batches."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._slots = [None, None]
+        self._events = [None, None]
+        self._turn = 0
+        self.h2d_bytes = 0
+
+    def stage(self, batch: Batch) -> Tuple[Batch, torch.cuda.Event]:
+        """Start the async copy of `batch` (CPU tensors, ideally pinned); returns device tensors and the
+        event the compute stream must wait on."""
+        slot = self._turn
+        self._turn ^= 1
+        model_input, gt = batch
+        nbytes = 0
+        with torch.cuda.stream(self.stream):
+            if self._events[slot] is not None:
+                self.stream.wait_event(self._events[slot])  # previous consumer of this slot is done
+            dev_in, dev_gt = {}, {}
+            for src, dst in ((model_input, dev_in), (gt, dev_gt)):
+                for k, v in src.items():
+                    if not v.is_pinned():
+                        v = v.pin_memory()
+                    dst[k] = v.to(self.device, non_blocking=True)
+                    nbytes += v.numel() * v.element_size()
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        self._slots[slot] = (dev_in, dev_gt)
+        self.h2d_bytes = nbytes
+        return (dev_in, dev_gt), ready
+
+    def release(self, slot_event: torch.cuda.Event):
+        self._events[self._turn ^ 1] = slot_event
+
+
+class GridTrainer:
+    """trainer.py:370-491 for a GridNet on the fused path."""
+
+    def __init__(self, cfg: dict, model: GridNet, loss_func: MisoLossMapping, batch_fn: Callable[[int], Batch],
+                 device="cuda:0"):
+        self.cfg = cfg
+        self.model = model
+        self.loss_func = loss_func
+        self.batch_fn = batch_fn
+        self.device = device
+        self.epochs = cfg.get("epochs", 50)
+        self.lr = cfg.get("learning_rate", 1e-3)
+        self.relchange_tol = cfg.get("relchange_tol", 0)
+        self.max_epochs_in_level = cfg.get("max_epochs_in_level", 100)
+        self.grid_training_mode = cfg.get("grid_training_mode", "coordinate+joint")
+        if cfg.get("optimizer", "adam") != "adam":
+            raise NotImplementedError("fused trainer implements optimizer: adam (the shipped configs)")
+        self.train_dict = {"loss": []}
+        self.total_steps = 0
+        self.set_optimizer()
+
+    def set_optimizer(self):
+        m = self.model
+        self.level_optimizers: List[FusedAdam] = []
+        if self.grid_training_mode != "joint":
+            for level in range(m.num_levels):
+                self.level_optimizers.append(FusedAdam(m.params_at_level(level), lr=self.lr))
+        self.joint_optimizer = FusedAdam(list(m.parameters()), lr=self.lr)
+        self.reset_convergence_check()
+        if self.grid_training_mode in ("coordinate", "coordinate+joint"):
+            self.active_level = 0
+            self.optimizer = self.level_optimizers[0]
+        elif self.grid_training_mode == "joint":
+            self.active_level = m.num_levels
+            self.optimizer = self.joint_optimizer
+        else:
+            raise ValueError(f"Invalid grid training mode: {self.grid_training_mode}")
+
+    def reset_convergence_check(self):
+        self.params_prev = None
+        self.relchange = np.inf
+        self.epochs_in_level = 0
+
+    def active_levels(self):
+        return None if self.active_level >= self.model.num_levels else {self.active_level}
+
+    def pre_epoch(self, epoch):
+        """trainer.py:455-480."""
+        if self.relchange < self.relchange_tol or self.epochs_in_level >= self.max_epochs_in_level:
+            if self.active_level < self.model.num_levels:
+                self.train_dict[f"level{self.active_level}_last_epoch"] = epoch
+                self.active_level += 1
+                if self.active_level >= self.model.num_levels:
+                    if self.grid_training_mode == "coordinate+joint":
+                        self.optimizer = self.joint_optimizer
+                else:
+                    self.optimizer = self.level_optimizers[self.active_level]
+                self.reset_convergence_check()
+        self.epochs_in_level += 1
+
+    def train_step(self, model_input, gt) -> torch.Tensor:
+        """loss.compute -> backward -> optimizer.step (trainer.py:209-217) as fused launches.  Returns the
+        (4,) device tensor [sdf, fs, eik, total]; nothing is synchronised."""
+        terms = self.loss_func.step_into_grads(self.model, model_input, gt, self.active_levels())
+        self.optimizer.step()
+        self.total_steps += 1
+        return terms
+
+    def train_epoch(self, epoch):
+        model_input, gt = self.batch_fn(epoch)
+        model_input, gt = prepare_batch(model_input, gt, self.device)
+        terms = self.train_step(model_input, gt)
+        self.train_dict["loss"].append(terms)
+        return terms
+
+    def train(self):
+        for epoch in range(self.epochs):
+            self.pre_epoch(epoch)
+            self.train_epoch(epoch)
+            if self.relchange_tol > 0:
+                self.relchange = self.relative_param_change(self.model.params_at_level(self.active_level))
+        return self.train_dict
+
+    def relative_param_change(self, params):
+        cur = [p.detach().clone() for p in params if p.requires_grad]
+        if self.params_prev is None:
+            self.params_prev = cur
+            return np.inf
+        num = sum(torch.sum((c - p) ** 2) for c, p in zip(cur, self.params_prev))
+        den = sum(torch.sum(p ** 2) for p in self.params_prev)
+        self.params_prev = cur
+        return torch.sqrt(num / den).item()
+
+
+class Mapper:
+    """slam/mapper.py:27-98: builds the mapping loss + trainer on one GridNet; `mapping(kfs, iterations,
+    level_iterations)` unlocks features, locks poses, trains."""
+
+    def __init__(self, model: GridNet, batch_fn: Callable[[int], Batch], cfg: dict, device="cuda:0"):
+        self.model = model
+        self.cfg = cfg
+        self.device = device
+        cm = cfg["mapping"]
+        self.loss_func = MisoLossMapping(loss_type=cm["loss_type"], weight_sdf=cm["weight_sdf"],
+                                         weight_eik=cm["weight_eik"], weight_fs=cm["weight_fs"],
+                                         trunc_dist=cm["trunc_dist"], finite_diff_eps=cm["finite_diff_eps"],
+                                         grad_method=cm["grad_method"], eik_trunc_dist=cm.get("eik_trunc_dist"))
+        self.batch_fn = batch_fn
+
+    def mapping(self, kfs=None, iterations=300, level_iterations=50):
+        grid = self.model
+        grid.unlock_feature()
+        grid.lock_pose()
+        cfg_train = dict(self.cfg.get("train", {}))
+        cfg_train["epochs"] = iterations
+        cfg_train["max_epochs_in_level"] = level_iterations
+        cfg_train["learning_rate"] = self.cfg["mapping"]["learning_rate"]
+        trainer = GridTrainer(cfg_train, grid, self.loss_func, self.batch_fn, device=self.device)
+        return trainer.train()

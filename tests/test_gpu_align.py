@@ -1,0 +1,178 @@
+"""GPU parity of the batched alignment kernel (C-ABI section 3) against the CPU oracle's restatement
+of pairwise_loss_latent (grid_opt/align/miso.py:116-211), check_submap_intersection
+(grid_atlas.py:405-420) and generic_align_multiple_submaps (align/base.py:89-163).
+Tolerances: loss 1e-5 rel (forward class), pose gradients and Adam pose updates 1e-4 rel,
+in-bound masks / valid counts / alignment-sample ordering bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from miso_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BOUND = [[-4.0, 4.0], [-2.0, 2.0], [-4.0, 4.0]]
+
+
+def build_atlases(num_submaps=3, base_cell=1.0, scale=2, seed=0, perturb=True, spacing=(4.0, 3.0)):
+    """(GridAtlas on cuda, OracleAtlas on cpu) with identical grids sampled from one smooth latent field."""
+    from miso_b200.models import GridAtlas
+    cfg = synth.model_cfg(BOUND, base_cell_size=base_cell, per_level_scale=scale, num_poses=1)
+    Rt, tt = synth.submap_layout(num_submaps, spacing=spacing)
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=4.0, trans_m=0.3) if perturb else (Rt, tt)
+    atlas = GridAtlas(cfg, device="cuda")
+    shapes = O.level_shapes(BOUND, base_cell, scale, 2, 4)
+    subs = []
+    for i in range(num_submaps):
+        atlas.add_submap(torch.tensor(BOUND), Rp[i], tp[i])
+        feats = synth.fill_submap_from_field(shapes, BOUND, Rt[i], tt[i])
+        # zero a slab so precompute_coordinates_for_alignment has something to prune
+        feats[0][:, :, :, :, :1] = 0
+        feats[1][:, :, :, :, :2] = 0
+        sm = atlas.get_submap(i)
+        sm.decoder.load_state_dict(synth.decoder_weights(8))
+        for l in range(2):
+            with torch.no_grad():
+                sm.features[l].feature.copy_(feats[l].cuda())
+        subs.append(O.OracleGridNet(BOUND, feats, None))
+    oat = O.OracleAtlas(subs, Rp, tp)
+    return atlas, oat
+
+
+def test_precompute_coordinates_bit_exact():
+    atlas, oat = build_atlases(2)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([0, 1])
+    for i in range(2):
+        for l in range(2):
+            a = atlas.coordinates_for_alignment(i, l).cpu()
+            b = oat.coords[(i, l)]
+            assert a.shape == b.shape and a.shape[0] > 0
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_pairwise_loss_and_pose_grads(level):
+    from miso_b200.align import pairwise_loss_latent
+    atlas, oat = build_atlases(3)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([0, 1])
+    for (s, d) in [(0, 1), (1, 2), (0, 2)]:
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        ld = pairwise_loss_latent(atlas, None, s, d, level=level, device="cuda")
+        (key, val), = ld.items()
+        assert key == f"align_latent_level{level}_{s}_{d}"
+        Rs, ts = oat.updated_submap_pose(s)
+        Rd, td = oat.updated_submap_pose(d)
+        for q in oat.rot + oat.tra:
+            q.grad = None
+        lo = O.pairwise_loss_latent(oat.submaps[s], oat.submaps[d], oat.coords[(s, level)], Rs, ts, Rd, td, level)
+        assert rel_err(val, lo) < 1e-5
+        if lo.requires_grad:
+            val.backward()
+            lo.backward()
+            for i in (s, d):
+                assert rel_err(atlas.rotation_corrections[i].grad, oat.rot[i].grad) < 1e-4
+                assert rel_err(atlas.translation_corrections[i].grad, oat.tra[i].grad) < 1e-4
+
+
+def test_mask_count_intersection_bit_exact():
+    from miso_b200.align import AlignBatch
+    atlas, oat = build_atlases(3)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([1])
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    batch = AlignBatch(atlas, pairs, level=1, want_masks=True, check_intersection=True)
+    poses = batch.pair_poses()
+    batch.update_intersections(poses)
+    out = batch.launch(poses)
+    for i, (s, d) in enumerate(pairs):
+        Rs, ts = oat.updated_submap_pose(s)
+        Rd, td = oat.updated_submap_pose(d)
+        _, mask, idx = O.pairwise_loss_latent(oat.submaps[s], oat.submaps[d], oat.coords[(s, 1)], Rs, ts, Rd, td, 1,
+                                              return_aux=True)
+        inter = bool(O.check_submap_intersection(oat.submaps[s], oat.submaps[d], Rs, ts, Rd, td))
+        assert bool(batch.enabled[i].item()) == inter
+        if inter:
+            assert torch.equal(batch.masks[i].cpu().bool(), mask[:, 0])
+            assert int(out[i, 1].item()) == int(mask.sum())
+            # nonzero() of the mask reproduces valid_indices (miso.py:184) in order
+            assert torch.equal(torch.nonzero(batch.masks[i], as_tuple=False)[:, 0].cpu(), idx if idx is not None else torch.empty(0, dtype=torch.long))
+
+
+def test_no_valid_points_gives_zero():
+    from miso_b200.align import AlignBatch
+    atlas, _ = build_atlases(2, spacing=(100.0, 100.0), perturb=False)
+    atlas.precompute_coordinates_for_alignment()
+    batch = AlignBatch(atlas, [(0, 1)], level=0, check_intersection=False)
+    loss = batch.losses(3000.0)
+    assert float(loss[0]) == 0.0
+    loss.sum().backward()  # gradients exist and are zero
+    assert torch.count_nonzero(atlas.rotation_corrections[1].grad) == 0
+
+
+def test_align_iterations_match_oracle_adam():
+    """k iterations of generic_align_multiple_submaps: total loss per iteration and the resulting pose
+    corrections (the Adam update) against the oracle loop."""
+    from miso_b200.align import generic_align_multiple_submaps
+    atlas, oat = build_atlases(3)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([0])
+    info = generic_align_multiple_submaps(atlas, None, ("latent", None), num_iters=4, lr=1e-2, level=0)
+    hist = O.align_multiple_submaps(oat, level=0, num_iters=4, lr=1e-2)
+    got = info["losses"].tolist()
+    assert len(got) == len(hist) == 5
+    assert np.allclose(got, hist, rtol=1e-4), (got, hist)
+    for i in range(1, 3):
+        assert rel_err(atlas.rotation_corrections[i], oat.rot[i]) < 1e-4
+        assert rel_err(atlas.translation_corrections[i], oat.tra[i]) < 1e-4
+    assert torch.count_nonzero(atlas.rotation_corrections[0]) == 0  # submap 0 stays fixed
+
+
+def test_alignment_reduces_pose_error():
+    from miso_b200.align import align_multiple_submaps_hierarchical
+    atlas, _ = build_atlases(3)
+    Rt, tt = synth.submap_layout(3, spacing=(4.0, 3.0))
+    def err():
+        e = 0.0
+        for i in range(1, 3):
+            _, t = atlas.updated_submap_pose(i)
+            e += float((t.cpu() - tt[i]).norm())
+        return e
+    e0 = err()
+    align_multiple_submaps_hierarchical(atlas, None, level_iters=60, lr=1e-2, latent_levels=[0, 1], skip_finetune=True)
+    assert err() < 0.5 * e0
+
+
+def test_gauss_newton_normal_equations():
+    """J^T J / J^T r of the latent residual wrt a right-multiplied dst twist, against autograd."""
+    from miso_b200.align import AlignBatch, gauss_newton_dst_step
+    atlas, oat = build_atlases(2)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([0])
+    batch = AlignBatch(atlas, [(0, 1)], level=0, check_intersection=False)
+    delta, H, g = gauss_newton_dst_step(batch, lm_lambda=0.0)
+    # oracle: residual vector as a function of a twist xi = (w, tau) applied as R_d Exp(w), t_d + tau
+    Rs, ts = oat.updated_submap_pose(0)
+    Rd0, td0 = oat.updated_submap_pose(1)
+    Rs, ts, Rd0, td0 = Rs.detach().double(), ts.detach().double(), Rd0.detach().double(), td0.detach().double()
+    src = O.OracleGridNet(BOUND, [f.double() for f in oat.submaps[0].features], None, second_order=True)
+    dst = O.OracleGridNet(BOUND, [f.double() for f in oat.submaps[1].features], None, second_order=True)
+    p = oat.coords[(0, 0)].double()
+
+    def resid(xi):
+        Rd = Rd0 @ torch.linalg.matrix_exp(O.hat(xi[None, :3])[0])
+        td = td0 + xi[3:, None]
+        q = O.transfrom_points_from(O.transform_points_to(p, Rs, ts), Rd, td)
+        m = O.coords_in_bound(q.detach(), dst.bound.double())[:, 0]
+        r = src.query_feature(p[m])[:, :4] - dst.query_feature(q[m])[:, :4]
+        return r.reshape(-1)
+
+    xi0 = torch.zeros(6, dtype=torch.float64)
+    J = torch.autograd.functional.jacobian(resid, xi0)
+    r0 = resid(xi0)
+    assert rel_err(H[0], J.T @ J) < 1e-4
+    assert rel_err(g[0], J.T @ r0) < 1e-4

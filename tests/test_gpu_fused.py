@@ -1,0 +1,220 @@
+"""GPU parity of the fused field kernels (C-ABI section 2) against the CPU oracle: features, SDF,
+analytic gradient, first-order backward, eikonal double-backward, the one-kernel mapping step, Adam.
+Tolerances (BASELINE.json north_star): forward 1e-5 relative; first/second-order gradients 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import SMALL_BOUND, make_pair, points_in, rel_err
+from miso_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F = 1e-5
+TOL_G = 1e-4
+
+
+@pytest.mark.parametrize("n_levels,fdim", [(2, 4), (1, 4), (3, 4), (2, 8), (1, 16)])
+def test_query_feature_and_forward(n_levels, fdim):
+    net, o1, _ = make_pair(n_levels=n_levels, fdim=fdim, scale=3)
+    x = points_in(SMALL_BOUND, 5000, seed=1)
+    with torch.no_grad():
+        f = net.query_feature(x.cuda())
+        y = net(x.cuda())
+    assert f.shape == (5000, n_levels * fdim)
+    assert rel_err(f, o1.query_feature(x)) < TOL_F
+    assert rel_err(y, o1(x)) < TOL_F
+    assert y.shape == (5000, 1)
+
+
+def test_forward_ignore_level_and_empty():
+    net, o1, _ = make_pair()
+    net.ignore_level(1)
+    o1.ignore_level_[1] = True
+    x = points_in(SMALL_BOUND, 1000, seed=2)
+    with torch.no_grad():
+        assert rel_err(net(x.cuda()), o1(x)) < TOL_F
+        assert rel_err(net.query_feature(x.cuda()), o1.query_feature(x)) < TOL_F
+        assert net(torch.zeros(0, 3, device="cuda")).shape == (0, 1)
+
+
+def test_first_order_backward_and_gradx():
+    net, o1, o2 = make_pair()
+    net.unlock_feature()
+    x = points_in(SMALL_BOUND, 4000, seed=3)
+    w = torch.randn(4000, 1, generator=torch.Generator().manual_seed(4))
+    xg = x.cuda().requires_grad_(True)
+    y = net(xg)
+    (y * w.cuda()).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    yo = o1(xo)
+    (yo * w).sum().backward()
+    assert rel_err(y, yo) < TOL_F
+    assert rel_err(xg.grad, xo.grad) < TOL_G
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, o1.features[l].grad) < TOL_G
+    # analytic spatial gradient output == gradient3d(..., 'autograd')
+    from miso_b200.diff import gradient3d
+    g = gradient3d(x.cuda().requires_grad_(True), net, method="autograd", create_graph=False)
+    go = O.gradient3d(x.clone().requires_grad_(True), o2, method="autograd", create_graph=False)
+    assert rel_err(g, go) < TOL_G
+
+
+@pytest.mark.parametrize("via", ["forward_with_gradient", "autograd.grad"])
+def test_eikonal_double_backward(via):
+    """mean((|grad_x f| - 1)^2) -> d/d grid : the path that needs grid_sampler_3d_grad2_kernel in the reference."""
+    net, _, o2 = make_pair()
+    net.unlock_feature()
+    x = points_in(SMALL_BOUND, 3000, seed=5, scale=0.95)
+    xg = x.cuda().requires_grad_(True)
+    if via == "forward_with_gradient":
+        _, g = net.forward_with_gradient(xg)
+    else:
+        y = net(xg)
+        g = torch.autograd.grad(y, xg, torch.ones_like(y), create_graph=True)[0]
+    loss = torch.mean((g.norm(dim=-1) - 1) ** 2)
+    loss.backward()
+    xo = x.clone().requires_grad_(True)
+    go = O.gradient3d(xo, o2, "autograd", create_graph=True)
+    lo = torch.mean((go.norm(dim=-1) - 1) ** 2)
+    lo.backward()
+    assert rel_err(loss, lo) < TOL_G
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, o2.features[l].grad) < TOL_G
+    # coordinate cotangent of the double backward (mixed second derivatives)
+    assert rel_err(xg.grad, xo.grad) < TOL_G
+
+
+def _batch(n=6000, num_kf=4, seed=1):
+    return synth.rgbd_batch(n, num_kf=num_kf, bound=SMALL_BOUND, seed=seed, wall_margin=0.3)
+
+
+def _to_cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.parametrize("loss_type,w_eik,eik_trunc,w_fs", [("L1", 0.0, None, 0.1), ("L1", 0.5, None, 0.1),
+                                                             ("L2", 0.5, 0.1, 0.5), ("L2", 0.0, None, 0.0)])
+def test_mapping_step_fused_vs_oracle(loss_type, w_eik, eik_trunc, w_fs):
+    """MisoLossMapping.compute -> backward: every term and d(total)/d(grid) against the oracle's
+    restatement of loss.py:754-813 (autograd second-order eikonal through the gather oracle)."""
+    from miso_b200.loss import MisoLossMapping
+    net, _, o2 = make_pair()
+    mi, gt, (R, t) = _batch()
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type=loss_type, weight_sdf=1.0, weight_eik=w_eik, weight_fs=w_fs, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=eik_trunc)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    total = sum(v.mean() for v in ld.values())
+    total.backward()
+    lo = O.mapping_loss(o2, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, loss_type, 1.0, w_eik, w_fs, 0.15,
+                        grad_method="autograd", eik_trunc_dist=eik_trunc)
+    sum(lo.values()).backward()
+    assert set(ld.keys()) == set(lo.keys())
+    for k in lo:
+        assert rel_err(ld[k], lo[k]) < TOL_G, k
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, o2.features[l].grad) < TOL_G
+
+
+def test_mapping_generic_path_matches_fused_and_oracle():
+    """Trainable decoder -> generic path (twice-differentiable per-level op + torch MLP), incl. decoder grads
+    and the finite-difference eikonal (configured default grad_method, scannet.yaml:49)."""
+    from miso_b200.loss import MisoLossMapping
+    net, o1, _ = make_pair(fix=False)
+    assert net.fused_spec() is None
+    mi, gt, (R, t) = _batch(3000)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    L = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="finitediff", finite_diff_eps=0.024, eik_trunc_dist=None)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    sum(v.mean() for v in ld.values()).backward()
+    lo = O.mapping_loss(o1, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, "L1", 1.0, 0.5, 0.1, 0.15,
+                        finite_diff_eps=0.024, grad_method="finitediff", eik_trunc_dist=None)
+    sum(lo.values()).backward()
+    for k in lo:
+        assert rel_err(ld[k], lo[k]) < TOL_G, k
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, o1.features[l].grad) < TOL_G
+    gp = [p.grad for p in net.decoder.parameters()]
+    op = [p.grad for p in o1.decoder.parameters()]
+    for a, b in zip(gp, op):
+        assert rel_err(a, b) < TOL_G
+
+
+def test_trainer_steps_match_oracle_adam():
+    """k fused train steps (count + mapping step + fused Adam/zero) vs oracle loss + torch.optim.Adam."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    net, _, o2 = make_pair()
+    mi, gt, (R, t) = _batch(4000)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=None)
+    tr = GridTrainer({"epochs": 5, "learning_rate": 1e-3, "grid_training_mode": "joint"}, net, L,
+                     lambda e: (mi, gt), device="cuda")
+    losses = [tr.train_epoch(e) for e in range(5)]
+    opt = torch.optim.Adam(list(o2.features.parameters()), lr=1e-3)
+    ol = []
+    for e in range(5):
+        opt.zero_grad()
+        lo = O.mapping_loss(o2, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, "L1", 1.0, 0.5, 0.1, 0.15,
+                            grad_method="autograd", eik_trunc_dist=None)
+        tot = sum(lo.values())
+        tot.backward()
+        opt.step()
+        ol.append(float(tot))
+    got = [float(l[3]) for l in losses]
+    assert np.allclose(got, ol, rtol=1e-4), (got, ol)
+    for l in range(2):
+        assert rel_err(net.features[l].feature, o2.features[l]) < TOL_G
+        # the fused Adam leaves a zeroed gradient buffer behind
+        assert torch.count_nonzero(net.features[l].feature.grad) == 0
+
+
+def test_adam_matches_torch():
+    from miso_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    p = torch.randn(1, 4, 6, 5, 7, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    p1 = torch.nn.Parameter(p.clone())
+    p2 = torch.nn.Parameter(p.clone())
+    o1 = FusedAdam([p1], lr=1e-3)
+    o2 = torch.optim.Adam([p2], lr=1e-3)
+    for i in range(4):
+        g = torch.randn_like(p)
+        p1.grad = g.clone()
+        p2.grad = g.clone()
+        o1.step()
+        o2.step()
+    assert rel_err(p1, p2) < 1e-6
+    assert torch.count_nonzero(p1.grad) == 0
+
+
+def test_full_size_properties():
+    """Size-independent checks at BASELINE config-1 scale (2^18 points, ScanNet-submap grid):
+    linearity of the interpolation in the grid values and zero output outside the bound."""
+    from miso_b200 import field
+    bound = synth.SCANNET_SUBMAP_BOUND
+    net, _, _ = make_pair(bound=bound, base_cell=0.5, scale=5, seed=3)
+    x = points_in(bound, 2 ** 18, seed=9).cuda()
+    feats = net.level_tensors()
+    b = net._bound_host
+    with torch.no_grad():
+        f1 = field.field_features_raw(feats, b, x)
+        f2 = field.field_features_raw([2.0 * f for f in feats], b, x)
+        assert rel_err(f2, 2.0 * f1) < 1e-6
+        far = x + 100.0
+        assert torch.count_nonzero(field.field_features_raw(feats, b, far)) == 0
+        # interpolating a constant field returns the constant strictly inside the grid
+        ones = [torch.ones_like(f) for f in feats]
+        inside = points_in(bound, 2 ** 16, seed=10, scale=0.9).cuda()
+        assert rel_err(field.field_features_raw(ones, b, inside), torch.ones(2 ** 16, 8)) < 1e-6
