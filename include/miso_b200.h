@@ -148,6 +148,8 @@ typedef struct miso_mapping_cfg {
   float eik_trunc_dist;   /* <0: no filter (None) */
   int32_t eik_mode;       /* 0 = off, 1 = analytic (autograd second-order equivalent) */
   float grad_scale;       /* upstream d(total) (normally 1) */
+  int64_t n_total;        /* denominator of the means; 0 = N.  Point-sharded multi-GPU fits pass the global
+                             batch size so that per-rank gradients / loss terms simply sum (all_reduce). */
 } miso_mapping_cfg_t;
 
 /* gt arrays are (N) float; valid is uint8/bool (N).  eik_count: device int32 counter holding the

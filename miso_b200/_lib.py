@@ -42,7 +42,7 @@ class Frames(C.Structure):
 class MappingCfg(C.Structure):
     _fields_ = [("loss_type", C.c_int32), ("weight_sdf", C.c_float), ("weight_fs", C.c_float),
                 ("weight_eik", C.c_float), ("trunc_dist", C.c_float), ("eik_trunc_dist", C.c_float),
-                ("eik_mode", C.c_int32), ("grad_scale", C.c_float)]
+                ("eik_mode", C.c_int32), ("grad_scale", C.c_float), ("n_total", C.c_int64)]
 
 
 class AlignPair(C.Structure):

@@ -368,7 +368,7 @@ static bool vec4_ok(int dtype, const void* base, const int64_t* sz, const int64_
 static int validate(int dtype, const void* input, const int64_t* sz, const int64_t* st, const void* grid, int64_t P,
                     int pad) {
   MISO_REQUIRE(dtype == MISO_F32 || dtype == MISO_F64, "grid_sample3d: dtype must be f32 or f64");
-  MISO_REQUIRE(input && grid && sz && st, "grid_sample3d: null input/grid");
+  MISO_REQUIRE(input && sz && st && (grid || P == 0), "grid_sample3d: null input/grid");
   MISO_REQUIRE(pad == MISO_PAD_ZEROS || pad == MISO_PAD_BORDER, "grid_sample3d: padding_mode must be zeros|border");
   for (int d = 0; d < 5; ++d) MISO_REQUIRE(sz[d] > 0, "grid_sample3d: empty input dimension %d", d);
   MISO_REQUIRE(P >= 0, "grid_sample3d: negative point count");

@@ -73,10 +73,11 @@ class _GridSample3dForward(torch.autograd.Function):
         inp = input.detach()
         out = torch.empty((B, P, Cc), dtype=input.dtype, device=input.device)
         with torch.cuda.device(input.device):
-            _lib.check(lib.miso_grid_sample3d_fwd(
-                _dtype_code(input), inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()), g.data_ptr(), P,
-                out.data_ptr(), _out_strides(out), _lib.PAD_MODES.index(padding_mode), int(bool(align_corners)),
-                _lib.stream_ptr(input.device)), "grid_sample3d_fwd")
+            if P > 0:
+                _lib.check(lib.miso_grid_sample3d_fwd(
+                    _dtype_code(input), inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()), g.data_ptr(), P,
+                    out.data_ptr(), _out_strides(out), _lib.PAD_MODES.index(padding_mode), int(bool(align_corners)),
+                    _lib.stream_ptr(input.device)), "grid_sample3d_fwd")
         ctx.save_for_backward(input, grid)
         ctx.padding_mode = _lib.PAD_MODES.index(padding_mode)
         ctx.align_corners = bool(align_corners)
@@ -111,7 +112,8 @@ class _GridSample3dBackward(torch.autograd.Function):
         grad_input = torch.zeros_like(inp) if need_input else None  # preserve_format keeps channels_last_3d
         grad_grid = torch.empty_like(g) if need_grid else None
         with torch.cuda.device(input.device):
-            _lib.check(lib.miso_grid_sample3d_bwd(
+            if P > 0:
+              _lib.check(lib.miso_grid_sample3d_bwd(
                 _dtype_code(input), go.data_ptr(), go_st, inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()),
                 g.data_ptr(), P, _lib.ptr(grad_input),
                 _lib.i64(grad_input.stride()) if grad_input is not None else None, _lib.ptr(grad_grid),
@@ -143,7 +145,8 @@ class _GridSample3dBackward(torch.autograd.Function):
         g_input = torch.zeros_like(inp) if need_input else None
         g_grid = torch.empty_like(g) if need_grid else None
         with torch.cuda.device(input.device):
-            _lib.check(lib.miso_grid_sample3d_bwd_bwd(
+            if P > 0:
+              _lib.check(lib.miso_grid_sample3d_bwd_bwd(
                 _dtype_code(input), _lib.ptr(ggi), _lib.i64(ggi.stride()) if ggi is not None else None, _lib.ptr(ggg),
                 go.data_ptr(), go_st, inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()), g.data_ptr(), P,
                 _lib.ptr(gg_out), _out_strides(gg_out) if gg_out is not None else None, _lib.ptr(g_input),

@@ -95,7 +95,8 @@ class MappingWorkspace:
 
 
 def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
-                     weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None):
+                     weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None,
+                     n_total=0, count_allreduce=None):
     """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
     terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped)."""
     lib = _lib.load()
@@ -109,6 +110,7 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
     cfg.eik_trunc_dist = float(eik_trunc_dist) if eik_trunc_dist is not None else -1.0
     cfg.eik_mode = 1 if (eik_on and weight_eik > 0) else 0
     cfg.grad_scale = float(grad_scale)
+    cfg.n_total = int(n_total)
     fld = _field.make_field(feats, spec.bound, grads, spec.ignore_mask)
     dec = spec.decoder.struct()
     fr = frames.struct() if frames is not None else None
@@ -118,6 +120,8 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
         if cfg.eik_mode == 1 and eik_trunc_dist is not None:
             _lib.check(lib.miso_mapping_count(gt_sdf.data_ptr(), N, cfg.eik_trunc_dist, ws.eik_count.data_ptr(),
                                               stream), "mapping_count")
+            if count_allreduce is not None:
+                count_allreduce([ws.eik_count])   # point-sharded fit: the eikonal mean runs over all ranks
         if PROFILE_EVENTS is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(dev))
@@ -157,7 +161,7 @@ class _FusedMappingLoss(torch.autograd.Function):
         grads = [torch.zeros_like(f) if n else None for f, n in zip(feats, need)]
         out = mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, **cfg)
         ctx.grads = grads
-        ctx.unit = cfg.get("_assume_unit", False)
+        ctx.set_materialize_grads(False)  # terms the caller drops arrive as None, not as zeros
         w = out.new_tensor([cfg["weight_sdf"], cfg["weight_fs"], cfg["weight_eik"] if cfg["eik_on"] else 0.0])
         terms = out[:3] * w
         ctx.mark_non_differentiable(out)
@@ -275,9 +279,11 @@ class MisoLossMappingBase:
         return loss_dict
 
     # -- autograd-free variant used by miso_b200.trainer (gradients go straight into param.grad) -----
-    def step_into_grads(self, model, model_input: dict, gt: dict, active_levels=None):
+    def step_into_grads(self, model, model_input: dict, gt: dict, active_levels=None, n_total=0,
+                        count_allreduce=None):
         """Runs the fused step accumulating into `feature.grad` of the active levels.  Returns the (4,)
-        loss tensor [sdf, fs, eik, total]."""
+        loss tensor [sdf, fs, eik, total].  `n_total` / `count_allreduce` are the point-sharded multi-GPU
+        hooks (miso_b200.dist): means run over the global batch so per-rank results sum."""
         if not self._fused_ok(model):
             raise RuntimeError("step_into_grads needs the fused path (fixed decoder, locked poses, "
                                "grad_method='autograd' when weight_eik > 0)")
@@ -292,7 +298,8 @@ class MisoLossMappingBase:
             grads.append(f.grad if active else None)
         raw = mapping_step_raw(feats, grads, model.fused_spec(), self._frames(model, ids),
                                _field._prep_x(coords_frame), _flat_f32(gt["sdf"][0]), _flat_u8(gt["sdf_valid"][0]),
-                               _flat_f32(gt["sdf_signs"][0]), _flat_f32(model_input["weights"][0]), **self._step_cfg())
+                               _flat_f32(gt["sdf_signs"][0]), _flat_f32(model_input["weights"][0]),
+                               n_total=n_total, count_allreduce=count_allreduce, **self._step_cfg())
         self.last_terms = raw
         return raw
 
@@ -302,14 +309,22 @@ class MisoLossMapping(MisoLossMappingBase):
     f'KF{k}' (grid_net.py:232-235)."""
 
     def frame_table(self, model):
-        R, t = model.all_kf_poses()
+        """Tables indexed by GLOBAL keyframe id (so the kernel consumes `sample_frame_ids` directly).  While
+        poses are locked the table is cached and only rebuilt when a pose tensor's version counter moves."""
         keys = model._pose_key_to_id
-        cache = getattr(model, "_miso_lut", None)
-        if cache is None or cache[0] != len(keys) or cache[1].device != R.device:
-            n = 1 + max([int(k[2:]) for k in keys], default=-1)
-            lut = torch.zeros(max(n, 1), dtype=torch.int64)
-            for k, v in keys.items():
-                lut[int(k[2:])] = v
-            cache = (len(keys), lut.to(R.device))
-            model._miso_lut = cache
-        return R, t, cache[1]
+        params = (model.rotation_corrections, model.translation_corrections, model.Rwk, model.twk)
+        locked = not (model.rotation_corrections.requires_grad or model.translation_corrections.requires_grad)
+        stamp = (len(keys), tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        cache = getattr(model, "_miso_frame_cache", None)
+        if locked and cache is not None and cache[0] == stamp:
+            return cache[1], cache[2], None
+        R, t = model.all_kf_poses()
+        n = 1 + max([int(k[2:]) for k in keys], default=-1)
+        lut = torch.zeros(max(n, 1), dtype=torch.int64)
+        for k, v in keys.items():
+            lut[int(k[2:])] = v
+        lut = lut.to(R.device)
+        Rg, tg = R[lut], t[lut]
+        if locked:
+            model._miso_frame_cache = (stamp, Rg.detach(), tg.detach())
+        return Rg, tg, None

@@ -127,10 +127,15 @@ class GridTrainer:
                 self.reset_convergence_check()
         self.epochs_in_level += 1
 
-    def train_step(self, model_input, gt) -> torch.Tensor:
+    def train_step(self, model_input, gt, n_total=0, allreduce=None) -> torch.Tensor:
         """loss.compute -> backward -> optimizer.step (trainer.py:209-217) as fused launches.  Returns the
-        (4,) device tensor [sdf, fs, eik, total]; nothing is synchronised."""
-        terms = self.loss_func.step_into_grads(self.model, model_input, gt, self.active_levels())
+        (4,) device tensor [sdf, fs, eik, total]; nothing is synchronised.  Point-sharded multi-GPU fit:
+        pass the global batch size and `miso_b200.dist.allreduce_sum_`; the dense grid gradients (and the
+        loss terms) are summed over ranks before the identical Adam update on every rank."""
+        terms = self.loss_func.step_into_grads(self.model, model_input, gt, self.active_levels(), n_total=n_total,
+                                               count_allreduce=allreduce)
+        if allreduce is not None:
+            allreduce([p.grad for p in self.optimizer.params if p.grad is not None] + [terms])
         self.optimizer.step()
         self.total_steps += 1
         return terms

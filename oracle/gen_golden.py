@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(`/root/reference`, CPU, via oracle/ref_loader.py) on small seeded inputs.  Run in the build
+container:  python -m oracle.gen_golden
+The fixtures store inputs AND reference outputs, so the oracle (tests/test_oracle_golden.py) and the
+CUDA path (tests/test_gpu_golden.py) can both be checked where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from miso_b200 import synth  # noqa: E402  (synthetic input generators only; no kernels involved)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+BOUND = [[-2.0, 2.0], [-1.0, 1.0], [-2.0, 2.0]]
+ABOUND = [[-4.0, 4.0], [-2.0, 2.0], [-4.0, 4.0]]
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_ref_gridnet(bound, base_cell=0.5, scale=5, std=0.1, seed=0, num_poses=4, feats=None):
+    from grid_opt.models.grid_net import GridNet
+    cfg = ref_loader.reference_model_cfg(bound, base_cell_size=base_cell, per_level_scale=scale, num_poses=num_poses)
+    net = GridNet(cfg, device="cpu")
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for l, lvl in enumerate(net.features):
+            f = feats[l] if feats is not None else torch.randn(lvl.feature.shape, generator=g) * std
+            lvl.feature.copy_(f)
+    net.decoder.load_state_dict(synth.decoder_weights(8, seed=seed))
+    return net
+
+
+def gen_gridnet():
+    import grid_opt.diff as rdiff
+    net = make_ref_gridnet(BOUND)
+    net.unlock_feature()
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(257, 3, generator=g) * 2 - 1) * torch.tensor([2.3, 1.15, 2.3])
+    w = torch.randn(257, 1, generator=g)
+    xg = x.clone().requires_grad_(True)
+    feat = net.query_feature(xg)
+    sdf = net(xg)
+    (sdf * w).sum().backward()
+    out = {"bound": np.asarray(BOUND, np.float32), "x": _np(x), "w": _np(w), "features": _np(feat), "sdf": _np(sdf),
+           "grad_x": _np(xg.grad)}
+    for l in range(2):
+        out[f"feat{l}"] = _np(net.features[l].feature)
+        out[f"grad_feat{l}"] = _np(net.features[l].feature.grad)
+    for k, v in net.decoder.state_dict().items():
+        out["dec." + k] = _np(v)
+    out["gradient3d_autograd"] = _np(rdiff.gradient3d(x.clone().requires_grad_(True), net, "autograd", create_graph=False))
+    out["gradient3d_fd"] = _np(rdiff.gradient3d(x.clone(), net, "finitediff", finite_diff_eps=0.024))
+    np.savez_compressed(os.path.join(OUT, "gridnet.npz"), **out)
+
+
+def gen_mapping():
+    import grid_opt.loss as rloss
+    out = {"bound": np.asarray(BOUND, np.float32)}
+    mi, gt, (R, t) = synth.rgbd_batch(900, num_kf=3, bound=BOUND, seed=5, wall_margin=0.3)
+    for k, v in {**mi, **gt}.items():
+        out["in." + k] = _np(v)
+    out["R"], out["t"] = _np(R), _np(t)
+    for tag, kw in {"L1fs": dict(loss_type="L1", weight_fs=0.1), "L2fs": dict(loss_type="L2", weight_fs=0.5)}.items():
+        net = make_ref_gridnet(BOUND, num_poses=3)
+        for k in range(3):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        L = rloss.MisoLossMapping(weight_sdf=1.0, weight_eik=0.0, trunc_dist=0.15, finite_diff_eps=0.024,
+                                  grad_method="finitediff", eik_trunc_dist=0.024, **kw)
+        ld = L.compute(net, mi, gt)
+        total = 0.0
+        for v in ld.values():
+            total = total + v.mean()
+        total.backward()
+        for k, v in ld.items():
+            out[f"{tag}.{k}"] = _np(v)
+        for l in range(2):
+            out[f"{tag}.grad_feat{l}"] = _np(net.features[l].feature.grad)
+    # eikonal through miso_loss_eikonal directly (MisoLossMappingBase.compute trips over `use_clip`, loss.py:788)
+    net = make_ref_gridnet(BOUND, num_poses=3)
+    net.unlock_feature()
+    g = torch.Generator().manual_seed(12)
+    xw = (torch.rand(400, 3, generator=g) * 2 - 1) * torch.tensor([1.9, 0.95, 1.9])
+    gts = torch.randn(400, 1, generator=g) * 0.05
+    e = rloss.miso_loss_eikonal(net, xw, gts, 0.05, "finitediff", 0.024)
+    e.backward()
+    out["eik.x"], out["eik.gt"], out["eik.fd_value"] = _np(xw), _np(gts), _np(e)
+    for l in range(2):
+        out[f"eik.fd_grad_feat{l}"] = _np(net.features[l].feature.grad)
+    for l in range(2):
+        out[f"feat{l}"] = _np(net.features[l].feature)
+    np.savez_compressed(os.path.join(OUT, "mapping.npz"), **out)
+
+
+def gen_align():
+    from grid_opt.models.grid_atlas import GridAtlas
+    import grid_opt.align.miso as amiso
+    from oracle import oracle as O
+    cfg = ref_loader.reference_model_cfg(ABOUND, base_cell_size=1.0, per_level_scale=2, num_poses=1)
+    Rt, tt = synth.submap_layout(2, spacing=(4.0, 3.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=4.0, trans_m=0.3)
+    atlas = GridAtlas(cfg, device="cpu")
+    shapes = O.level_shapes(ABOUND, 1.0, 2, 2, 4)
+    out = {"bound": np.asarray(ABOUND, np.float32)}
+    for i in range(2):
+        atlas.add_submap(torch.tensor(ABOUND), Rp[i], tp[i])
+        feats = synth.fill_submap_from_field(shapes, ABOUND, Rt[i], tt[i])
+        feats[0][:, :, :, :, :1] = 0
+        feats[1][:, :, :, :, :2] = 0
+        sm = atlas.get_submap(i)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(feats[l])
+                out[f"sm{i}.feat{l}"] = _np(feats[l])
+        out[f"sm{i}.R"], out[f"sm{i}.t"] = _np(Rp[i]), _np(tp[i])
+    atlas.precompute_coordinates_for_alignment()
+    for l in range(2):
+        for i in range(2):
+            out[f"coords.sm{i}.level{l}"] = _np(atlas.coordinates_for_alignment(i, l))
+    out["intersect01"] = np.asarray(bool(atlas.check_submap_intersection(0, 1)))
+    for level in range(2):
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        ld = amiso.pairwise_loss_latent(atlas, None, 0, 1, level=level, device="cpu")
+        (key, val), = ld.items()
+        val.backward()
+        out[f"L{level}.loss"] = _np(val)
+        out[f"L{level}.key"] = np.asarray(key)
+        for i in range(2):
+            out[f"L{level}.grad_rot{i}"] = _np(atlas.rotation_corrections[i].grad)
+            out[f"L{level}.grad_tra{i}"] = _np(atlas.translation_corrections[i].grad)
+    np.savez_compressed(os.path.join(OUT, "align.npz"), **out)
+
+
+def main():
+    ref_loader.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    gen_gridnet()
+    gen_mapping()
+    gen_align()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

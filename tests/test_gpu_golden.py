@@ -1,0 +1,120 @@
+"""GPU: the CUDA path against the committed outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/gen_golden.py) -- no oracle in between.  Tolerances: forward 1e-5, gradients 1e-4
+relative; alignment-sample ordering bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from miso_b200 import synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def gpu_net(z, gz, num_poses=4, fix=True):
+    from miso_b200.models import GridNet
+    net = GridNet(synth.model_cfg(z["bound"].tolist(), num_poses=num_poses, fix=fix), device="cuda")
+    with torch.no_grad():
+        for l in range(2):
+            net.features[l].feature.copy_(T(z[f"feat{l}"]).cuda())
+    net.decoder.load_state_dict({k[len("dec."):]: T(gz[k]) for k in gz.files if k.startswith("dec.")})
+    return net
+
+
+@pytest.mark.parametrize("fix", [True, False])
+def test_gridnet_against_reference_outputs(fix):
+    """fix=True -> fused kernel; fix=False -> generic per-level plugin + torch MLP."""
+    from miso_b200.diff import gradient3d
+    z = load("gridnet.npz")
+    net = gpu_net(z, z, fix=fix)
+    assert (net.fused_spec() is not None) == fix
+    net.unlock_feature()
+    x = T(z["x"]).cuda().requires_grad_(True)
+    with torch.no_grad():
+        assert rel_err(net.query_feature(T(z["x"]).cuda()), T(z["features"])) < 1e-5
+    y = net(x)
+    (y * T(z["w"]).cuda()).sum().backward()
+    assert rel_err(y, T(z["sdf"])) < 1e-5
+    assert rel_err(x.grad, T(z["grad_x"])) < 1e-4
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, T(z[f"grad_feat{l}"])) < 1e-4
+    ga = gradient3d(T(z["x"]).cuda().requires_grad_(True), net, "autograd", create_graph=False)
+    assert rel_err(ga, T(z["gradient3d_autograd"])) < 1e-4
+    gf = gradient3d(T(z["x"]).cuda(), net, "finitediff", finite_diff_eps=0.024)
+    assert rel_err(gf, T(z["gradient3d_fd"])) < 1e-4
+
+
+@pytest.mark.parametrize("tag,loss_type,w_fs", [("L1fs", "L1", 0.1), ("L2fs", "L2", 0.5)])
+def test_mapping_step_against_reference_outputs(tag, loss_type, w_fs):
+    from miso_b200.loss import MisoLossMapping
+    z, gz = load("mapping.npz"), load("gridnet.npz")
+    net = gpu_net(z, gz, num_poses=3)
+    R, t = T(z["R"]), T(z["t"])
+    for k in range(3):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    mi = {k: T(z["in." + k]).cuda() for k in ("coords_frame", "sample_frame_ids", "weights")}
+    gt = {k: T(z["in." + k]).cuda() for k in ("sdf", "sdf_valid", "sdf_signs")}
+    L = MisoLossMapping(loss_type=loss_type, weight_sdf=1.0, weight_eik=0.0, weight_fs=w_fs, trunc_dist=0.15)
+    ld = L.compute(net, mi, gt)
+    sum(v.mean() for v in ld.values()).backward()
+    for k, v in ld.items():
+        assert rel_err(v, T(z[f"{tag}.{k}"])) < 1e-5, k
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, T(z[f"{tag}.grad_feat{l}"])) < 1e-4
+
+
+def test_finite_difference_eikonal_against_reference_outputs():
+    """The configured default grad_method (finitediff, scannet.yaml:49): six extra fused forward passes."""
+    from miso_b200.loss import miso_loss_eikonal
+    z, gz = load("mapping.npz"), load("gridnet.npz")
+    net = gpu_net(z, gz, num_poses=3)
+    net.unlock_feature()
+    e = miso_loss_eikonal(net, T(z["eik.x"]).cuda(), T(z["eik.gt"]).cuda(), 0.05, "finitediff", 0.024)
+    e.backward()
+    assert rel_err(e, T(z["eik.fd_value"])) < 1e-4
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, T(z[f"eik.fd_grad_feat{l}"])) < 1e-4
+
+
+def test_alignment_against_reference_outputs():
+    from miso_b200.align import AlignBatch, pairwise_loss_latent
+    from miso_b200.models import GridAtlas
+    z = load("align.npz")
+    bound = z["bound"].tolist()
+    atlas = GridAtlas(synth.model_cfg(bound, base_cell_size=1.0, per_level_scale=2, num_poses=1), device="cuda")
+    for i in range(2):
+        atlas.add_submap(torch.tensor(bound), T(z[f"sm{i}.R"]), T(z[f"sm{i}.t"]))
+        with torch.no_grad():
+            for l in range(2):
+                atlas.get_submap(i).features[l].feature.copy_(T(z[f"sm{i}.feat{l}"]).cuda())
+    atlas.precompute_coordinates_for_alignment()
+    for l in range(2):
+        for i in range(2):
+            assert torch.equal(atlas.coordinates_for_alignment(i, l).cpu(), T(z[f"coords.sm{i}.level{l}"]))
+    batch = AlignBatch(atlas, [(0, 1)], level=1, check_intersection=True)
+    batch.update_intersections(batch.pair_poses())
+    assert bool(batch.enabled[0].item()) == bool(z["intersect01"])
+    assert bool(atlas.check_submap_intersection(0, 1)) == bool(z["intersect01"])
+    for level in range(2):
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        (key, val), = pairwise_loss_latent(atlas, None, 0, 1, level=level, device="cuda").items()
+        assert key == str(z[f"L{level}.key"])
+        val.backward()
+        assert rel_err(val, T(z[f"L{level}.loss"])) < 1e-5
+        for i in range(2):
+            assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"L{level}.grad_rot{i}"])) < 1e-4
+            assert rel_err(atlas.translation_corrections[i].grad, T(z[f"L{level}.grad_tra{i}"])) < 1e-4
