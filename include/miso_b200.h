@@ -223,6 +223,14 @@ int miso_transform_points(const float* x, const int64_t* ids, const float* R, co
 int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int32_t step, int32_t zero_grad, miso_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the
+ *    3xTF32 split, activations in TMEM, weights in shared memory): D (M,64) = A (M,64) * W^T
+ *    (transpose=0, the forward layer h W2^T as nn.Linear computes it) or A * W (transpose=1, the backward
+ *    product).  W is a row-major 64x64 fp32 matrix (nn.Linear.weight layout, modules.py:18).
+ * ------------------------------------------------------------------------------------------ */
+int miso_tc_selftest(const float* A, const float* W, int32_t transpose, float* D, int64_t M, miso_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,10 @@
 // memory and read as warp-uniform 128-bit broadcasts, all MLP math as packed FFMA2 (fma.rn.f32x2),
 // corner fetches as 128-bit read-only loads from the channels-last grid, scatter as 128-bit
 // red.global.add.v4.f32.  Persistent CTAs (grid = SMs x occupancy) loop over 256-point tiles.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace miso {
 
@@ -551,6 +554,282 @@ __global__ void __launch_bounds__(kThreads, MISO_MAP_MIN_BLOCKS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// kernel: whole mapping step with the two 64x64 decoder layers on the tensor cores (tcgen05, 3xTF32)
+//
+// CTA = 2 warpgroups x 128 threads; a warpgroup owns one 128-point tile at a time (thread <-> point <->
+// TMEM lane).  Per tile: gather + layer 1 on SIMT -> h1 split hi/lo into TMEM -> 24 x tcgen05.mma with
+// W2 (shared memory, canonical layout) -> thread reads its row of h2 from TMEM: ReLU, W3 dot, mask ->
+// t = D2 W3^T split into TMEM -> 24 x tcgen05.mma with W2^T -> thread reads g1, applies D1, J = W1^T g1
+// on SIMT -> grad_x sdf, loss terms, one scatter.  The two warpgroups interleave: while one waits for
+// its MMAs the other gathers / scatters.
+// ---------------------------------------------------------------------------------------------
+template <int F>
+struct TcSmem {
+  alignas(128) unsigned char w2_hi[tc::kWeightBytes];
+  alignas(128) unsigned char w2_lo[tc::kWeightBytes];
+  alignas(128) unsigned char w2t_hi[tc::kWeightBytes];
+  alignas(128) unsigned char w2t_lo[tc::kWeightBytes];
+  alignas(16) float W1[H * F];
+  alignas(16) float b1[H];
+  alignas(16) float b2[H];
+  alignas(16) float W3[H];
+  alignas(16) float W3hi[H];
+  alignas(16) float W3lo[H];
+  float b3[4];
+  uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+constexpr int kTcThreads = 256;
+
+__device__ __forceinline__ void wg_barrier(int wg) {
+  asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "r"(128) : "memory");
+}
+
+template <int L, int C>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    mapping_step_tc_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
+                           const __grid_constant__ miso_frames_t fr, const __grid_constant__ MapArgs m) {
+  constexpr int F = L * C;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcSmem<F>* s = reinterpret_cast<TcSmem<F>*>(smem_raw);
+  __shared__ float red[32];
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127;
+
+  // ---- one-time setup: TMEM, barriers, weights --------------------------------------------------
+  if (warp == 0) tc::tmem_alloc(&s->tmem_base, 512);
+  if (tid == 0) {
+    tc::mbar_init(&s->bar[0], 1);
+    tc::mbar_init(&s->bar[1], 1);
+    tc::fence_mbar_init();
+  }
+  tc::stage_weights(dec.W2, false, s->w2_hi, s->w2_lo, tid, kTcThreads);   // B[n=j][k] = W2[j][k]
+  tc::stage_weights(dec.W2, true, s->w2t_hi, s->w2t_lo, tid, kTcThreads);  // B[n=k][j] = W2[j][k]
+  for (int i = tid; i < H * F; i += kTcThreads) s->W1[i] = dec.W1[i];
+  for (int i = tid; i < H; i += kTcThreads) {
+    s->b1[i] = dec.b1[i];
+    s->b2[i] = dec.b2[i];
+    const float w3 = dec.W3[i];
+    s->W3[i] = w3;
+    float hi, lo;
+    tc::tf32_split(w3, hi, lo);
+    s->W3hi[i] = hi;
+    s->W3lo[i] = lo;
+  }
+  if (tid == 0) s->b3[0] = dec.b3[0];
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  const uint32_t tbase = s->tmem_base + (uint32_t)(wg * 256);
+  const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr uint32_t kColHi = 0, kColLo = 64, kColD = 128;
+  const uint32_t w2_hi = tc::smem_u32(s->w2_hi), w2_lo = tc::smem_u32(s->w2_lo);
+  const uint32_t w2t_hi = tc::smem_u32(s->w2t_hi), w2t_lo = tc::smem_u32(s->w2t_lo);
+  uint64_t* bar = &s->bar[wg];
+  uint32_t parity = 0;
+
+  const FieldGeom g = field_geom(fl);
+  const bool eik_on = m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f;
+  const bool eik_filter = m.cfg.eik_trunc_dist >= 0.f;
+  const float n_den = (float)(m.cfg.n_total > 0 ? m.cfg.n_total : m.N);
+  const float invN = 1.0f / n_den;
+  float n_eik = n_den;
+  if (eik_on && eik_filter) n_eik = (float)(*m.eik_count);
+  const float inv_neik = 1.0f / n_eik;
+
+  float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
+  const int64_t num_tiles = (m.N + 127) / 128;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + wg; tile < num_tiles; tile += (int64_t)gridDim.x * 2) {
+    const int64_t n = tile * 128 + wtid;
+    const bool active = n < m.N;
+    float p[3] = {0.f, 0.f, 0.f}, xn[3];
+    if (active) load_point(m.x, fr, n, p);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
+    float f[F], dfx[F], dfy[F], dfz[F];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if (!active || ((fl.ignore_mask >> l) & 1u)) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
+      } else {
+        Cell c = level_cell(fl.level[l], xn);
+        gather_level<C, true>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+      }
+    }
+    // ---- layer 1 (SIMT): h1 = relu(W1 f + b1) -> split -> TMEM --------------------------------
+    float2 fp[F / 2];
+#pragma unroll
+    for (int i = 0; i < F / 2; ++i) fp[i] = make_float2(f[2 * i], f[2 * i + 1]);
+    unsigned m1[2] = {0u, 0u};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = half * 32 + i;
+        float2 a0 = make_float2(0.f, 0.f);
+        const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
+#pragma unroll
+        for (int q = 0; q < F / 4; ++q) {
+          float4 w0 = r0[q];
+          a0 = ffma2(make_float2(w0.x, w0.y), fp[2 * q], a0);
+          a0 = ffma2(make_float2(w0.z, w0.w), fp[2 * q + 1], a0);
+        }
+        const float x0 = (a0.x + a0.y) + s->b1[k];
+        m1[half] |= (x0 > 0.f ? 1u : 0u) << i;
+        float h, lw;
+        tc::tf32_split(fmaxf(x0, 0.f), h, lw);
+        hi[i] = __float_as_uint(h);
+        lo[i] = __float_as_uint(lw);
+      }
+      tc::tmem_st32(lane_base + kColHi + half * 32, hi);
+      tc::tmem_st32(lane_base + kColLo + half * 32, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    wg_barrier(wg);
+    if (wtid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32(tbase + kColD, tbase + kColHi, tbase + kColLo, w2_hi, w2_lo);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, parity);
+    parity ^= 1;
+    tc::fence_after_sync();
+    // ---- layer 2 epilogue + layer 3: sdf = W3 relu(h2 + b2) + b3 ; t = D2 W3^T -> TMEM -----------
+    float pred = s->b3[0];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t d[32];
+      tc::tmem_ld32(lane_base + kColD + half * 32, d);
+      tc::wait_ld();
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int j = half * 32 + i;
+        const float h2 = __uint_as_float(d[i]) + s->b2[j];
+        const bool on = h2 > 0.f;
+        pred = fmaf(s->W3[j], fmaxf(h2, 0.f), pred);
+        hi[i] = on ? __float_as_uint(s->W3hi[j]) : 0u;
+        lo[i] = on ? __float_as_uint(s->W3lo[j]) : 0u;
+      }
+      tc::tmem_st32(lane_base + kColHi + half * 32, hi);
+      tc::tmem_st32(lane_base + kColLo + half * 32, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    wg_barrier(wg);
+    if (wtid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32(tbase + kColD, tbase + kColHi, tbase + kColLo, w2t_hi, w2t_lo);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, parity);
+    parity ^= 1;
+    tc::fence_after_sync();
+    // ---- g1 = D1 (W2^T t) ; J = W1^T g1 (SIMT) ---------------------------------------------------
+    float2 Jp[F / 2];
+#pragma unroll
+    for (int i = 0; i < F / 2; ++i) Jp[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t d[32];
+      tc::tmem_ld32(lane_base + kColD + half * 32, d);
+      tc::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = half * 32 + i;
+        const float e = ((m1[half] >> i) & 1u) ? __uint_as_float(d[i]) : 0.f;
+        const float2 ee = make_float2(e, e);
+        const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
+#pragma unroll
+        for (int q = 0; q < F / 4; ++q) {
+          float4 w0 = r0[q];
+          Jp[2 * q] = ffma2(make_float2(w0.x, w0.y), ee, Jp[2 * q]);
+          Jp[2 * q + 1] = ffma2(make_float2(w0.z, w0.w), ee, Jp[2 * q + 1]);
+        }
+      }
+    }
+    float J[F];
+#pragma unroll
+    for (int i = 0; i < F / 2; ++i) J[2 * i] = Jp[i].x, J[2 * i + 1] = Jp[i].y;
+
+    if (active) {
+      if (m.sdf_out) m.sdf_out[n] = pred;
+      const float gt = m.gt_sdf[n];
+      float a = 0.f;
+      if (m.gt_valid[n]) {
+        const float w = m.weights ? m.weights[n] : 1.f;
+        const float e = pred - gt;
+        if (m.cfg.loss_type == 0) {
+          acc_sdf += w * fabsf(e);
+          a += m.cfg.weight_sdf * w * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
+        } else {
+          acc_sdf += w * e * e;
+          a += m.cfg.weight_sdf * w * 2.f * e;
+        }
+      }
+      if (m.cfg.weight_fs != 0.f && m.gt_sign[n] == 1.f) {
+        const float up = fmaxf(pred - gt, 0.f), lo = fmaxf(m.cfg.trunc_dist - pred, 0.f);
+        acc_fs += fmaxf(up, lo);
+        if (up > lo) a += m.cfg.weight_fs;
+        else if (lo > up) a -= m.cfg.weight_fs;
+      }
+      a *= invN * m.cfg.grad_scale;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (eik_on && (!eik_filter || fabsf(gt) < m.cfg.eik_trunc_dist)) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+          for (int i = 0; i < C; ++i) {
+            sx = fmaf(J[l * C + i], dfx[l * C + i], sx);
+            sy = fmaf(J[l * C + i], dfy[l * C + i], sy);
+            sz = fmaf(J[l * C + i], dfz[l * C + i], sz);
+          }
+          gx = fmaf(sx, (float)fl.level[l].X * g.inv_len[0], gx);
+          gy = fmaf(sy, (float)fl.level[l].Y * g.inv_len[1], gy);
+          gz = fmaf(sz, (float)fl.level[l].Z * g.inv_len[2], gz);
+        }
+        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float e = nrm - 1.f;
+        acc_eik += e * e;
+        if (nrm > 0.f) {
+          const float k = m.cfg.weight_eik * m.cfg.grad_scale * 2.f * e * inv_neik / nrm;
+          v[0] = k * gx, v[1] = k * gy, v[2] = k * gz;
+        }
+      }
+      if (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          if (((fl.ignore_mask >> l) & 1u) || !fl.level[l].grad) continue;
+          const miso_level_t& lv = fl.level[l];
+          Cell c = level_cell(lv, xn);
+          float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
+          scatter_level<C>(lv, c, a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
+        }
+      }
+    }
+  }
+  float s0 = block_sum(acc_sdf, red);
+  float s1 = block_sum(acc_fs, red);
+  float s2 = block_sum(acc_eik, red);
+  if (threadIdx.x == 0) {
+    m.partials[blockIdx.x * 4 + 0] = s0;
+    m.partials[blockIdx.x * 4 + 1] = s1;
+    m.partials[blockIdx.x * 4 + 2] = s2;
+    m.partials[blockIdx.x * 4 + 3] = 0.f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(s->tmem_base, 512);
+}
+
 __global__ void mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
                                         miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out) {
   // fixed-order reduction => deterministic loss values
@@ -665,6 +944,16 @@ static int blocks_for(K kernel, size_t smem, int64_t N) {
     }                                                                              \
   } while (0)
 
+// MISO_MLP=simt forces the FP32 SIMT decoder; default is the tcgen05 (3xTF32) decoder
+static bool use_tensor_cores() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MISO_MLP");
+    cached = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 static miso_frames_t frames_or_none(const miso_frames_t* fr) {
   miso_frames_t z;
   z.ids = nullptr, z.R = nullptr, z.t = nullptr, z.num_frames = 0;
@@ -765,13 +1054,23 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
   int nblocks = 0;
-  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
-    constexpr size_t smem = sizeof(DecoderSmem<L * C>);
-    auto k = mapping_step_kernel<L, C>;
-    nblocks = blocks_for(k, smem, N);
-    if ((int64_t)nblocks * 4 > miso_mapping_workspace_floats()) nblocks = (int)(miso_mapping_workspace_floats() / 4);
-    k<<<nblocks, kThreads, smem, s>>>(*field, *dec, fr, m);
-  });
+  if (use_tensor_cores()) {
+    MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+      constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
+      auto k = mapping_step_tc_kernel<L, C>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      nblocks = grid_for((N + 255) / 256, 1, sm_count());
+      k<<<nblocks, kTcThreads, smem, s>>>(*field, *dec, fr, m);
+    });
+  } else {
+    MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+      constexpr size_t smem = sizeof(DecoderSmem<L * C>);
+      auto k = mapping_step_kernel<L, C>;
+      nblocks = blocks_for(k, smem, N);
+      if ((int64_t)nblocks * 4 > miso_mapping_workspace_floats()) nblocks = (int)(miso_mapping_workspace_floats() / 4);
+      k<<<nblocks, kThreads, smem, s>>>(*field, *dec, fr, m);
+    });
+  }
   if (int e = check_launch("mapping_step")) return e;
   mapping_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nblocks, N, *cfg, eik_count, loss_out);
   return check_launch("mapping_finalize");
