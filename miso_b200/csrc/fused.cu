@@ -555,36 +555,213 @@ __global__ void __launch_bounds__(kThreads, MISO_MAP_MIN_BLOCKS)
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel: whole mapping step with the two 64x64 decoder layers on the tensor cores (tcgen05, 3xTF32)
+// Decoder on the tensor cores (tcgen05, 3xTF32).
 //
-// CTA = 2 warpgroups x 128 threads; a warpgroup owns one 128-point tile at a time (thread <-> point <->
-// TMEM lane).  Per tile: gather + layer 1 on SIMT -> h1 split hi/lo into TMEM -> 24 x tcgen05.mma with
-// W2 (shared memory, canonical layout) -> thread reads its row of h2 from TMEM: ReLU, W3 dot, mask ->
-// t = D2 W3^T split into TMEM -> 24 x tcgen05.mma with W2^T -> thread reads g1, applies D1, J = W1^T g1
-// on SIMT -> grad_x sdf, loss terms, one scatter.  The two warpgroups interleave: while one waits for
-// its MMAs the other gathers / scatters.
+// CTA = 4 warpgroups x 128 threads; a warpgroup owns one 128-point tile at a time (thread <-> point <->
+// TMEM lane).  Per tile: gather + layer 1 on SIMT -> h1 split: hi into TMEM (64 columns), lo into
+// shared memory (canonical K-major operand) -> 24 x tcgen05.mma against W2 -> each thread reads its row
+// of h2 from TMEM: bias, ReLU, W3 dot, mask -> t = D2 W3^T split the same way -> 24 x tcgen05.mma
+// against W2^T -> thread reads g1, applies D1, J = W1^T g1 on SIMT.  TMEM per tile = 64 (A_hi) + 64 (D)
+// columns, so four tiles are in flight per SM (16 warps) and the warpgroups hide each other's MMA,
+// gather and scatter latency.
 // ---------------------------------------------------------------------------------------------
+constexpr int kTcWgs = 4;
+constexpr int kTcThreads = kTcWgs * 128;
+constexpr int kTcABytes = tc::kTileM * tc::kK * 4;  // one A_lo operand: 32 KB
+
 template <int F>
 struct TcSmem {
   alignas(128) unsigned char w2_hi[tc::kWeightBytes];
   alignas(128) unsigned char w2_lo[tc::kWeightBytes];
   alignas(128) unsigned char w2t_hi[tc::kWeightBytes];
   alignas(128) unsigned char w2t_lo[tc::kWeightBytes];
+  alignas(128) unsigned char a_lo[kTcWgs][kTcABytes];
   alignas(16) float W1[H * F];
   alignas(16) float b1[H];
-  alignas(16) float b2[H];
-  alignas(16) float W3[H];
-  alignas(16) float W3hi[H];
-  alignas(16) float W3lo[H];
+  alignas(16) float4 ep[H];  // {b2, W3, tf32_hi(W3), tf32_lo(W3)} per hidden unit
   float b3[4];
-  uint64_t bar[2];
+  uint64_t bar[kTcWgs];
   uint32_t tmem_base;
 };
 
-constexpr int kTcThreads = 256;
+template <int F>
+struct TcTile {
+  TcSmem<F>* s;
+  uint32_t a_tmem;      // TMEM address of A_hi (lane 0 of this warpgroup's slice)
+  uint32_t d_tmem;      // TMEM address of D
+  uint32_t lane_bits;   // this warp's lane quarter, already shifted
+  uint32_t a_lo_smem;   // shared-memory address of this warpgroup's A_lo operand
+  unsigned char* a_lo_row;  // this thread's row inside it
+  uint64_t* bar;
+  uint32_t parity;
+  int wg, wtid;
+};
 
 __device__ __forceinline__ void wg_barrier(int wg) {
   asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "r"(128) : "memory");
+}
+
+// one-time CTA setup: TMEM allocation, barriers, weights in canonical layout.  Ends with a CTA barrier.
+template <int F>
+__device__ __forceinline__ TcTile<F> tc_setup(unsigned char* smem_raw, const miso_decoder_t& dec) {
+  TcSmem<F>* s = reinterpret_cast<TcSmem<F>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc(&s->tmem_base, 512);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kTcWgs; ++i) tc::mbar_init(&s->bar[i], 1);
+    tc::fence_mbar_init();
+  }
+  tc::stage_weights(dec.W2, false, s->w2_hi, s->w2_lo, tid, kTcThreads);   // B[n=j][k] = W2[j][k]
+  tc::stage_weights(dec.W2, true, s->w2t_hi, s->w2t_lo, tid, kTcThreads);  // B[n=k][j] = W2[j][k]
+  for (int i = tid; i < H * F; i += kTcThreads) s->W1[i] = dec.W1[i];
+  for (int i = tid; i < H; i += kTcThreads) {
+    s->b1[i] = dec.b1[i];
+    const float w3 = dec.W3[i];
+    float hi, lo;
+    tc::tf32_split(w3, hi, lo);
+    s->ep[i] = make_float4(dec.b2[i], w3, hi, lo);
+  }
+  if (tid == 0) s->b3[0] = dec.b3[0];
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  TcTile<F> t;
+  t.s = s;
+  t.wg = tid >> 7;
+  t.wtid = tid & 127;
+  const uint32_t tbase = s->tmem_base + (uint32_t)(t.wg * 128);
+  t.a_tmem = tbase;
+  t.d_tmem = tbase + 64;
+  t.lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+  t.a_lo_smem = tc::smem_u32(s->a_lo[t.wg]);
+  t.a_lo_row = s->a_lo[t.wg] + tc::a_row_offset(t.wtid);
+  t.bar = &s->bar[t.wg];
+  t.parity = 0;
+  return t;
+}
+
+template <int F>
+__device__ __forceinline__ void tc_teardown(const TcTile<F>& t) {
+  tc::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(t.s->tmem_base, 512);
+}
+
+// store 16 hidden values of this thread's row: hi -> TMEM columns [16q,16q+16), lo -> shared memory
+__device__ __forceinline__ void tc_store_chunk(uint32_t a_tmem_lane, unsigned char* a_lo_row, int q,
+                                               const uint32_t (&hi)[16], const float (&lo)[16]) {
+  tc::tmem_st16(a_tmem_lane + q * 16, hi);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<float4*>(a_lo_row + (q * 4 + c) * tc::kLBO) =
+        make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+}
+
+// whole-warpgroup collective: publish A (TMEM + smem), run the 24 MMAs against (b_hi, b_lo), wait for D
+template <int F>
+__device__ __forceinline__ void tc_gemm(TcTile<F>& t, uint32_t b_hi, uint32_t b_lo) {
+  tc::wait_st();
+  tc::fence_proxy_async();   // generic-proxy STS of A_lo -> visible to the tensor core (async proxy)
+  tc::fence_before_sync();
+  wg_barrier(t.wg);
+  if (t.wtid == 0) {
+    tc::fence_after_sync();
+    tc::issue_gemm_3xtf32_mixed(t.d_tmem, t.a_tmem, t.a_lo_smem, b_hi, b_lo);
+    tc::mma_commit(t.bar);
+  }
+  tc::mbar_wait(t.bar, t.parity);
+  t.parity ^= 1;
+  tc::fence_after_sync();
+}
+
+// MLP forward (+ Jacobian wrt the F inputs) for this thread's point.  Must be called by all 128 threads
+// of the warpgroup (inactive points pass zeros).
+template <int F, bool kJac>
+__device__ __forceinline__ float decoder_tc(TcTile<F>& t, const float (&f)[F], float (&J)[F]) {
+  TcSmem<F>* s = t.s;
+  const uint32_t a_lane = t.a_tmem + t.lane_bits, d_lane = t.d_tmem + t.lane_bits;
+  float2 fp[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) fp[i] = make_float2(f[2 * i], f[2 * i + 1]);
+  // ---- layer 1 (SIMT): h1 = relu(W1 f + b1) ------------------------------------------------------
+  unsigned m1[2] = {0u, 0u};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t hi[16];
+    float lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = q * 16 + i;
+      float2 a0 = make_float2(s->b1[k], 0.f);
+      const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
+#pragma unroll
+      for (int c = 0; c < F / 4; ++c) {
+        float4 w0 = r0[c];
+        a0 = ffma2(make_float2(w0.x, w0.y), fp[2 * c], a0);
+        a0 = ffma2(make_float2(w0.z, w0.w), fp[2 * c + 1], a0);
+      }
+      const float x0 = a0.x + a0.y;
+      m1[q >> 1] |= (x0 > 0.f ? 1u : 0u) << ((q & 1) * 16 + i);
+      float h;
+      tc::tf32_split(fmaxf(x0, 0.f), h, lo[i]);
+      hi[i] = __float_as_uint(h);
+    }
+    tc_store_chunk(a_lane, t.a_lo_row, q, hi, lo);
+  }
+  tc_gemm(t, tc::smem_u32(s->w2_hi), tc::smem_u32(s->w2_lo));
+  // ---- layer 2 epilogue + layer 3: sdf = W3 relu(h2 + b2) + b3 ; t = D2 W3^T ----------------------
+  float pred = s->b3[0];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t d[16];
+    tc::tmem_ld16(d_lane + q * 16, d);
+    tc::wait_ld();
+    uint32_t hi[16];
+    float lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 e = s->ep[q * 16 + i];
+      const float h2 = __uint_as_float(d[i]) + e.x;
+      const bool on = h2 > 0.f;
+      pred = fmaf(e.y, fmaxf(h2, 0.f), pred);
+      hi[i] = on ? __float_as_uint(e.z) : 0u;
+      lo[i] = on ? e.w : 0.f;
+    }
+    if constexpr (kJac) tc_store_chunk(a_lane, t.a_lo_row, q, hi, lo);
+  }
+  if constexpr (!kJac) {
+    tc::fence_before_sync();  // D is overwritten by the next tile's MMA only after the next barrier
+    return pred;
+  }
+  tc_gemm(t, tc::smem_u32(s->w2t_hi), tc::smem_u32(s->w2t_lo));
+  // ---- g1 = D1 (W2^T t) ; J = W1^T g1 (SIMT) --------------------------------------------------------
+  float2 Jp[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) Jp[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t d[16];
+    tc::tmem_ld16(d_lane + q * 16, d);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = q * 16 + i;
+      const float e = ((m1[q >> 1] >> ((q & 1) * 16 + i)) & 1u) ? __uint_as_float(d[i]) : 0.f;
+      const float2 ee = make_float2(e, e);
+      const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
+#pragma unroll
+      for (int c = 0; c < F / 4; ++c) {
+        float4 w0 = r0[c];
+        Jp[2 * c] = ffma2(make_float2(w0.x, w0.y), ee, Jp[2 * c]);
+        Jp[2 * c + 1] = ffma2(make_float2(w0.z, w0.w), ee, Jp[2 * c + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) J[2 * i] = Jp[i].x, J[2 * i + 1] = Jp[i].y;
+  return pred;
 }
 
 template <int L, int C>
@@ -593,43 +770,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                            const __grid_constant__ miso_frames_t fr, const __grid_constant__ MapArgs m) {
   constexpr int F = L * C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TcSmem<F>* s = reinterpret_cast<TcSmem<F>*>(smem_raw);
   __shared__ float red[32];
-  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127;
-
-  // ---- one-time setup: TMEM, barriers, weights --------------------------------------------------
-  if (warp == 0) tc::tmem_alloc(&s->tmem_base, 512);
-  if (tid == 0) {
-    tc::mbar_init(&s->bar[0], 1);
-    tc::mbar_init(&s->bar[1], 1);
-    tc::fence_mbar_init();
-  }
-  tc::stage_weights(dec.W2, false, s->w2_hi, s->w2_lo, tid, kTcThreads);   // B[n=j][k] = W2[j][k]
-  tc::stage_weights(dec.W2, true, s->w2t_hi, s->w2t_lo, tid, kTcThreads);  // B[n=k][j] = W2[j][k]
-  for (int i = tid; i < H * F; i += kTcThreads) s->W1[i] = dec.W1[i];
-  for (int i = tid; i < H; i += kTcThreads) {
-    s->b1[i] = dec.b1[i];
-    s->b2[i] = dec.b2[i];
-    const float w3 = dec.W3[i];
-    s->W3[i] = w3;
-    float hi, lo;
-    tc::tf32_split(w3, hi, lo);
-    s->W3hi[i] = hi;
-    s->W3lo[i] = lo;
-  }
-  if (tid == 0) s->b3[0] = dec.b3[0];
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-
-  const uint32_t tbase = s->tmem_base + (uint32_t)(wg * 256);
-  const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr uint32_t kColHi = 0, kColLo = 64, kColD = 128;
-  const uint32_t w2_hi = tc::smem_u32(s->w2_hi), w2_lo = tc::smem_u32(s->w2_lo);
-  const uint32_t w2t_hi = tc::smem_u32(s->w2t_hi), w2t_lo = tc::smem_u32(s->w2t_lo);
-  uint64_t* bar = &s->bar[wg];
-  uint32_t parity = 0;
+  TcTile<F> t = tc_setup<F>(smem_raw, dec);
 
   const FieldGeom g = field_geom(fl);
   const bool eik_on = m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f;
@@ -642,8 +784,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
   const int64_t num_tiles = (m.N + 127) / 128;
-  for (int64_t tile = (int64_t)blockIdx.x * 2 + wg; tile < num_tiles; tile += (int64_t)gridDim.x * 2) {
-    const int64_t n = tile * 128 + wtid;
+  for (int64_t tile = (int64_t)blockIdx.x * kTcWgs + t.wg; tile < num_tiles; tile += (int64_t)gridDim.x * kTcWgs) {
+    const int64_t n = tile * 128 + t.wtid;
     const bool active = n < m.N;
     float p[3] = {0.f, 0.f, 0.f}, xn[3];
     if (active) load_point(m.x, fr, n, p);
@@ -660,103 +802,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         gather_level<C, true>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
       }
     }
-    // ---- layer 1 (SIMT): h1 = relu(W1 f + b1) -> split -> TMEM --------------------------------
-    float2 fp[F / 2];
-#pragma unroll
-    for (int i = 0; i < F / 2; ++i) fp[i] = make_float2(f[2 * i], f[2 * i + 1]);
-    unsigned m1[2] = {0u, 0u};
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = half * 32 + i;
-        float2 a0 = make_float2(0.f, 0.f);
-        const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
-#pragma unroll
-        for (int q = 0; q < F / 4; ++q) {
-          float4 w0 = r0[q];
-          a0 = ffma2(make_float2(w0.x, w0.y), fp[2 * q], a0);
-          a0 = ffma2(make_float2(w0.z, w0.w), fp[2 * q + 1], a0);
-        }
-        const float x0 = (a0.x + a0.y) + s->b1[k];
-        m1[half] |= (x0 > 0.f ? 1u : 0u) << i;
-        float h, lw;
-        tc::tf32_split(fmaxf(x0, 0.f), h, lw);
-        hi[i] = __float_as_uint(h);
-        lo[i] = __float_as_uint(lw);
-      }
-      tc::tmem_st32(lane_base + kColHi + half * 32, hi);
-      tc::tmem_st32(lane_base + kColLo + half * 32, lo);
-    }
-    tc::wait_st();
-    tc::fence_before_sync();
-    wg_barrier(wg);
-    if (wtid == 0) {
-      tc::fence_after_sync();
-      tc::issue_gemm_3xtf32(tbase + kColD, tbase + kColHi, tbase + kColLo, w2_hi, w2_lo);
-      tc::mma_commit(bar);
-    }
-    tc::mbar_wait(bar, parity);
-    parity ^= 1;
-    tc::fence_after_sync();
-    // ---- layer 2 epilogue + layer 3: sdf = W3 relu(h2 + b2) + b3 ; t = D2 W3^T -> TMEM -----------
-    float pred = s->b3[0];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t d[32];
-      tc::tmem_ld32(lane_base + kColD + half * 32, d);
-      tc::wait_ld();
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int j = half * 32 + i;
-        const float h2 = __uint_as_float(d[i]) + s->b2[j];
-        const bool on = h2 > 0.f;
-        pred = fmaf(s->W3[j], fmaxf(h2, 0.f), pred);
-        hi[i] = on ? __float_as_uint(s->W3hi[j]) : 0u;
-        lo[i] = on ? __float_as_uint(s->W3lo[j]) : 0u;
-      }
-      tc::tmem_st32(lane_base + kColHi + half * 32, hi);
-      tc::tmem_st32(lane_base + kColLo + half * 32, lo);
-    }
-    tc::wait_st();
-    tc::fence_before_sync();
-    wg_barrier(wg);
-    if (wtid == 0) {
-      tc::fence_after_sync();
-      tc::issue_gemm_3xtf32(tbase + kColD, tbase + kColHi, tbase + kColLo, w2t_hi, w2t_lo);
-      tc::mma_commit(bar);
-    }
-    tc::mbar_wait(bar, parity);
-    parity ^= 1;
-    tc::fence_after_sync();
-    // ---- g1 = D1 (W2^T t) ; J = W1^T g1 (SIMT) ---------------------------------------------------
-    float2 Jp[F / 2];
-#pragma unroll
-    for (int i = 0; i < F / 2; ++i) Jp[i] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t d[32];
-      tc::tmem_ld32(lane_base + kColD + half * 32, d);
-      tc::wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = half * 32 + i;
-        const float e = ((m1[half] >> i) & 1u) ? __uint_as_float(d[i]) : 0.f;
-        const float2 ee = make_float2(e, e);
-        const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
-#pragma unroll
-        for (int q = 0; q < F / 4; ++q) {
-          float4 w0 = r0[q];
-          Jp[2 * q] = ffma2(make_float2(w0.x, w0.y), ee, Jp[2 * q]);
-          Jp[2 * q + 1] = ffma2(make_float2(w0.z, w0.w), ee, Jp[2 * q + 1]);
-        }
-      }
-    }
     float J[F];
-#pragma unroll
-    for (int i = 0; i < F / 2; ++i) J[2 * i] = Jp[i].x, J[2 * i + 1] = Jp[i].y;
+    const float pred = decoder_tc<F, true>(t, f, J);
 
     if (active) {
       if (m.sdf_out) m.sdf_out[n] = pred;
@@ -825,9 +872,64 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     m.partials[blockIdx.x * 4 + 2] = s2;
     m.partials[blockIdx.x * 4 + 3] = 0.f;
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(s->tmem_base, 512);
+  tc_teardown<F>(t);
+}
+
+// fused forward (sdf, jac, gradx) with the tensor-core decoder
+template <int L, int C, bool kJac>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    sdf_forward_tc_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
+                          const __grid_constant__ miso_frames_t fr, const float* __restrict__ x, int64_t N,
+                          float* __restrict__ sdf, float* __restrict__ jac, float* __restrict__ gradx,
+                          float* __restrict__ xw) {
+  constexpr int F = L * C;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcTile<F> t = tc_setup<F>(smem_raw, dec);
+  const FieldGeom g = field_geom(fl);
+  const int64_t num_tiles = (N + 127) / 128;
+  for (int64_t tile = (int64_t)blockIdx.x * kTcWgs + t.wg; tile < num_tiles; tile += (int64_t)gridDim.x * kTcWgs) {
+    const int64_t n = tile * 128 + t.wtid;
+    const bool active = n < N;
+    float p[3] = {0.f, 0.f, 0.f}, xn[3];
+    if (active) load_point(x, fr, n, p);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
+    float f[F], dfx[F], dfy[F], dfz[F];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if (!active || ((fl.ignore_mask >> l) & 1u)) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
+      } else {
+        Cell c = level_cell(fl.level[l], xn);
+        gather_level<C, kJac>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+        if constexpr (kJac) {
+          float kx = (float)fl.level[l].X * g.inv_len[0], ky = (float)fl.level[l].Y * g.inv_len[1],
+                kz = (float)fl.level[l].Z * g.inv_len[2];
+#pragma unroll
+          for (int i = 0; i < C; ++i) dfx[l * C + i] *= kx, dfy[l * C + i] *= ky, dfz[l * C + i] *= kz;
+        }
+      }
+    }
+    float J[F];
+    const float val = decoder_tc<F, kJac>(t, f, J);
+    if (!active) continue;
+    sdf[n] = val;
+    if (xw) xw[3 * n] = p[0], xw[3 * n + 1] = p[1], xw[3 * n + 2] = p[2];
+    if constexpr (kJac) {
+      if (jac) {
+#pragma unroll
+        for (int i = 0; i < F; i += 4) *reinterpret_cast<float4*>(jac + n * F + i) = make_float4(J[i], J[i + 1], J[i + 2], J[i + 3]);
+      }
+      if (gradx) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int i = 0; i < F; ++i) gx = fmaf(J[i], dfx[i], gx), gy = fmaf(J[i], dfy[i], gy), gz = fmaf(J[i], dfz[i], gz);
+        gradx[3 * n] = gx, gradx[3 * n + 1] = gy, gradx[3 * n + 2] = gz;
+      }
+    }
+  }
+  tc_teardown<F>(t);
 }
 
 __global__ void mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
@@ -996,6 +1098,22 @@ extern "C" int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t*
   cudaStream_t s = (cudaStream_t)stream;
   const miso_frames_t fr = frames_or_none(frames);
   const bool want_jac = jac || gradx;
+  if (use_tensor_cores() && N >= 4096) {
+    MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+      constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
+      const int nb = grid_for((N + kTcThreads - 1) / kTcThreads, 1, sm_count());
+      if (want_jac) {
+        auto k = sdf_forward_tc_kernel<L, C, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<nb, kTcThreads, smem, s>>>(*field, *dec, fr, x, N, sdf, jac, gradx, xw);
+      } else {
+        auto k = sdf_forward_tc_kernel<L, C, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<nb, kTcThreads, smem, s>>>(*field, *dec, fr, x, N, sdf, jac, gradx, xw);
+      }
+    });
+    return check_launch("sdf_forward(tc)");
+  }
   MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
     constexpr size_t smem = sizeof(DecoderSmem<L * C>);
     if (want_jac) {
@@ -1059,7 +1177,7 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
       constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
       auto k = mapping_step_tc_kernel<L, C>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      nblocks = grid_for((N + 255) / 256, 1, sm_count());
+      nblocks = grid_for((N + kTcThreads - 1) / kTcThreads, 1, sm_count());
       k<<<nblocks, kTcThreads, smem, s>>>(*field, *dec, fr, m);
     });
   } else {

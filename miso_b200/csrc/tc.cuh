@@ -101,6 +101,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem_d] (+)= A[smem desc] * B[smem desc]   (one K=8 step); issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -119,6 +129,43 @@ __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t tmem
     for (int ks = 0; ks < kK / 8; ++ks)
       mma_tf32_ts(tmem_d, a + ks * 8, make_b_desc(b + ks * 2 * kLBO), idesc, (pass | ks) ? 1u : 0u);
   }
+}
+
+// 3xTF32 product with A_hi in TMEM and A_lo in shared memory (canonical K-major layout, 128 rows):
+// halves the TMEM footprint of a tile (A_hi 64 + D 64 columns) so four tiles fit in the 512 columns.
+__device__ __forceinline__ void issue_gemm_3xtf32_mixed(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t smem_a_lo,
+                                                        uint32_t smem_b_hi, uint32_t smem_b_lo) {
+  const uint32_t idesc = make_idesc();
+#pragma unroll
+  for (int ks = 0; ks < kK / 8; ++ks)
+    mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8, make_b_desc(smem_b_hi + ks * 2 * kLBO), idesc, ks ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < kK / 8; ++ks)
+    mma_tf32_ss(tmem_d, make_b_desc(smem_a_lo + ks * 2 * kLBO), make_b_desc(smem_b_hi + ks * 2 * kLBO), idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < kK / 8; ++ks)
+    mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8, make_b_desc(smem_b_lo + ks * 2 * kLBO), idesc, 1u);
+}
+
+// byte offset of row m's first 16-byte chunk inside a canonical K-major A operand (128 rows x 64)
+__device__ __forceinline__ uint32_t a_row_offset(int m) { return (uint32_t)((m >> 3) * kSBO + (m & 7) * 16); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 // ---- TMEM <-> registers, 32 lanes x 32 columns per call (this warp's lane quarter) ---------------
