@@ -150,6 +150,15 @@ def run_ours(args):
                           device=device)
     dev_batches = [({k: v.to(device) for k, v in mi.items()}, {k: v.to(device) for k, v in gt.items()})
                    for mi, gt in batches]
+    if os.environ.get("MISO_PRESORT", "0") == "1":   # experiment: Morton-ordered batches (not the default)
+        from miso_b200.sorting import morton_order
+        R, t = net.all_kf_poses()
+        sorted_batches = []
+        for mi, gt in dev_batches:
+            perm = morton_order(mi["coords_frame"][0], mi["sample_frame_ids"][0, :, 0], R, t, net._bound_host)
+            sorted_batches.append(({k: v[:, perm].contiguous() for k, v in mi.items()},
+                                   {k: v[:, perm].contiguous() for k, v in gt.items()}))
+        dev_batches = sorted_batches
 
     def barrier():
         torch.cuda.synchronize()

@@ -210,65 +210,74 @@ __device__ __forceinline__ Cell level_cell(const miso_level_t& lv, const float (
 }
 
 // Gather C channels of one level: features f[C] and index-space derivatives d[3][C].
+// Separable evaluation (lerp along x, then y, then z) of the trilinear form and of its three partial
+// derivatives: 22 flops per channel instead of 32 FMAs + 32 corner-weight products.  Out-of-range corners
+// contribute the value 0 (zeros padding, gridsample_cuda.cu:385-441), exactly like masking their weights.
 template <int C, bool kDeriv>
 __device__ __forceinline__ void gather_level(const miso_level_t& lv, const Cell& c, float* __restrict__ f,
                                              float* __restrict__ dfx, float* __restrict__ dfy,
                                              float* __restrict__ dfz) {
-  float w[8];
   long long off[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float wx, wy, wz;
-    axis_w(c, k, wx, wy, wz);
-    bool ok = (c.valid >> k) & 1u;
-    w[k] = ok ? (wx * wy) * wz : 0.f;
-    off[k] = ok ? corner_off(lv, c, k) : 0;
-  }
+  for (int k = 0; k < 8; ++k) off[k] = ((c.valid >> k) & 1u) ? corner_off(lv, c, k) : -1;
 #pragma unroll
   for (int ch = 0; ch < C; ch += 4) {
-    float4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ldg_f4(lv.feat + off[k] + ch);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[8][4];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      acc.x = fmaf(v[k].x, w[k], acc.x);
-      acc.y = fmaf(v[k].y, w[k], acc.y);
-      acc.z = fmaf(v[k].z, w[k], acc.z);
-      acc.w = fmaf(v[k].w, w[k], acc.w);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (off[k] >= 0) t = ldg_f4(lv.feat + off[k] + ch);
+      v[k][0] = t.x, v[k][1] = t.y, v[k][2] = t.z, v[k][3] = t.w;
     }
-    f[ch] = acc.x, f[ch + 1] = acc.y, f[ch + 2] = acc.z, f[ch + 3] = acc.w;
-    if constexpr (kDeriv) {
-      float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ay = ax, az = ax;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float wx, wy, wz;
-        axis_w(c, k, wx, wy, wz);
-        bool ok = (c.valid >> k) & 1u;
-        float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
-        float wdx = ok ? sx * wy * wz : 0.f, wdy = ok ? wx * sy * wz : 0.f, wdz = ok ? wx * wy * sz : 0.f;
-        ax.x = fmaf(v[k].x, wdx, ax.x), ax.y = fmaf(v[k].y, wdx, ax.y), ax.z = fmaf(v[k].z, wdx, ax.z), ax.w = fmaf(v[k].w, wdx, ax.w);
-        ay.x = fmaf(v[k].x, wdy, ay.x), ay.y = fmaf(v[k].y, wdy, ay.y), ay.z = fmaf(v[k].z, wdy, ay.z), ay.w = fmaf(v[k].w, wdy, ay.w);
-        az.x = fmaf(v[k].x, wdz, az.x), az.y = fmaf(v[k].y, wdz, az.y), az.z = fmaf(v[k].z, wdz, az.z), az.w = fmaf(v[k].w, wdz, az.w);
+    for (int e = 0; e < 4; ++e) {
+      float a[4], d[4];
+#pragma unroll
+      for (int yz = 0; yz < 4; ++yz) {
+        d[yz] = v[2 * yz + 1][e] - v[2 * yz][e];
+        a[yz] = fmaf(c.fx, d[yz], v[2 * yz][e]);
       }
-      dfx[ch] = ax.x, dfx[ch + 1] = ax.y, dfx[ch + 2] = ax.z, dfx[ch + 3] = ax.w;
-      dfy[ch] = ay.x, dfy[ch + 1] = ay.y, dfy[ch + 2] = ay.z, dfy[ch + 3] = ay.w;
-      dfz[ch] = az.x, dfz[ch + 1] = az.y, dfz[ch + 2] = az.z, dfz[ch + 3] = az.w;
+      float ay[2], ey[2], dxy[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        ey[z] = a[2 * z + 1] - a[2 * z];
+        ay[z] = fmaf(c.fy, ey[z], a[2 * z]);
+        if constexpr (kDeriv) dxy[z] = fmaf(c.fy, d[2 * z + 1] - d[2 * z], d[2 * z]);
+      }
+      const float ez = ay[1] - ay[0];
+      f[ch + e] = fmaf(c.fz, ez, ay[0]);
+      if constexpr (kDeriv) {
+        dfz[ch + e] = ez;
+        dfy[ch + e] = fmaf(c.fz, ey[1] - ey[0], ey[0]);
+        dfx[ch + e] = fmaf(c.fz, dxy[1] - dxy[0], dxy[0]);
+      }
     }
   }
 }
 
 // Scatter (a*w_c + vi . dw_c/di) * J into one level's gradient buffer; vi is in index space.
+// The per-corner coefficient is built separably:  coef = wz*(wy*(a*wx + vix*sx) + viy*sy*wx) + viz*sz*wx*wy.
 template <int C>
 __device__ __forceinline__ void scatter_level(const miso_level_t& lv, const Cell& c, float a, float vix, float viy,
                                               float viz, const float* __restrict__ J) {
+  const float wx[2] = {1.0f - c.fx, c.fx}, wy[2] = {1.0f - c.fy, c.fy}, wz[2] = {1.0f - c.fz, c.fz};
+  float px[2] = {fmaf(a, wx[0], -vix), fmaf(a, wx[1], vix)};
+  float r[4], q[4];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float sy = dy ? viy : -viy;
+      r[2 * dy + dx] = fmaf(wy[dy], px[dx], sy * wx[dx]);
+      q[2 * dy + dx] = wx[dx] * wy[dy];
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (!((c.valid >> k) & 1u)) continue;
-    float wx, wy, wz;
-    axis_w(c, k, wx, wy, wz);
-    float sx = (k & 1) ? 1.f : -1.f, sy = (k & 2) ? 1.f : -1.f, sz = (k & 4) ? 1.f : -1.f;
-    float coef = a * ((wx * wy) * wz) + vix * (sx * wy * wz) + viy * (wx * sy * wz) + viz * (wx * wy * sz);
+    const int dz = k >> 2;
+    const float sz = dz ? viz : -viz;
+    const float coef = fmaf(wz[dz], r[k & 3], sz * q[k & 3]);
     float* dst = lv.grad + corner_off(lv, c, k);
 #pragma unroll
     for (int ch = 0; ch < C; ch += 4)
@@ -576,9 +585,10 @@ struct TcSmem {
   alignas(128) unsigned char w2t_hi[tc::kWeightBytes];
   alignas(128) unsigned char w2t_lo[tc::kWeightBytes];
   alignas(128) unsigned char a_lo[kTcWgs][kTcABytes];
-  alignas(16) float W1[H * F];
-  alignas(16) float b1[H];
-  alignas(16) float4 ep[H];  // {b2, W3, tf32_hi(W3), tf32_lo(W3)} per hidden unit
+  alignas(16) float W1[H * F];    // [k][i]  (layer 1)
+  alignas(16) float W1T[F * H];   // [i][k]  (Jacobian product, pairs over k)
+  alignas(16) float2 b1p[H];      // {b1, 0}: FFMA2 accumulator seed
+  alignas(16) float2 ep[H];       // {b2, W3} per hidden unit
   float b3[4];
   uint64_t bar[kTcWgs];
   uint32_t tmem_base;
@@ -613,14 +623,23 @@ __device__ __forceinline__ TcTile<F> tc_setup(unsigned char* smem_raw, const mis
     tc::fence_mbar_init();
   }
   tc::stage_weights(dec.W2, false, s->w2_hi, s->w2_lo, tid, kTcThreads);   // B[n=j][k] = W2[j][k]
-  tc::stage_weights(dec.W2, true, s->w2t_hi, s->w2t_lo, tid, kTcThreads);  // B[n=k][j] = W2[j][k]
-  for (int i = tid; i < H * F; i += kTcThreads) s->W1[i] = dec.W1[i];
-  for (int i = tid; i < H; i += kTcThreads) {
-    s->b1[i] = dec.b1[i];
-    const float w3 = dec.W3[i];
+  // backward operand with W3 folded in: B'[n=k][j] = W3[j] * W2[j][k], so A is the exact 0/1 ReLU mask
+  for (int i = tid; i < H * H; i += kTcThreads) {
+    const int k = i / H, j = i % H;
     float hi, lo;
-    tc::tf32_split(w3, hi, lo);
-    s->ep[i] = make_float4(dec.b2[i], w3, hi, lo);
+    tc::tf32_split(dec.W3[j] * dec.W2[j * H + k], hi, lo);
+    const uint32_t off = tc::b_offset(k, j);
+    *reinterpret_cast<float*>(s->w2t_hi + off) = hi;
+    *reinterpret_cast<float*>(s->w2t_lo + off) = lo;
+  }
+  for (int i = tid; i < H * F; i += kTcThreads) {
+    const float w = dec.W1[i];
+    s->W1[i] = w;
+    s->W1T[(i % F) * H + i / F] = w;
+  }
+  for (int i = tid; i < H; i += kTcThreads) {
+    s->b1p[i] = make_float2(dec.b1[i], 0.f);
+    s->ep[i] = make_float2(dec.b2[i], dec.W3[i]);
   }
   if (tid == 0) s->b3[0] = dec.b3[0];
   tc::fence_proxy_async();
@@ -660,15 +679,16 @@ __device__ __forceinline__ void tc_store_chunk(uint32_t a_tmem_lane, unsigned ch
 }
 
 // whole-warpgroup collective: publish A (TMEM + smem), run the 24 MMAs against (b_hi, b_lo), wait for D
-template <int F>
+template <int F, bool kExactA>
 __device__ __forceinline__ void tc_gemm(TcTile<F>& t, uint32_t b_hi, uint32_t b_lo) {
   tc::wait_st();
-  tc::fence_proxy_async();   // generic-proxy STS of A_lo -> visible to the tensor core (async proxy)
+  if constexpr (!kExactA) tc::fence_proxy_async();  // generic-proxy STS of A_lo -> visible to the async proxy
   tc::fence_before_sync();
   wg_barrier(t.wg);
   if (t.wtid == 0) {
     tc::fence_after_sync();
-    tc::issue_gemm_3xtf32_mixed(t.d_tmem, t.a_tmem, t.a_lo_smem, b_hi, b_lo);
+    if constexpr (kExactA) tc::issue_gemm_exactA(t.d_tmem, t.a_tmem, b_hi, b_lo);
+    else tc::issue_gemm_3xtf32_mixed(t.d_tmem, t.a_tmem, t.a_lo_smem, b_hi, b_lo);
     tc::mma_commit(t.bar);
   }
   tc::mbar_wait(t.bar, t.parity);
@@ -694,7 +714,7 @@ __device__ __forceinline__ float decoder_tc(TcTile<F>& t, const float (&f)[F], f
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int k = q * 16 + i;
-      float2 a0 = make_float2(s->b1[k], 0.f);
+      float2 a0 = s->b1p[k];
       const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
 #pragma unroll
       for (int c = 0; c < F / 4; ++c) {
@@ -705,62 +725,62 @@ __device__ __forceinline__ float decoder_tc(TcTile<F>& t, const float (&f)[F], f
       const float x0 = a0.x + a0.y;
       m1[q >> 1] |= (x0 > 0.f ? 1u : 0u) << ((q & 1) * 16 + i);
       float h;
-      tc::tf32_split(fmaxf(x0, 0.f), h, lo[i]);
+      tc::tf32_split_fast(fmaxf(x0, 0.f), h, lo[i]);
       hi[i] = __float_as_uint(h);
     }
     tc_store_chunk(a_lane, t.a_lo_row, q, hi, lo);
   }
-  tc_gemm(t, tc::smem_u32(s->w2_hi), tc::smem_u32(s->w2_lo));
-  // ---- layer 2 epilogue + layer 3: sdf = W3 relu(h2 + b2) + b3 ; t = D2 W3^T ----------------------
+  tc_gemm<F, false>(t, tc::smem_u32(s->w2_hi), tc::smem_u32(s->w2_lo));
+  // ---- layer 2 epilogue + layer 3: sdf = W3 relu(h2 + b2) + b3 ; A <- ReLU mask (exact in tf32) ------
   float pred = s->b3[0];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t d[16];
     tc::tmem_ld16(d_lane + q * 16, d);
     tc::wait_ld();
-    uint32_t hi[16];
-    float lo[16];
+    uint32_t mk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float4 e = s->ep[q * 16 + i];
+      const float2 e = s->ep[q * 16 + i];
       const float h2 = __uint_as_float(d[i]) + e.x;
-      const bool on = h2 > 0.f;
       pred = fmaf(e.y, fmaxf(h2, 0.f), pred);
-      hi[i] = on ? __float_as_uint(e.z) : 0u;
-      lo[i] = on ? e.w : 0.f;
+      mk[i] = h2 > 0.f ? 0x3f800000u : 0u;
     }
-    if constexpr (kJac) tc_store_chunk(a_lane, t.a_lo_row, q, hi, lo);
+    if constexpr (kJac) tc::tmem_st16(a_lane + q * 16, mk);
   }
   if constexpr (!kJac) {
     tc::fence_before_sync();  // D is overwritten by the next tile's MMA only after the next barrier
     return pred;
   }
-  tc_gemm(t, tc::smem_u32(s->w2t_hi), tc::smem_u32(s->w2t_lo));
-  // ---- g1 = D1 (W2^T t) ; J = W1^T g1 (SIMT) --------------------------------------------------------
-  float2 Jp[F / 2];
+  tc_gemm<F, true>(t, tc::smem_u32(s->w2t_hi), tc::smem_u32(s->w2t_lo));
+  // ---- g1 = D1 (W2^T D2 W3^T) ; J = W1^T g1 (SIMT, packed over pairs of hidden units) ----------------
+  float2 Jp[F];
 #pragma unroll
-  for (int i = 0; i < F / 2; ++i) Jp[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < F; ++i) Jp[i] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t d[16];
     tc::tmem_ld16(d_lane + q * 16, d);
     tc::wait_ld();
+    float2 e[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int k = q * 16 + i;
-      const float e = ((m1[q >> 1] >> ((q & 1) * 16 + i)) & 1u) ? __uint_as_float(d[i]) : 0.f;
-      const float2 ee = make_float2(e, e);
-      const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
+    for (int i = 0; i < 8; ++i) {
+      const unsigned bits = m1[q >> 1] >> ((q & 1) * 16 + 2 * i);
+      e[i] = make_float2((bits & 1u) ? __uint_as_float(d[2 * i]) : 0.f, (bits & 2u) ? __uint_as_float(d[2 * i + 1]) : 0.f);
+    }
 #pragma unroll
-      for (int c = 0; c < F / 4; ++c) {
-        float4 w0 = r0[c];
-        Jp[2 * c] = ffma2(make_float2(w0.x, w0.y), ee, Jp[2 * c]);
-        Jp[2 * c + 1] = ffma2(make_float2(w0.z, w0.w), ee, Jp[2 * c + 1]);
+    for (int i = 0; i < F; ++i) {
+      const float4* r0 = reinterpret_cast<const float4*>(s->W1T + i * H + q * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 w0 = r0[c];
+        Jp[i] = ffma2(make_float2(w0.x, w0.y), e[2 * c], Jp[i]);
+        Jp[i] = ffma2(make_float2(w0.z, w0.w), e[2 * c + 1], Jp[i]);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < F / 2; ++i) J[2 * i] = Jp[i].x, J[2 * i + 1] = Jp[i].y;
+  for (int i = 0; i < F; ++i) J[i] = Jp[i].x + Jp[i].y;
   return pred;
 }
 
@@ -788,7 +808,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int64_t n = tile * 128 + t.wtid;
     const bool active = n < m.N;
     float p[3] = {0.f, 0.f, 0.f}, xn[3];
-    if (active) load_point(m.x, fr, n, p);
+    // loss inputs are fetched up front so their latency hides behind the gather and the decoder
+    float gt = 0.f, wgt = 1.f, sgn = 0.f;
+    unsigned char vld = 0;
+    if (active) {
+      load_point(m.x, fr, n, p);
+      gt = m.gt_sdf[n];
+      vld = m.gt_valid[n];
+      sgn = m.gt_sign[n];
+      if (m.weights) wgt = m.weights[n];
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
     float f[F], dfx[F], dfy[F], dfz[F];
@@ -807,10 +836,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     if (active) {
       if (m.sdf_out) m.sdf_out[n] = pred;
-      const float gt = m.gt_sdf[n];
       float a = 0.f;
-      if (m.gt_valid[n]) {
-        const float w = m.weights ? m.weights[n] : 1.f;
+      if (vld) {
+        const float w = wgt;
         const float e = pred - gt;
         if (m.cfg.loss_type == 0) {
           acc_sdf += w * fabsf(e);
@@ -820,7 +848,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           a += m.cfg.weight_sdf * w * 2.f * e;
         }
       }
-      if (m.cfg.weight_fs != 0.f && m.gt_sign[n] == 1.f) {
+      if (m.cfg.weight_fs != 0.f && sgn == 1.f) {
         const float up = fmaxf(pred - gt, 0.f), lo = fmaxf(m.cfg.trunc_dist - pred, 0.f);
         acc_fs += fmaxf(up, lo);
         if (up > lo) a += m.cfg.weight_fs;

@@ -42,6 +42,12 @@ __device__ __forceinline__ void tf32_split(float a, float& hi, float& lo) {
   hi = tf32_rn(a);
   lo = tf32_rn(a - hi);
 }
+// 2-instruction split for the per-point activations: hi = truncate(a) (LOP3), lo = a - hi (exact; the
+// tensor core ignores its low 13 bits).  |error| <= 2^-21 |a|; weights keep the round-to-nearest split.
+__device__ __forceinline__ void tf32_split_fast(float a, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+  lo = a - hi;
+}
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, LBO, SBO in
 // 16-byte units, version 1, SWIZZLE_NONE
@@ -145,6 +151,18 @@ __device__ __forceinline__ void issue_gemm_3xtf32_mixed(uint32_t tmem_d, uint32_
 #pragma unroll
   for (int ks = 0; ks < kK / 8; ++ks)
     mma_tf32_ts(tmem_d, tmem_a_hi + ks * 8, make_b_desc(smem_b_lo + ks * 2 * kLBO), idesc, 1u);
+}
+
+// D = A * (B_hi + B_lo) for an A that is exactly representable in tf32 (0/1 masks): 16 MMAs, A in TMEM only
+__device__ __forceinline__ void issue_gemm_exactA(uint32_t tmem_d, uint32_t tmem_a, uint32_t smem_b_hi,
+                                                  uint32_t smem_b_lo) {
+  const uint32_t idesc = make_idesc();
+#pragma unroll
+  for (int ks = 0; ks < kK / 8; ++ks)
+    mma_tf32_ts(tmem_d, tmem_a + ks * 8, make_b_desc(smem_b_hi + ks * 2 * kLBO), idesc, ks ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < kK / 8; ++ks)
+    mma_tf32_ts(tmem_d, tmem_a + ks * 8, make_b_desc(smem_b_lo + ks * 2 * kLBO), idesc, 1u);
 }
 
 // byte offset of row m's first 16-byte chunk inside a canonical K-major A operand (128 rows x 64)
