@@ -234,6 +234,17 @@ def run_ours(args):
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the e2e run"
 
+    align = None
+    if not args.no_extras:
+        del dev_batches
+        torch.cuda.empty_cache()
+        align = bench_align(device, iters=10, warmup=2, world=world, rank=rank)
+        if world > 1:
+            # pair-sharded: an iteration ends when the slowest rank is done
+            for lv in align.values():
+                lv["ms_per_iter"] = max_over_ranks(lv["ms_per_iter"])
+                lv["iters_per_s"] = 1e3 / lv["ms_per_iter"]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -264,9 +275,14 @@ def run_ours(args):
                      "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
                      "fp32_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12},
         "final_loss_terms": final_loss,
+        "extra": {"align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
+                  "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "
+                  "<= 32 k samples/pair, level 1: <= 4 M samples/pair"},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_arm(steps=2, warmup=1)
+        if not args.no_extras:
+            line["extra"]["align_cpu_baseline"] = cpu_align_arm(iters=1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -306,6 +322,108 @@ def cpu_reference_arm(steps, warmup, sample_points=1 << 18):
             "sec_per_step": sec}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# second half of the metric: latent-space alignment iterations / s (BASELINE.json configs[2])
+# ------------------------------------------------------------------------------------------------
+ALIGN_SUBMAPS = 16
+
+
+def build_align_atlas(device, small=False):
+    """16 ScanNet-submap-shaped GridNets tiled 4x4 with >= 30 % overlap, grids sampled from one smooth latent
+    field at the true poses, then perturbed by ~10 deg / 0.5 m (demo/align_submaps.py:267-273)."""
+    from miso_b200 import synth
+    from miso_b200.models import GridAtlas
+    bound = synth.SCANNET_SUBMAP_BOUND
+    cfg = synth.model_cfg(bound, num_poses=1) if not small else synth.model_cfg(bound, base_cell_size=1.0, per_level_scale=2, num_poses=1)
+    Rt, tt = synth.submap_layout(ALIGN_SUBMAPS, spacing=(12.0, 12.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=10.0, trans_m=0.5)
+    atlas = GridAtlas(cfg, device=device)
+    for i in range(ALIGN_SUBMAPS):
+        atlas.add_submap(torch.tensor(bound), Rp[i], tp[i])
+        sm = atlas.get_submap(i)
+        shapes = [tuple(f.feature.shape) for f in sm.features]
+        feats = synth.fill_submap_from_field(shapes, bound, Rt[i], tt[i], device=device)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(feats[l])
+        sm.lock_feature()
+    return atlas
+
+
+def bench_align(device, iters=10, warmup=2, world=1, rank=0):
+    """align iters/s: one iteration = intersection test + latent loss of every overlapping pair + backward +
+    Adam step on the 15 free submap poses (generic_align_multiple_submaps body, align/base.py:127-159)."""
+    import torch.optim as optim
+    from miso_b200 import dist as mdist
+    from miso_b200.align import AlignBatch
+    atlas = build_align_atlas(device)
+    atlas.precompute_coordinates_for_alignment()
+    pairs = [(s, d) for s in range(ALIGN_SUBMAPS) for d in range(s + 1, ALIGN_SUBMAPS)]
+    mine = [p for i, p in enumerate(pairs) if i % world == rank]
+    out = {}
+    for level in (0, 1):
+        batch = AlignBatch(atlas, mine, level, check_intersection=True)
+        params = []
+        for i in range(1, ALIGN_SUBMAPS):
+            params += list(atlas.params_for_submap_pose(i))
+        opt = optim.Adam([{"params": params, "lr": 1e-2}], lr=1e-2)
+
+        def one_iter():
+            opt.zero_grad()
+            poses = batch.pair_poses()
+            batch.update_intersections(poses)
+            loss = torch.nan_to_num(batch.losses(3000.0, poses)).sum()
+            loss.backward()
+            if world > 1:
+                mdist.allreduce_sum_([p.grad for p in params])
+            opt.step()
+            return loss
+
+        for _ in range(warmup):
+            one_iter()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            last = one_iter()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        n_on = int(batch.enabled[:len(mine)].sum().item()) if mine else 0
+        samples = sum(batch._coords[s].shape[0] for (s, d), en in zip(mine, batch.enabled.tolist()) if en)
+        bytes_pp = 12 + (level + 1) * 16 + (level + 1) * 8 * 16      # coords + cached src feats + dst corners
+        out[f"level{level}"] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "pairs": len(mine), "pairs_overlapping": n_on,
+                                "samples_per_iter": samples, "loss": float(last),
+                                "hbm_gbs_algorithmic": samples * bytes_pp / (ms * 1e-3) / 1e9}
+    return out
+
+
+def cpu_align_arm(iters=1):
+    """Oracle port of the reference's alignment iteration on the host (level 0, same 16-submap layout)."""
+    from miso_b200 import synth
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count())
+    bound = synth.SCANNET_SUBMAP_BOUND
+    shapes = O.level_shapes(bound, 0.5, 5, 2, 4)
+    Rt, tt = synth.submap_layout(ALIGN_SUBMAPS, spacing=(12.0, 12.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=10.0, trans_m=0.5)
+    subs = []
+    for i in range(ALIGN_SUBMAPS):
+        f0 = synth.fill_submap_from_field(shapes[:1], bound, Rt[i], tt[i])[0]
+        subs.append(O.OracleGridNet(bound, [f0, torch.zeros(1, 4, 2, 2, 2)], None))   # level 0 only needs the coarse grid
+    atlas = O.OracleAtlas(subs, Rp, tp)
+    for i, sm in enumerate(subs):
+        coords = O.vertex_positions(sm.features[0].shape, bound)
+        atlas.coords[(i, 0)] = coords
+    # the intersection test uses the finest level's vertices in the reference; bound it with the coarse ones here
+    t0 = time.perf_counter()
+    O.align_multiple_submaps(atlas, level=0, num_iters=iters - 1, lr=1e-2, check_intersection=False)
+    sec = (time.perf_counter() - t0) / iters
+    return {"iters_per_s": 1.0 / sec, "sec_per_iter": sec, "cores": os.cpu_count(), "kind": "port",
+            "sample": "level 0 only (M0 = 32000 samples/pair, 120 pairs, intersection test skipped), 1 iteration"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -331,6 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the alignment half of the metric")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
