@@ -454,7 +454,13 @@ class GridNet(BaseNet):
         """grid_net.py:306-325."""
         spec = self.fused_spec()
         if spec is not None:
-            pred, _ = _field.fused_sdf(x, self.level_tensors(), spec)
+            needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(f.requires_grad for f in self.level_tensors()))
+            if needs_graph:
+                pred, _ = _field.fused_sdf(x, self.level_tensors(), spec)
+            else:
+                # inference / dense queries (utils_sdf.extract_fields): forward only, no Jacobian pass
+                sdf, _, _, _ = _field.sdf_forward_raw(self.level_tensors(), spec, x, want_jac=False, want_gradx=False)
+                pred = sdf.unsqueeze(1)
         else:
             feats = grid_interp_regular(self.features, x, self.ignore_level_)
             pred = grid_decode(feats, x, self.decoder, self.pos_invariant)
@@ -623,6 +629,29 @@ class GridAtlas(BaseNet):
     def get_submap(self, submap_id: int) -> GridNet:
         assert submap_id >= 0 and submap_id < self.num_submaps
         return self.submaps[submap_id]
+
+    def query_feature(self, x_world: torch.Tensor):
+        """grid_atlas.py:374-391: in-bound-masked mean of the submaps' features at world points."""
+        sum_feats = 0
+        sum_weights = 0
+        for submap_id in self.active_submaps:
+            submap = self.get_submap(submap_id)
+            R_world_submap, t_world_submap = self.updated_submap_pose(submap_id)
+            x_submap = utils_geometry.transfrom_points_from(x_world, R_world_submap, t_world_submap)
+            mask_bnd = utils_geometry.coords_in_bound(x_submap, submap.bound)
+            submap_feats = submap.query_feature(x_submap)
+            sum_feats = sum_feats + mask_bnd * submap_feats
+            sum_weights = sum_weights + mask_bnd
+        sum_weights = torch.where(sum_weights == 0, torch.ones_like(sum_weights), sum_weights).float()
+        return sum_feats / sum_weights
+
+    def forward(self, x_world: torch.Tensor, noise_std=0):
+        """grid_atlas.py:393-399: decode the mean feature with submap 0's decoder."""
+        mean_feats = self.query_feature(x_world)
+        pred = grid_decode(mean_feats, None, self.submaps[0].decoder, True)
+        if noise_std > 0:
+            pred = pred + torch.randn(pred.shape, device=x_world.device) * noise_std
+        return pred
 
     def check_submap_intersection(self, src_id: int, dst_id: int, overlap_thresh=1e-2):
         """grid_atlas.py:405-420 (torch ops; the batched kernel version lives in miso_b200.align)."""

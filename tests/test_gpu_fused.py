@@ -218,3 +218,62 @@ def test_full_size_properties():
         ones = [torch.ones_like(f) for f in feats]
         inside = points_in(bound, 2 ** 16, seed=10, scale=0.9).cuda()
         assert rel_err(field.field_features_raw(ones, b, inside), torch.ones(2 ** 16, 8)) < 1e-6
+
+
+def test_tracker_lm_normal_equations_and_step():
+    """Tracker.lm_step (tracker.py:148-212): fused sdf + analytic gradient -> J^T W J, J^T W r, 6x6 solve,
+    against the oracle's restatement (autograd gradient)."""
+    from miso_b200.tracker import Tracker
+    net, _, o2 = make_pair()
+    g = torch.Generator().manual_seed(0)
+    xf = (torch.rand(4000, 3, generator=g) - 0.5) * torch.tensor([2.0, 1.0, 2.0])
+    gt_sdf = torch.randn(4000, 1, generator=g) * 0.05
+    w0 = torch.tensor([[0.1, -0.2, 0.05]])
+    Rwf = O.so3_exp_map(w0)[0]
+    twf = torch.tensor([[0.1], [0.05], [-0.1]])
+    net.set_initial_kf_pose(0, Rwf, twf, kf_key="KF0")
+    for loss_type in ("L2", "GM"):
+        tr = Tracker(net, loss_type=loss_type, gm_scale_sdf=0.1, lm_lambda=1e-4)
+        H, b, fov = tr.normal_equations(xf.cuda(), gt_sdf.cuda(), Rwf.cuda(), twf.cuda())
+        Ho, bo, do = O.lm_normal_equations(o2, xf, gt_sdf, Rwf, twf, loss_type=loss_type, gm_scale=0.1, lm_lambda=1e-4)
+        assert rel_err(H, Ho) < TOL_G and rel_err(b, bo) < TOL_G
+        assert rel_err(torch.linalg.solve(H, -b), do) < 1e-3   # 6x6 solve amplifies by cond(H)
+    mi = {"coords_frame": xf[None].cuda(), "sample_frame_ids": torch.zeros(1, 4000, 1, dtype=torch.long).cuda()}
+    gt = {"sdf": gt_sdf[None].cuda(), "sdf_valid": torch.ones(1, 4000, 1, dtype=torch.bool).cuda()}
+    info = tr.lm_step(0, mi, gt)
+    assert rel_err(net.rotation_corrections[0], do[:3, 0]) < 1e-3
+    assert rel_err(net.translation_corrections[0], do[3:]) < 1e-3
+    assert 0.0 <= info["fov_overlap"] <= 1.0
+
+
+def test_inference_forward_and_atlas_query():
+    """Forward-only path (no Jacobian pass) and GridAtlas.query_feature's masked mean (grid_atlas.py:374-391)."""
+    from miso_b200.models import GridAtlas
+    net, o1, _ = make_pair()
+    x = points_in(SMALL_BOUND, 20000, seed=11)
+    with torch.no_grad():
+        y = net(x.cuda())
+    assert rel_err(y, o1(x)) < TOL_F
+    atlas = GridAtlas(synth.model_cfg(SMALL_BOUND, num_poses=1), device="cuda")
+    ors = []
+    for i in range(2):
+        R = O.so3_exp_map(torch.tensor([[0.0, 0.1 * i, 0.0]]))[0]
+        t = torch.tensor([[1.0 * i], [0.0], [0.5 * i]])
+        atlas.add_submap(torch.tensor(SMALL_BOUND), R, t)
+        gsm = torch.Generator().manual_seed(i)
+        feats = [torch.randn(f.feature.shape, generator=gsm) * 0.1 for f in atlas.get_submap(i).features]
+        with torch.no_grad():
+            for l in range(2):
+                atlas.get_submap(i).features[l].feature.copy_(feats[l].cuda())
+        ors.append((O.OracleGridNet(SMALL_BOUND, feats, None), R, t))
+    xw = points_in(SMALL_BOUND, 5000, seed=12, scale=1.3)
+    with torch.no_grad():
+        got = atlas.query_feature(xw.cuda())
+    sf, sw = 0, 0
+    for om, R, t in ors:
+        xs = O.transfrom_points_from(xw, R, t)
+        m = O.coords_in_bound(xs, om.bound)
+        sf = sf + m * om.query_feature(xs)
+        sw = sw + m
+    sw = torch.where(sw == 0, torch.ones_like(sw), sw).float()
+    assert rel_err(got, sf / sw) < TOL_F
