@@ -197,32 +197,14 @@ def run_ours(args):
     final_loss = [float(v) for v in last.tolist()]
 
     # ---------------- end-to-end through the trainer API with host buffers ----------------
-    copy_stream = torch.cuda.Stream(device)
     loss_host = torch.zeros(args.steps + args.warmup, 4).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for d in batches[0] for v in d.values())
 
-    def stage(i):
-        mi, gt = batches[i % NUM_HOST_BATCHES]
-        with torch.cuda.stream(copy_stream):
-            dmi = {k: v.to(device, non_blocking=True) for k, v in mi.items()}
-            dgt = {k: v.to(device, non_blocking=True) for k, v in gt.items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return dmi, dgt, ev
-
     def e2e_loop(n, offset):
-        cur = torch.cuda.current_stream(device)
-        nxt = stage(offset)
-        for i in range(n):
-            dmi, dgt, ev = nxt
-            if i + 1 < n:
-                nxt = stage(offset + i + 1)      # H2D of batch i+1 overlaps step i
-            cur.wait_event(ev)
-            for d in (dmi, dgt):
-                for v in d.values():
-                    v.record_stream(cur)
-            terms = trainer.train_step(dmi, dgt)
-            loss_host[offset + i].copy_(terms, non_blocking=True)   # D2H read of the step's loss
+        # public API: GridTrainer.train_host_batches -- pinned host batches in, H2D on a copy stream
+        # overlapping the previous step, loss terms read back D2H every step
+        trainer.train_host_batches((batches[(offset + i) % NUM_HOST_BATCHES] for i in range(n)),
+                                   loss_sink=loss_host[offset:offset + n])
 
     e2e_loop(args.warmup, 0)
     barrier()

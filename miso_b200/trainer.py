@@ -30,41 +30,61 @@ def prepare_batch(model_input, gt, device="cuda:0"):
 
 
 class HostBatchStager:
-    """Double-buffered pinned-host -> device staging of (model_input, gt) batches."""
+    """Double-buffered host -> device staging of (model_input, gt) batches on a copy stream.
 
-    def __init__(self, device):
+    Device buffers are allocated once per slot (no allocator traffic, no record_stream bookkeeping in the
+    loop); `stage()` enqueues the H2D copies of a batch into the free slot, `acquire()` makes the compute
+    stream wait for them, `release()` marks the slot reusable once the step that consumed it has been
+    enqueued.  With pinned host tensors (DataLoader(pin_memory=True)) the copy of batch i+1 overlaps step i."""
+
+    def __init__(self, device, slots: int = 2):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
-        self._slots = [None, None]
-        self._events = [None, None]
-        self._turn = 0
+        self.slots = [None] * slots
+        self.ready = [None] * slots      # copy-stream event: data landed
+        self.free = [None] * slots       # compute-stream event: consumer enqueued
         self.h2d_bytes = 0
+        self._next = 0
 
-    def stage(self, batch: Batch) -> Tuple[Batch, torch.cuda.Event]:
-        """Start the async copy of `batch` (CPU tensors, ideally pinned); returns device tensors and the
-        event the compute stream must wait on."""
-        slot = self._turn
-        self._turn ^= 1
+    def _buffers(self, slot, batch):
+        bufs = self.slots[slot]
         model_input, gt = batch
+        ok = bufs is not None and all(k in bufs[0] and bufs[0][k].shape == v.shape and bufs[0][k].dtype == v.dtype
+                                      for k, v in model_input.items()) and \
+            all(k in bufs[1] and bufs[1][k].shape == v.shape and bufs[1][k].dtype == v.dtype for k, v in gt.items())
+        if not ok:
+            bufs = ({k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in model_input.items()},
+                    {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in gt.items()})
+            self.slots[slot] = bufs
+        return bufs
+
+    def stage(self, batch: Batch) -> int:
+        """Enqueue the async copy of `batch` (CPU tensors, ideally pinned) into the next slot; returns it."""
+        slot = self._next
+        self._next = (self._next + 1) % len(self.slots)
+        bufs = self._buffers(slot, batch)
         nbytes = 0
         with torch.cuda.stream(self.stream):
-            if self._events[slot] is not None:
-                self.stream.wait_event(self._events[slot])  # previous consumer of this slot is done
-            dev_in, dev_gt = {}, {}
-            for src, dst in ((model_input, dev_in), (gt, dev_gt)):
+            if self.free[slot] is not None:
+                self.stream.wait_event(self.free[slot])
+            for src, dst in zip(batch, bufs):
                 for k, v in src.items():
-                    if not v.is_pinned():
-                        v = v.pin_memory()
-                    dst[k] = v.to(self.device, non_blocking=True)
+                    dst[k].copy_(v, non_blocking=True)
                     nbytes += v.numel() * v.element_size()
-            ready = torch.cuda.Event()
-            ready.record(self.stream)
-        self._slots[slot] = (dev_in, dev_gt)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[slot] = ev
         self.h2d_bytes = nbytes
-        return (dev_in, dev_gt), ready
+        return slot
 
-    def release(self, slot_event: torch.cuda.Event):
-        self._events[self._turn ^ 1] = slot_event
+    def acquire(self, slot: int) -> Batch:
+        torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        return self.slots[slot]
+
+    def release(self, slot: int):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev
 
 
 class GridTrainer:
@@ -146,6 +166,30 @@ class GridTrainer:
         terms = self.train_step(model_input, gt)
         self.train_dict["loss"].append(terms)
         return terms
+
+    def train_host_batches(self, batches, loss_sink: Optional[torch.Tensor] = None):
+        """Run one fused step per host batch with the copy of batch i+1 overlapping step i (the pipelined
+        form of train_epoch for batches that live in pinned host memory).  When `loss_sink` (a pinned
+        (len, 4) tensor) is given, every step's loss terms are read back device->host asynchronously."""
+        if not hasattr(self, "_stager"):
+            self._stager = HostBatchStager(self.device)
+        st = self._stager
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        slot = st.stage(first)
+        i = 0
+        while slot is not None:
+            nxt = next(it, None)
+            nslot = st.stage(nxt) if nxt is not None else None
+            model_input, gt = st.acquire(slot)
+            terms = self.train_step(model_input, gt)
+            st.release(slot)
+            if loss_sink is not None:
+                loss_sink[i].copy_(terms, non_blocking=True)
+            slot = nslot
+            i += 1
 
     def train(self):
         for epoch in range(self.epochs):
