@@ -349,10 +349,11 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
         params = []
         for i in range(1, ALIGN_SUBMAPS):
             params += list(atlas.params_for_submap_pose(i))
-        opt = optim.Adam([{"params": params, "lr": 1e-2}], lr=1e-2)
+        use_graph = world == 1      # the pair-sharded run keeps the NCCL all_reduce outside a graph
+        opt = optim.Adam([{"params": params, "lr": 1e-2}], lr=1e-2, capturable=use_graph)
 
         def one_iter():
-            opt.zero_grad()
+            opt.zero_grad(set_to_none=False)
             poses = batch.pair_poses()
             batch.update_intersections(poses)
             loss = torch.nan_to_num(batch.losses(3000.0, poses)).sum()
@@ -362,13 +363,29 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
             opt.step()
             return loss
 
-        for _ in range(warmup):
-            one_iter()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 3)):
+                one_iter()
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        graph = None
+        if use_graph:
+            # one whole iteration (poses, intersections, alignment kernel, backward, Adam) as a CUDA graph
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = one_iter().detach()
+            graph.replay()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            last = one_iter()
+            if graph is not None:
+                graph.replay()
+                last = static_loss
+            else:
+                last = one_iter()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
@@ -376,7 +393,7 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
         samples = sum(batch._coords[s].shape[0] for (s, d), en in zip(mine, batch.enabled.tolist()) if en)
         bytes_pp = 12 + (level + 1) * 16 + (level + 1) * 8 * 16      # coords + cached src feats + dst corners
         out[f"level{level}"] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "pairs": len(mine), "pairs_overlapping": n_on,
-                                "samples_per_iter": samples, "loss": float(last),
+                                "samples_per_iter": samples, "loss": float(last), "cuda_graph": graph is not None,
                                 "hbm_gbs_algorithmic": samples * bytes_pp / (ms * 1e-3) / 1e9}
     return out
 

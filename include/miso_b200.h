@@ -185,7 +185,7 @@ int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, cons
 typedef struct miso_align_pair {
   int32_t src, dst;        /* indices into fields[] */
   int32_t levels_used;     /* level+1: channels [0, C*levels_used) enter the residual (miso.py:133-134) */
-  int32_t reserved;
+  int32_t reserved;        /* miso_align_intersections: output slot / pose row of this pair */
   const float* p;          /* (M,3) src-frame samples: GridAtlas.coordinates_for_alignment (grid_atlas.py:581-587) */
   int64_t M;
   const float* fsrc;       /* optional (M,K) cached f_src(p): constant across iterations */
@@ -201,12 +201,15 @@ int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_
                      int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t want_gn,
                      miso_stream_t stream);
 
-/* check_submap_intersection (grid_atlas.py:405-420) for all pairs in one launch: for pair i counts
- * the src vertices (pairs[i].p, M) that land inside fields[dst].bound; enabled_out[i] =
- * (count / M > overlap_thresh).  counts_out (num_pairs) int64 optional. */
+/* check_submap_intersection (grid_atlas.py:405-420) for all pairs in one launch.  Here pairs[i].p / M are
+ * the SOURCE submap's finest-level vertex positions, pairs[i].reserved is the pair's output slot (also its
+ * row in `poses`), and the array is sorted so pairs that share a source are contiguous; groups (num_groups x 2
+ * int32: first pair, count <= 32) lets a block read each vertex once and test it against every destination
+ * paired with that source.  enabled_out[slot] = (count / M > overlap_thresh); counts_out (num_pairs) uint64. */
 int miso_align_intersections(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
-                             int32_t num_pairs, int64_t max_M, const float* poses, float overlap_thresh,
-                             int32_t* enabled_out, unsigned long long* counts_out, miso_stream_t stream);
+                             int32_t num_pairs, const int32_t* groups, int32_t num_groups, int64_t max_M,
+                             const float* poses, float overlap_thresh, int32_t* enabled_out,
+                             unsigned long long* counts_out, miso_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Helpers around the path.

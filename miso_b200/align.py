@@ -105,12 +105,23 @@ class AlignBatch:
                 v = self._verts[src]
                 self.max_V = max(self.max_V, v.shape[0])
                 ip = _lib.AlignPair()
-                ip.src, ip.dst, ip.levels_used = src, dst, 0
+                ip.src, ip.dst, ip.levels_used, ip.reserved = src, dst, 0, i
                 ip.p, ip.M = v.data_ptr(), v.shape[0]
                 isect_structs.append(ip)
         self.check_intersection = check_intersection
         self.pairs_dev = _structs_to_device(pair_structs, self.device) if P else None
-        self.isect_dev = _structs_to_device(isect_structs, self.device) if (P and check_intersection) else None
+        self.isect_dev, self.groups_dev, self.num_groups = None, None, 0
+        if P and check_intersection:
+            # group by source submap (<= 32 pairs per group): one vertex read serves every pair of the group
+            isect_structs.sort(key=lambda q: q.src)
+            groups, start = [], 0
+            for j in range(1, len(isect_structs) + 1):
+                if j == len(isect_structs) or isect_structs[j].src != isect_structs[start].src or j - start == 32:
+                    groups.append((start, j - start))
+                    start = j
+            self.isect_dev = _structs_to_device(isect_structs, self.device)
+            self.groups_dev = torch.tensor(groups, dtype=torch.int32, device=self.device).contiguous()
+            self.num_groups = len(groups)
         self.src_idx = torch.tensor([s for s, _ in self.pairs], dtype=torch.long, device=self.device)
         self.dst_idx = torch.tensor([d for _, d in self.pairs], dtype=torch.long, device=self.device)
         self.K = K
@@ -144,9 +155,9 @@ class AlignBatch:
         p = poses24.detach().contiguous().float()
         with torch.cuda.device(self.device):
             _lib.check(lib.miso_align_intersections(
-                self.fields_dev.data_ptr(), self.num_fields, self.isect_dev.data_ptr(), len(self.pairs), self.max_V,
-                p.data_ptr(), float(overlap_thresh), self.enabled.data_ptr(), self.counts.data_ptr(),
-                _lib.stream_ptr(self.device)), "align_intersections")
+                self.fields_dev.data_ptr(), self.num_fields, self.isect_dev.data_ptr(), len(self.pairs),
+                self.groups_dev.data_ptr(), self.num_groups, self.max_V, p.data_ptr(), float(overlap_thresh),
+                self.enabled.data_ptr(), self.counts.data_ptr(), _lib.stream_ptr(self.device)), "align_intersections")
 
     def launch(self, poses24: torch.Tensor, want_gn: bool = False) -> torch.Tensor:
         lib = _lib.load()
@@ -246,20 +257,23 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
                                    lr=1e-2, rel_change_thresh=0, submap_pairs=None, check_intersection=True,
                                    pose_reg_weight=0, pose_thresh_rad=1.0, pose_thresh_m=1.0, verbose=True,
                                    save_iterations=False, *, level: int = 0, align_weight=3000.0,
-                                   subsample_points=None, pair_filter=None, allreduce=None):
+                                   subsample_points=None, pair_filter=None, allreduce=None, use_cuda_graph=False):
     """base.py:89-163 with the pair loop replaced by one batched launch per iteration.
 
     `pairwise_loss_tuple` is accepted for signature compatibility; the loss is the latent L2 loss at
     `level`.  `pair_filter` / `allreduce` are the multi-GPU hooks (miso_b200.dist): a rank evaluates
     only its share of the pairs and the per-submap pose gradients are summed across ranks before Adam.
-    Runs `num_iters + 1` iterations like the reference (`while iter <= num_iters`, base.py:127)."""
+    Runs `num_iters + 1` iterations like the reference (`while iter <= num_iters`, base.py:127).
+    `use_cuda_graph=True` captures one whole iteration (pose composition, intersection test, alignment
+    kernel, backward, Adam) into a CUDA graph after 3 eager warm-up iterations and replays it: level 0 has
+    only ~32 k samples per pair, so the iteration is launch-bound without it."""
     def pose_params():
         params = []
         for submap_id in range(1, grid_atlas.num_submaps):  # submap 0 stays fixed (base.py:104-108)
             params += list(grid_atlas.params_for_submap_pose(submap_id))
         return params
 
-    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr)
+    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr, capturable=bool(use_cuda_graph))
     if submap_pairs is None:
         submap_pairs = [(s, d) for s in range(grid_atlas.num_submaps) for d in range(s + 1, grid_atlas.num_submaps)]
     my_pairs = list(submap_pairs) if pair_filter is None else [p for i, p in enumerate(submap_pairs) if pair_filter(i, p)]
@@ -272,7 +286,43 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
     params_prev = None
     losses_hist = []
     it = 0
-    while it <= num_iters:
+    graph, static_loss = None, None
+    can_graph = use_cuda_graph and not save_iterations and rel_change_thresh <= 0 and allreduce is None
+
+    def one_iteration():
+        optimizer.zero_grad(set_to_none=False) if graph_params_ready[0] else optimizer.zero_grad()
+        poses24 = batch.pair_poses()
+        if check_intersection:
+            batch.update_intersections(poses24)
+        total = torch.nan_to_num(batch.losses(align_weight, poses24)).sum()
+        if pose_reg_weight > 0:
+            reg = grid_atlas_pose_trust_region_loss(grid_atlas, thresh_rad=pose_thresh_rad, thresh_m=pose_thresh_m,
+                                                    weight=pose_reg_weight)
+            total = total + sum(reg.values())
+        total.backward()
+        optimizer.step()
+        return total.detach()
+
+    graph_params_ready = [False]
+    if can_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            while it <= min(2, num_iters):          # eager warm-up iterations (also materialise .grad)
+                losses_hist.append(one_iteration())
+                it += 1
+        torch.cuda.current_stream().wait_stream(side)
+        graph_params_ready[0] = True
+        if it <= num_iters:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = one_iteration()
+            # the capture itself does not execute: every replay is one iteration
+            while it <= num_iters:
+                graph.replay()
+                losses_hist.append(static_loss.clone())
+                it += 1
+    while graph is None and it <= num_iters:
         if save_iterations:
             R, t = batch.submap_poses()
             T = torch.eye(4, device=R.device).repeat(R.shape[0], 1, 1)

@@ -267,29 +267,58 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// check_submap_intersection for every pair, grouped by source submap: a block reads each source vertex ONCE
+// and tests it against all destination submaps paired with that source (up to kMaxGroup), instead of
+// re-reading the 48 MB vertex list once per pair.  `pairs` must be sorted so that pairs sharing (p, M) are
+// contiguous; groups[g] = {first pair, number of pairs}.
+constexpr int kMaxGroup = 32;
+
 __global__ void __launch_bounds__(kThreads)
     align_intersection_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
-                              const float* __restrict__ poses, unsigned long long* __restrict__ counts) {
-  const int pi = blockIdx.y;
-  const miso_align_pair_t pr = pairs[pi];
-  if (pr.M <= 0) return;
-  const miso_field_t& dst = fields[pr.dst];
-  Pose24 P;
-  load_pose(poses, pi, P);
-  float dbound[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) dbound[i] = dst.bound[i];
-  unsigned cnt = 0;
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < pr.M; n += (int64_t)gridDim.x * blockDim.x) {
-    float p[3] = {pr.p[3 * n], pr.p[3 * n + 1], pr.p[3 * n + 2]};
-    float u[3], q[3];
-    xform(P.A1, P.b1, p, u);
-    xform(P.A2, P.b2, u, q);
-    cnt += in_bound(q, dbound) ? 1u : 0u;
+                              const int2* __restrict__ groups, const float* __restrict__ poses,
+                              unsigned long long* __restrict__ counts) {
+  const int2 grp = groups[blockIdx.y];
+  const int first = grp.x, np = grp.y;
+  const miso_align_pair_t pr0 = pairs[first];
+  if (pr0.M <= 0) return;
+  __shared__ float s_pose[kMaxGroup][24];
+  __shared__ float s_bound[kMaxGroup][6];
+  __shared__ int s_slot[kMaxGroup];
+  for (int i = threadIdx.x; i < np * 24; i += blockDim.x) {
+    const int j = i / 24;
+    s_pose[j][i % 24] = poses[(int64_t)pairs[first + j].reserved * 24 + i % 24];
   }
+  for (int i = threadIdx.x; i < np * 6; i += blockDim.x) s_bound[i / 6][i % 6] = fields[pairs[first + i / 6].dst].bound[i % 6];
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_slot[i] = pairs[first + i].reserved;
+  __syncthreads();
+  // lane j of every warp accumulates the count of pair j (ballot + popc), so no per-thread count array
+  const int lane = threadIdx.x & 31;
+  unsigned my_cnt = 0;
+  float A1[9], b1[3];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(counts + pi, (unsigned long long)cnt);
+  for (int i = 0; i < 9; ++i) A1[i] = s_pose[0][i];   // src -> world is shared by the whole group
+#pragma unroll
+  for (int i = 0; i < 3; ++i) b1[i] = s_pose[0][9 + i];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_iter = (pr0.M + stride - 1) / stride;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t n = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = n < pr0.M;
+    float p[3] = {0.f, 0.f, 0.f}, u[3];
+    if (live) p[0] = pr0.p[3 * n], p[1] = pr0.p[3 * n + 1], p[2] = pr0.p[3 * n + 2];
+    xform(A1, b1, p, u);
+    for (int j = 0; j < np; ++j) {
+      float A2[9], b2[3], q[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A2[i] = s_pose[j][12 + i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b2[i] = s_pose[j][21 + i];
+      xform(A2, b2, u, q);
+      const unsigned hit = __ballot_sync(0xffffffffu, live && in_bound(q, s_bound[j]));
+      if (lane == j) my_cnt += __popc(hit);
+    }
+  }
+  if (lane < np && my_cnt) atomicAdd(counts + s_slot[lane], (unsigned long long)my_cnt);
 }
 
 __global__ void align_intersection_finalize(const miso_align_pair_t* __restrict__ pairs, int num_pairs,
@@ -299,8 +328,9 @@ __global__ void align_intersection_finalize(const miso_align_pair_t* __restrict_
   if (i >= num_pairs) return;
   // overlap_percentage = num_valid / num_all (float32 division of int64 tensors in torch) > thresh
   const int64_t M = pairs[i].M;
-  float frac = M > 0 ? (float)counts[i] / (float)M : 0.f;
-  enabled[i] = frac > thresh ? 1 : 0;
+  const int slot = pairs[i].reserved;
+  float frac = M > 0 ? (float)counts[slot] / (float)M : 0.f;
+  enabled[slot] = frac > thresh ? 1 : 0;
 }
 
 }  // namespace miso
@@ -329,18 +359,20 @@ extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, 
 }
 
 extern "C" int miso_align_intersections(const miso_field_t* fields, int32_t num_fields,
-                                        const miso_align_pair_t* pairs, int32_t num_pairs, int64_t max_M,
-                                        const float* poses, float overlap_thresh, int32_t* enabled_out,
-                                        unsigned long long* counts_out, miso_stream_t stream) {
-  MISO_REQUIRE(fields && pairs && poses && enabled_out && counts_out, "align_intersections: null argument");
-  MISO_REQUIRE(num_fields > 0 && num_pairs >= 0 && num_pairs <= 65535, "align_intersections: bad counts");
+                                        const miso_align_pair_t* pairs, int32_t num_pairs, const int32_t* groups,
+                                        int32_t num_groups, int64_t max_M, const float* poses, float overlap_thresh,
+                                        int32_t* enabled_out, unsigned long long* counts_out, miso_stream_t stream) {
+  MISO_REQUIRE(fields && pairs && poses && enabled_out && counts_out && groups, "align_intersections: null argument");
+  MISO_REQUIRE(num_fields > 0 && num_pairs >= 0 && num_groups >= 0 && num_groups <= 65535,
+               "align_intersections: bad counts");
   if (num_pairs == 0) return MISO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(counts_out, 0, sizeof(unsigned long long) * num_pairs, s);
-  if (max_M > 0) {
-    int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_pairs, sm_count() * 8))));
-    dim3 grid(bx, num_pairs);
-    align_intersection_kernel<<<grid, kThreads, 0, s>>>(fields, pairs, poses, counts_out);
+  if (max_M > 0 && num_groups > 0) {
+    int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_groups, sm_count() * 8))));
+    dim3 grid(bx, num_groups);
+    align_intersection_kernel<<<grid, kThreads, 0, s>>>(fields, pairs, reinterpret_cast<const int2*>(groups), poses,
+                                                        counts_out);
   }
   align_intersection_finalize<<<(num_pairs + 127) / 128, 128, 0, s>>>(pairs, num_pairs, counts_out, overlap_thresh,
                                                                        enabled_out);
