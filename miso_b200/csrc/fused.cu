@@ -255,6 +255,17 @@ __device__ __forceinline__ void gather_level(const miso_level_t& lv, const Cell&
   }
 }
 
+__device__ __forceinline__ float ldg_early_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned ldg_early_u8(const uint8_t* p) {
+  unsigned r;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
 // Scatter (a*w_c + vi . dw_c/di) * J into one level's gradient buffer; vi is in index space.
 // The per-corner coefficient is built separably:  coef = wz*(wy*(a*wx + vix*sx) + viy*sy*wx) + viz*sz*wx*wy.
 template <int C>
@@ -282,6 +293,123 @@ __device__ __forceinline__ void scatter_level(const miso_level_t& lv, const Cell
 #pragma unroll
     for (int ch = 0; ch < C; ch += 4)
       red_add_f4(dst + ch, coef * J[ch], coef * J[ch + 1], coef * J[ch + 2], coef * J[ch + 3]);
+  }
+}
+
+// ---- lean per-level cell for the tensor-core kernels: 32-bit element index (host guarantees every level has
+// < 2^31 elements on this path), kept in registers from the gather to the scatter so the index math, the
+// validity tests and the 64-bit address arithmetic are done once per point and level -----------------------
+struct CellLite {
+  int base;        // element index of corner (ix0,iy0,iz0); may be "virtual" (negative) when that corner is outside
+  float fx, fy, fz;
+  unsigned valid;  // bit k set when corner k lies inside the grid
+};
+
+__device__ __forceinline__ CellLite make_cell_lite(const miso_level_t& lv, const float (&xn)[3]) {
+  const float ix = unnormalize_nc(xn[0], lv.X), iy = unnormalize_nc(xn[1], lv.Y), iz = unnormalize_nc(xn[2], lv.Z);
+  const float flx = floorf(ix), fly = floorf(iy), flz = floorf(iz);
+  const int x0 = (int)fminf(fmaxf(flx, -2.0f), (float)lv.X + 1.0f);
+  const int y0 = (int)fminf(fmaxf(fly, -2.0f), (float)lv.Y + 1.0f);
+  const int z0 = (int)fminf(fmaxf(flz, -2.0f), (float)lv.Z + 1.0f);
+  CellLite c;
+  c.fx = ix - flx, c.fy = iy - fly, c.fz = iz - flz;
+  c.base = z0 * (int)lv.sZ + y0 * (int)lv.sY + x0 * (int)lv.sX;
+  if (x0 >= 0 && x0 + 1 < lv.X && y0 >= 0 && y0 + 1 < lv.Y && z0 >= 0 && z0 + 1 < lv.Z) {
+    c.valid = 0xffu;  // interior: the overwhelmingly common case, no per-corner tests
+  } else {
+    const unsigned vx = ((unsigned)x0 < (unsigned)lv.X ? 1u : 0u) | ((unsigned)(x0 + 1) < (unsigned)lv.X ? 2u : 0u);
+    const unsigned vy = ((unsigned)y0 < (unsigned)lv.Y ? 1u : 0u) | ((unsigned)(y0 + 1) < (unsigned)lv.Y ? 2u : 0u);
+    const unsigned vz = ((unsigned)z0 < (unsigned)lv.Z ? 1u : 0u) | ((unsigned)(z0 + 1) < (unsigned)lv.Z ? 2u : 0u);
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v |= (((vx >> (k & 1)) & (vy >> ((k >> 1) & 1)) & (vz >> (k >> 2))) & 1u) << k;
+    c.valid = v;
+  }
+  return c;
+}
+
+__device__ __forceinline__ int corner_delta(const miso_level_t& lv, int k) {
+  return ((k & 1) ? (int)lv.sX : 0) + ((k & 2) ? (int)lv.sY : 0) + ((k & 4) ? (int)lv.sZ : 0);
+}
+
+template <bool kDeriv>
+__device__ __forceinline__ void lerp_corners4(const float4 (&v)[8], const CellLite& c, float* __restrict__ f,
+                                              float* __restrict__ dfx, float* __restrict__ dfy,
+                                              float* __restrict__ dfz) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a[4], d[4];
+#pragma unroll
+    for (int yz = 0; yz < 4; ++yz) {
+      const float v0 = reinterpret_cast<const float*>(&v[2 * yz])[e];
+      const float v1 = reinterpret_cast<const float*>(&v[2 * yz + 1])[e];
+      d[yz] = v1 - v0;
+      a[yz] = fmaf(c.fx, d[yz], v0);
+    }
+    float ay[2], ey[2], dxy[2];
+#pragma unroll
+    for (int z = 0; z < 2; ++z) {
+      ey[z] = a[2 * z + 1] - a[2 * z];
+      ay[z] = fmaf(c.fy, ey[z], a[2 * z]);
+      if constexpr (kDeriv) dxy[z] = fmaf(c.fy, d[2 * z + 1] - d[2 * z], d[2 * z]);
+    }
+    const float ez = ay[1] - ay[0];
+    f[e] = fmaf(c.fz, ez, ay[0]);
+    if constexpr (kDeriv) {
+      dfz[e] = ez;
+      dfy[e] = fmaf(c.fz, ey[1] - ey[0], ey[0]);
+      dfx[e] = fmaf(c.fz, dxy[1] - dxy[0], dxy[0]);
+    }
+  }
+}
+
+template <int C, bool kDeriv>
+__device__ __forceinline__ void gather_level_lite(const miso_level_t& lv, const CellLite& c, float* __restrict__ f,
+                                                  float* __restrict__ dfx, float* __restrict__ dfy,
+                                                  float* __restrict__ dfz) {
+#pragma unroll
+  for (int ch = 0; ch < C; ch += 4) {
+    float4 v[8];
+    if (c.valid == 0xffu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ldg_f4(lv.feat + (c.base + corner_delta(lv, k) + ch));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((c.valid >> k) & 1u) v[k] = ldg_f4(lv.feat + (c.base + corner_delta(lv, k) + ch));
+      }
+    }
+    lerp_corners4<kDeriv>(v, c, f + ch, dfx + ch, dfy + ch, dfz + ch);
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void scatter_level_lite(const miso_level_t& lv, const CellLite& c, float a, float vix,
+                                                   float viy, float viz, const float* __restrict__ J) {
+  const float wx[2] = {1.0f - c.fx, c.fx}, wy[2] = {1.0f - c.fy, c.fy}, wz[2] = {1.0f - c.fz, c.fz};
+  const float px[2] = {fmaf(a, wx[0], -vix), fmaf(a, wx[1], vix)};
+  float r[4], q[4];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float sy = dy ? viy : -viy;
+      r[2 * dy + dx] = fmaf(wy[dy], px[dx], sy * wx[dx]);
+      q[2 * dy + dx] = wx[dx] * wy[dy];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int dz = k >> 2;
+    const float sz = dz ? viz : -viz;
+    const float coef = fmaf(wz[dz], r[k & 3], sz * q[k & 3]);
+    if (c.valid == 0xffu || ((c.valid >> k) & 1u)) {
+      float* dst = lv.grad + (c.base + corner_delta(lv, k));
+#pragma unroll
+      for (int ch = 0; ch < C; ch += 4)
+        red_add_f4(dst + ch, coef * J[ch], coef * J[ch + 1], coef * J[ch + 2], coef * J[ch + 3]);
+    }
   }
 }
 
@@ -585,9 +713,9 @@ struct TcSmem {
   alignas(128) unsigned char w2t_hi[tc::kWeightBytes];
   alignas(128) unsigned char w2t_lo[tc::kWeightBytes];
   alignas(128) unsigned char a_lo[kTcWgs][kTcABytes];
-  alignas(16) float W1[H * F];    // [k][i]  (layer 1)
+  alignas(128) unsigned char w1e_hi[H * (F + 8) * 4];  // layer 1: canonical [64][KP], row = {W1[n][0..F), b1[n], 0..}
+  alignas(128) unsigned char w1e_lo[H * (F + 8) * 4];
   alignas(16) float W1T[F * H];   // [i][k]  (Jacobian product, pairs over k)
-  alignas(16) float2 b1p[H];      // {b1, 0}: FFMA2 accumulator seed
   alignas(16) float2 ep[H];       // {b2, W3} per hidden unit
   float b3[4];
   uint64_t bar[kTcWgs];
@@ -632,15 +760,18 @@ __device__ __forceinline__ TcTile<F> tc_setup(unsigned char* smem_raw, const mis
     *reinterpret_cast<float*>(s->w2t_hi + off) = hi;
     *reinterpret_cast<float*>(s->w2t_lo + off) = lo;
   }
-  for (int i = tid; i < H * F; i += kTcThreads) {
-    const float w = dec.W1[i];
-    s->W1[i] = w;
-    s->W1T[(i % F) * H + i / F] = w;
+  constexpr int KP = ((F + 1 + 7) / 8) * 8;   // F inputs + the bias column, padded to the tf32 K step
+  for (int i = tid; i < H * KP; i += kTcThreads) {
+    const int n = i / KP, k = i % KP;
+    const float w = k < F ? dec.W1[n * F + k] : (k == F ? dec.b1[n] : 0.f);
+    float hi, lo;
+    tc::tf32_split(w, hi, lo);
+    const uint32_t off = tc::b_offset_k(n, k, KP);
+    *reinterpret_cast<float*>(s->w1e_hi + off) = hi;
+    *reinterpret_cast<float*>(s->w1e_lo + off) = lo;
   }
-  for (int i = tid; i < H; i += kTcThreads) {
-    s->b1p[i] = make_float2(dec.b1[i], 0.f);
-    s->ep[i] = make_float2(dec.b2[i], dec.W3[i]);
-  }
+  for (int i = tid; i < H * F; i += kTcThreads) s->W1T[(i % F) * H + i / F] = dec.W1[i];
+  for (int i = tid; i < H; i += kTcThreads) s->ep[i] = make_float2(dec.b2[i], dec.W3[i]);
   if (tid == 0) s->b3[0] = dec.b3[0];
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -705,27 +836,52 @@ __device__ __forceinline__ float decoder_tc(TcTile<F>& t, const float (&f)[F], f
   float2 fp[F / 2];
 #pragma unroll
   for (int i = 0; i < F / 2; ++i) fp[i] = make_float2(f[2 * i], f[2 * i + 1]);
-  // ---- layer 1 (SIMT): h1 = relu(W1 f + b1) ------------------------------------------------------
-  unsigned m1[2] = {0u, 0u};
+  // ---- layer 1 on the tensor core: [f, 1] (K = F+1 padded to 8) x [W1 | b1]^T, 3xTF32 ---------------
+  constexpr int KP = ((F + 1 + 7) / 8) * 8;
+  {
+    uint32_t fh[KP], flo[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      float h = 0.f, l = 0.f;
+      if (i < F) tc::tf32_split_fast(f[i], h, l);
+      else if (i == F) h = 1.0f;
+      fh[i] = __float_as_uint(h);
+      flo[i] = __float_as_uint(l);
+    }
+#pragma unroll
+    for (int c = 0; c < KP / 8; ++c) {
+      uint32_t a8[8], b8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a8[i] = fh[8 * c + i], b8[i] = flo[8 * c + i];
+      tc::tmem_st8(a_lane + 8 * c, a8);
+      tc::tmem_st8(a_lane + KP + 8 * c, b8);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    wg_barrier(t.wg);
+    if (t.wtid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32_smallk<KP>(t.d_tmem, t.a_tmem, t.a_tmem + KP, tc::smem_u32(s->w1e_hi), tc::smem_u32(s->w1e_lo));
+      tc::mma_commit(t.bar);
+    }
+    tc::mbar_wait(t.bar, t.parity);
+    t.parity ^= 1;
+    tc::fence_after_sync();
+  }
+  // epilogue 1: h1 = relu(D) -> hi into TMEM, lo into shared memory; sign bits kept for the Jacobian pass
+  unsigned m1[2] = {0u, 0u};   // bit (31 - (k & 31)) of word k>>5 = sign of pre-activation k
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    uint32_t d[16];
+    tc::tmem_ld16(d_lane + q * 16, d);
+    tc::wait_ld();
     uint32_t hi[16];
     float lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int k = q * 16 + i;
-      float2 a0 = s->b1p[k];
-      const float4* r0 = reinterpret_cast<const float4*>(s->W1 + k * F);
-#pragma unroll
-      for (int c = 0; c < F / 4; ++c) {
-        float4 w0 = r0[c];
-        a0 = ffma2(make_float2(w0.x, w0.y), fp[2 * c], a0);
-        a0 = ffma2(make_float2(w0.z, w0.w), fp[2 * c + 1], a0);
-      }
-      const float x0 = a0.x + a0.y;
-      m1[q >> 1] |= (x0 > 0.f ? 1u : 0u) << ((q & 1) * 16 + i);
+      m1[q >> 1] = __funnelshift_l(d[i], m1[q >> 1], 1);
       float h;
-      tc::tf32_split_fast(fmaxf(x0, 0.f), h, lo[i]);
+      tc::tf32_split_fast(fmaxf(__uint_as_float(d[i]), 0.f), h, lo[i]);
       hi[i] = __float_as_uint(h);
     }
     tc_store_chunk(a_lane, t.a_lo_row, q, hi, lo);
@@ -765,8 +921,11 @@ __device__ __forceinline__ float decoder_tc(TcTile<F>& t, const float (&f)[F], f
     float2 e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const unsigned bits = m1[q >> 1] >> ((q & 1) * 16 + 2 * i);
-      e[i] = make_float2((bits & 1u) ? __uint_as_float(d[2 * i]) : 0.f, (bits & 2u) ? __uint_as_float(d[2 * i + 1]) : 0.f);
+      // sign bit of hidden unit k sits at bit 31 - (k & 31); set = pre-activation negative = ReLU off
+      const int k0 = (q & 1) * 16 + 2 * i;
+      const unsigned w = m1[q >> 1];
+      e[i] = make_float2(((w >> (31 - k0)) & 1u) ? 0.f : __uint_as_float(d[2 * i]),
+                         ((w >> (30 - k0)) & 1u) ? 0.f : __uint_as_float(d[2 * i + 1]));
     }
 #pragma unroll
     for (int i = 0; i < F; ++i) {
@@ -813,23 +972,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     unsigned char vld = 0;
     if (active) {
       load_point(m.x, fr, n, p);
-      gt = m.gt_sdf[n];
-      vld = m.gt_valid[n];
-      sgn = m.gt_sign[n];
-      if (m.weights) wgt = m.weights[n];
+      // asm volatile: keeps these loads up here (the compiler would otherwise sink them to their first use
+      // after the decoder, exposing a full memory latency in the loss epilogue)
+      gt = ldg_early_f32(m.gt_sdf + n);
+      vld = (unsigned char)ldg_early_u8(m.gt_valid + n);
+      sgn = ldg_early_f32(m.gt_sign + n);
+      if (m.weights) wgt = ldg_early_f32(m.weights + n);
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
     float f[F], dfx[F], dfy[F], dfz[F];
+    CellLite cells[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      if (!active || ((fl.ignore_mask >> l) & 1u)) {
-#pragma unroll
-        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
-      } else {
-        Cell c = level_cell(fl.level[l], xn);
-        gather_level<C, true>(fl.level[l], c, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
-      }
+      cells[l] = make_cell_lite(fl.level[l], xn);
+      if (!active || ((fl.ignore_mask >> l) & 1u)) cells[l].valid = 0u;   // contributes zeros, scatters nothing
+      gather_level_lite<C, true>(fl.level[l], cells[l], f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
     }
     float J[F];
     const float pred = decoder_tc<F, true>(t, f, J);
@@ -882,11 +1040,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) {
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-          if (((fl.ignore_mask >> l) & 1u) || !fl.level[l].grad) continue;
+          if (!fl.level[l].grad) continue;
           const miso_level_t& lv = fl.level[l];
-          Cell c = level_cell(lv, xn);
           float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
-          scatter_level<C>(lv, c, a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
+          scatter_level_lite<C>(lv, cells[l], a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
         }
       }
     }
@@ -1075,6 +1232,15 @@ static int blocks_for(K kernel, size_t smem, int64_t N) {
   } while (0)
 
 // MISO_MLP=simt forces the FP32 SIMT decoder; default is the tcgen05 (3xTF32) decoder
+static bool fits_int32(const miso_field_t* f) {
+  for (int l = 0; l < f->num_levels; ++l) {
+    const miso_level_t& lv = f->level[l];
+    const int64_t span = (int64_t)(lv.Z + 2) * lv.sZ + (int64_t)(lv.Y + 2) * lv.sY + (int64_t)(lv.X + 2) * lv.sX;
+    if (span >= (int64_t)0x7fffffff) return false;
+  }
+  return true;
+}
+
 static bool use_tensor_cores() {
   static int cached = -1;
   if (cached < 0) {
@@ -1200,7 +1366,7 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
   int nblocks = 0;
-  if (use_tensor_cores()) {
+  if (use_tensor_cores() && fits_int32(field)) {
     MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
       constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
       auto k = mapping_step_tc_kernel<L, C>;

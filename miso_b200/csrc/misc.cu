@@ -48,10 +48,15 @@ __global__ void __launch_bounds__(kThreads)
                 int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 pv = reinterpret_cast<float4*>(p)[i];
     float4 gv = reinterpret_cast<float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
+    // voxels no sample has ever touched (g = m = v = 0) have an exactly-zero Adam update: skip the parameter
+    // read and all four stores (12 B instead of 32 B of traffic per parameter, same result bit for bit)
+    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f && mv.x == 0.f && mv.y == 0.f && mv.z == 0.f &&
+        mv.w == 0.f && vv.x == 0.f && vv.y == 0.f && vv.z == 0.f && vv.w == 0.f)
+      continue;
+    float4 pv = reinterpret_cast<float4*>(p)[i];
     float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
           va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll

@@ -60,6 +60,19 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   return d;
 }
 
+// same, for an operand whose rows hold `k_elems` K-elements (SBO = k_elems/4 core matrices)
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr, int k_elems) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((kLBO >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((((uint32_t)k_elems / 4) * kLBO >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t b_offset_k(int n, int k, int k_elems) {
+  return (uint32_t)((n >> 3) * (k_elems / 4) * kLBO + (k >> 2) * kLBO + (n & 7) * 16 + (k & 3) * 4);
+}
+
 // instruction descriptor (InstrDescriptor): D=f32, A=B=tf32, both K-major, N=64, M=128
 __device__ __forceinline__ uint32_t make_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -167,6 +180,28 @@ __device__ __forceinline__ void issue_gemm_exactA(uint32_t tmem_d, uint32_t tmem
 
 // byte offset of row m's first 16-byte chunk inside a canonical K-major A operand (128 rows x 64)
 __device__ __forceinline__ uint32_t a_row_offset(int m) { return (uint32_t)((m >> 3) * kSBO + (m & 7) * 16); }
+
+// 3xTF32 product with a short K (the first decoder layer: K = F inputs + 1 bias column, padded to 8):
+// A_hi / A_lo both in TMEM, B = canonical [64][KP] operands
+template <int KP>
+__device__ __forceinline__ void issue_gemm_3xtf32_smallk(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo,
+                                                         uint32_t smem_b_hi, uint32_t smem_b_lo) {
+  const uint32_t idesc = make_idesc();
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = (pass == 1) ? tmem_a_lo : tmem_a_hi;
+    const uint32_t b = (pass == 2) ? smem_b_lo : smem_b_hi;
+#pragma unroll
+    for (int ks = 0; ks < KP / 8; ++ks)
+      mma_tf32_ts(tmem_d, a + ks * 8, make_desc_k(b + ks * 2 * kLBO, KP), idesc, (pass | ks) ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
