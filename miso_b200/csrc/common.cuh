@@ -32,6 +32,15 @@ __device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+// predicated form: no branch around the reduction (keeps the surrounding code convergent)
+__device__ __forceinline__ void red_add_f4_if(unsigned pred, float* addr, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }

@@ -385,8 +385,8 @@ __device__ __forceinline__ void gather_level_lite(const miso_level_t& lv, const 
 }
 
 template <int C>
-__device__ __forceinline__ void scatter_level_lite(const miso_level_t& lv, const CellLite& c, float a, float vix,
-                                                   float viy, float viz, const float* __restrict__ J) {
+__device__ __forceinline__ void scatter_level_lite(const miso_level_t& lv, const CellLite& c, unsigned on, float a,
+                                                   float vix, float viy, float viz, const float* __restrict__ J) {
   const float wx[2] = {1.0f - c.fx, c.fx}, wy[2] = {1.0f - c.fy, c.fy}, wz[2] = {1.0f - c.fz, c.fz};
   const float px[2] = {fmaf(a, wx[0], -vix), fmaf(a, wx[1], vix)};
   float r[4], q[4];
@@ -404,12 +404,12 @@ __device__ __forceinline__ void scatter_level_lite(const miso_level_t& lv, const
     const int dz = k >> 2;
     const float sz = dz ? viz : -viz;
     const float coef = fmaf(wz[dz], r[k & 3], sz * q[k & 3]);
-    if (c.valid == 0xffu || ((c.valid >> k) & 1u)) {
-      float* dst = lv.grad + (c.base + corner_delta(lv, k));
+    // out-of-grid corners have a "virtual" index: clamp the address, the predicate suppresses the access
+    const unsigned ok = on & (c.valid >> k) & 1u;
+    float* dst = lv.grad + (ok ? c.base + corner_delta(lv, k) : 0);
 #pragma unroll
-      for (int ch = 0; ch < C; ch += 4)
-        red_add_f4(dst + ch, coef * J[ch], coef * J[ch + 1], coef * J[ch + 2], coef * J[ch + 3]);
-    }
+    for (int ch = 0; ch < C; ch += 4)
+      red_add_f4_if(ok, dst + ch, coef * J[ch], coef * J[ch + 1], coef * J[ch + 2], coef * J[ch + 3]);
   }
 }
 
@@ -705,6 +705,25 @@ __global__ void __launch_bounds__(kThreads, MISO_MAP_MIN_BLOCKS)
 constexpr int kTcWgs = 4;
 constexpr int kTcThreads = kTcWgs * 128;
 constexpr int kTcABytes = tc::kTileM * tc::kK * 4;  // one A_lo operand: 32 KB
+constexpr int kTcMaxSmemPoses = 256;                // keyframe pose table kept in shared memory (12 KB)
+
+// load_point with the pose table in shared memory (same arithmetic as load_point)
+__device__ __forceinline__ void load_point_smem(const float* __restrict__ x, const miso_frames_t& fr, int64_t n,
+                                                const float* __restrict__ spose, float (&p)[3]) {
+  if (!fr.ids || !spose) {
+    load_point(x, fr, n, p);
+    return;
+  }
+  const float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
+  int64_t id = fr.ids[n];
+  if (id < 0 || id >= fr.num_frames) id = 0;
+  const float4* P = reinterpret_cast<const float4*>(spose + id * 12);
+  const float4 q0 = P[0], q1 = P[1], q2 = P[2];
+  const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+  const float tt[3] = {q2.y, q2.z, q2.w};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) p[j] = fmaf(c, R[3 * j + 2], fmaf(b, R[3 * j + 1], a * R[3 * j])) + tt[j];
+}
 
 template <int F>
 struct TcSmem {
@@ -720,6 +739,7 @@ struct TcSmem {
   float b3[4];
   uint64_t bar[kTcWgs];
   uint32_t tmem_base;
+  alignas(16) float poses[kTcMaxSmemPoses * 12];   // R (9) + t (3) per keyframe, staged when they fit
 };
 
 template <int F>
@@ -961,6 +981,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (eik_on && eik_filter) n_eik = (float)(*m.eik_count);
   const float inv_neik = 1.0f / n_eik;
 
+  // keyframe pose table -> shared memory (one dependent global round trip less per point)
+  const bool poses_in_smem = fr.ids != nullptr && fr.num_frames <= kTcMaxSmemPoses;
+  if (poses_in_smem) {
+    for (int i = threadIdx.x; i < fr.num_frames * 9; i += kTcThreads) t.s->poses[(i / 9) * 12 + i % 9] = fr.R[i];
+    for (int i = threadIdx.x; i < fr.num_frames * 3; i += kTcThreads) t.s->poses[(i / 3) * 12 + 9 + i % 3] = fr.t[i];
+  }
+  __syncthreads();
+
   float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
   const int64_t num_tiles = (m.N + 127) / 128;
   for (int64_t tile = (int64_t)blockIdx.x * kTcWgs + t.wg; tile < num_tiles; tile += (int64_t)gridDim.x * kTcWgs) {
@@ -971,13 +999,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float gt = 0.f, wgt = 1.f, sgn = 0.f;
     unsigned char vld = 0;
     if (active) {
-      load_point(m.x, fr, n, p);
+      load_point_smem(m.x, fr, n, poses_in_smem ? t.s->poses : nullptr, p);
       // asm volatile: keeps these loads up here (the compiler would otherwise sink them to their first use
       // after the decoder, exposing a full memory latency in the loss epilogue)
       gt = ldg_early_f32(m.gt_sdf + n);
       vld = (unsigned char)ldg_early_u8(m.gt_valid + n);
       sgn = ldg_early_f32(m.gt_sign + n);
       if (m.weights) wgt = ldg_early_f32(m.weights + n);
+      // pull the NEXT tile's per-point inputs towards L1 while this tile is processed
+      const int64_t n2 = n + (int64_t)gridDim.x * kTcWgs * 128;
+      if (n2 < m.N) {
+        prefetch_l1(m.x + 3 * n2);
+        prefetch_l1(m.x + 3 * n2 + 2);
+        if (fr.ids) prefetch_l1(fr.ids + n2);
+        prefetch_l1(m.gt_sdf + n2);
+        prefetch_l1(m.gt_sign + n2);
+        prefetch_l1(m.gt_valid + n2);
+        if (m.weights) prefetch_l1(m.weights + n2);
+      }
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
@@ -992,60 +1031,54 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float J[F];
     const float pred = decoder_tc<F, true>(t, f, J);
 
-    if (active) {
-      if (m.sdf_out) m.sdf_out[n] = pred;
-      float a = 0.f;
-      if (vld) {
-        const float w = wgt;
-        const float e = pred - gt;
-        if (m.cfg.loss_type == 0) {
-          acc_sdf += w * fabsf(e);
-          a += m.cfg.weight_sdf * w * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
-        } else {
-          acc_sdf += w * e * e;
-          a += m.cfg.weight_sdf * w * 2.f * e;
-        }
+    // ---- loss terms + scatter, written without divergent regions (inactive lanes carry zeros) ----------
+    if (active && m.sdf_out) m.sdf_out[n] = pred;
+    float a = 0.f;
+    if (vld) {
+      const float e = pred - gt;
+      if (m.cfg.loss_type == 0) {
+        acc_sdf += wgt * fabsf(e);
+        a = m.cfg.weight_sdf * wgt * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
+      } else {
+        acc_sdf += wgt * e * e;
+        a = m.cfg.weight_sdf * wgt * 2.f * e;
       }
-      if (m.cfg.weight_fs != 0.f && sgn == 1.f) {
-        const float up = fmaxf(pred - gt, 0.f), lo = fmaxf(m.cfg.trunc_dist - pred, 0.f);
-        acc_fs += fmaxf(up, lo);
-        if (up > lo) a += m.cfg.weight_fs;
-        else if (lo > up) a -= m.cfg.weight_fs;
-      }
-      a *= invN * m.cfg.grad_scale;
-      float v[3] = {0.f, 0.f, 0.f};
-      if (eik_on && (!eik_filter || fabsf(gt) < m.cfg.eik_trunc_dist)) {
-        float gx = 0.f, gy = 0.f, gz = 0.f;
+    }
+    if (m.cfg.weight_fs != 0.f && sgn == 1.f) {
+      const float up = fmaxf(pred - gt, 0.f), lo = fmaxf(m.cfg.trunc_dist - pred, 0.f);
+      acc_fs += fmaxf(up, lo);
+      a += up > lo ? m.cfg.weight_fs : (lo > up ? -m.cfg.weight_fs : 0.f);
+    }
+    a *= invN * m.cfg.grad_scale;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (eik_on) {
+      float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-          float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int l = 0; l < L; ++l) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
-          for (int i = 0; i < C; ++i) {
-            sx = fmaf(J[l * C + i], dfx[l * C + i], sx);
-            sy = fmaf(J[l * C + i], dfy[l * C + i], sy);
-            sz = fmaf(J[l * C + i], dfz[l * C + i], sz);
-          }
-          gx = fmaf(sx, (float)fl.level[l].X * g.inv_len[0], gx);
-          gy = fmaf(sy, (float)fl.level[l].Y * g.inv_len[1], gy);
-          gz = fmaf(sz, (float)fl.level[l].Z * g.inv_len[2], gz);
+        for (int i = 0; i < C; ++i) {
+          sx = fmaf(J[l * C + i], dfx[l * C + i], sx);
+          sy = fmaf(J[l * C + i], dfy[l * C + i], sy);
+          sz = fmaf(J[l * C + i], dfz[l * C + i], sz);
         }
-        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
-        const float e = nrm - 1.f;
-        acc_eik += e * e;
-        if (nrm > 0.f) {
-          const float k = m.cfg.weight_eik * m.cfg.grad_scale * 2.f * e * inv_neik / nrm;
-          v[0] = k * gx, v[1] = k * gy, v[2] = k * gz;
-        }
+        gx = fmaf(sx, (float)fl.level[l].X * g.inv_len[0], gx);
+        gy = fmaf(sy, (float)fl.level[l].Y * g.inv_len[1], gy);
+        gz = fmaf(sz, (float)fl.level[l].Z * g.inv_len[2], gz);
       }
-      if (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) {
+      const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float e = nrm - 1.f;
+      const bool use = active && (!eik_filter || fabsf(gt) < m.cfg.eik_trunc_dist);
+      acc_eik += use ? e * e : 0.f;
+      const float k = (use && nrm > 0.f) ? m.cfg.weight_eik * m.cfg.grad_scale * 2.f * e * inv_neik / nrm : 0.f;
+      v[0] = k * gx, v[1] = k * gy, v[2] = k * gz;
+    }
+    const unsigned nz = (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) ? 1u : 0u;
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-          if (!fl.level[l].grad) continue;
-          const miso_level_t& lv = fl.level[l];
-          float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
-          scatter_level_lite<C>(lv, cells[l], a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
-        }
-      }
+    for (int l = 0; l < L; ++l) {
+      const miso_level_t& lv = fl.level[l];
+      float kx = (float)lv.X * g.inv_len[0], ky = (float)lv.Y * g.inv_len[1], kz = (float)lv.Z * g.inv_len[2];
+      scatter_level_lite<C>(lv, cells[l], (nz && lv.grad) ? 1u : 0u, a, v[0] * kx, v[1] * ky, v[2] * kz, J + l * C);
     }
   }
   float s0 = block_sum(acc_sdf, red);
