@@ -40,6 +40,7 @@ LOSS_CFG = dict(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, t
 BYTES_PER_POINT = 12 + 8 + 4 + 1 + 4 + 4 + 256 + 256
 SURVEY_BYTES_PER_POINT = 1068   # SURVEY.md section 8d two-pass figure (fwd + bwd re-gather + eikonal scatter)
 FLOPS_PER_POINT = 2 * (2 * (8 * 64 + 64 * 64) + 64)  # MLP forward + Jacobian backward, FMA = 2 flops
+NCU_DRAM_BYTES_PER_LAUNCH = 119318016 + 11839488     # profiles/r01_ncu_mapping_step_tc.csv (2^20 points)
 
 
 def measured_hbm_peak():
@@ -193,7 +194,6 @@ def run_ours(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     kern_ms = [a.elapsed_time(b) for a, b in mloss.PROFILE_EVENTS]
     mloss.PROFILE_EVENTS = None
-    clocks = sampler.stop() if sampler else None
     final_loss = [float(v) for v in last.tolist()]
 
     # ---------------- end-to-end through the trainer API with host buffers ----------------
@@ -214,6 +214,7 @@ def run_ours(args):
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    clocks = sampler.stop() if sampler else None   # sampled across both timed regions (value + e2e)
     assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the e2e run"
 
     align = None
@@ -251,11 +252,15 @@ def run_ours(args):
         "e2e": {"value": world * N_POINTS / (e2e_ms / args.steps * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "mapping_step_kernel<2,4> (+finalize)", "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "mapping_step_tc_kernel<2,4> (+finalize)", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                                       "kernel at this size (profiles/r01_ncu_mapping_step_tc.csv); below the algorithmic "
+                                       "bytes because the 64 MB grid and its gradient stay L2-resident",
                      "bytes_per_point": BYTES_PER_POINT, "survey_bytes_per_point": SURVEY_BYTES_PER_POINT,
                      "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
-                     "fp32_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12},
+                     "fp32_equiv_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12,
+                     "decoder": os.environ.get("MISO_MLP", "tcgen05 3xTF32")},
         "final_loss_terms": final_loss,
         "extra": {"align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
                   "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "
@@ -444,8 +449,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the alignment half of the metric")
