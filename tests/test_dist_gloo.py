@@ -71,22 +71,25 @@ def _worker(rank, world, port, q):
         pairs = [(s, d) for s in range(3) for d in range(s + 1, 3)]
         mine = [p for i, p in enumerate(pairs) if mdist.pair_filter()(i, p)]
         total = torch.zeros(())
+        per_pair = torch.zeros(len(pairs))
         for s, d in mine:
             Rs, ts = atlas.updated_submap_pose(s)
             Rd, td = atlas.updated_submap_pose(d)
-            total = total + O.pairwise_loss_latent(subs[s], subs[d], atlas.coords[(s, 0)], Rs, ts, Rd, td, 0)
+            val = O.pairwise_loss_latent(subs[s], subs[d], atlas.coords[(s, 0)], Rs, ts, Rd, td, 0)
+            per_pair[pairs.index((s, d))] = float(val.detach())
+            total = total + val
         if total.requires_grad:
             total.backward()
         pg = [p.grad if p.grad is not None else torch.zeros_like(p) for p in atlas.rot + atlas.tra]
         tl = total.detach().clone().reshape(1)
-        mdist.allreduce_sum_(pg + [tl])
+        mdist.allreduce_sum_(pg + [tl, per_pair])
         # ---- submap-per-rank -------------------------------------------------------------------
         owned = mdist.submaps_for_rank(5)
         local = {i: {"id": torch.tensor(i), "rank": rank} for i in owned}
         gathered = mdist.gather_submaps_to_rank0(local, 5)
         if rank == 0:
             q.put({"grads": [g.clone() for g in grads], "loss": lt, "pose_grads": [g.clone() for g in pg], "align": tl,
-                   "gathered": [int(g["id"]) for g in gathered], "owners": [g["rank"] for g in gathered], "mine": mine})
+                   "per_pair": per_pair.tolist(), "gathered": [int(g["id"]) for g in gathered], "owners": [g["rank"] for g in gathered], "mine": mine})
     finally:
         dist.destroy_process_group()
 
@@ -119,13 +122,18 @@ def test_world2_gloo_partitions_match_single_process():
     atlas = O.OracleAtlas(subs, Rp, tp)
     atlas.precompute([0])
     total = 0
+    per_pair = []
     for s in range(3):
         for d in range(s + 1, 3):
             Rs, ts = atlas.updated_submap_pose(s)
             Rd, td = atlas.updated_submap_pose(d)
-            total = total + O.pairwise_loss_latent(subs[s], subs[d], atlas.coords[(s, 0)], Rs, ts, Rd, td, 0)
+            val = O.pairwise_loss_latent(subs[s], subs[d], atlas.coords[(s, 0)], Rs, ts, Rd, td, 0)
+            per_pair.append(float(val.detach()))
+            total = total + val
     total.backward()
-    assert abs(float(res["align"]) - float(total)) < 1e-5 * abs(float(total))
+    # the host logic under test: the all-reduced total is the sum of the per-pair terms the ranks computed
+    assert abs(float(res["align"]) - sum(res["per_pair"])) < 1e-5 * abs(float(total)), (res["align"], res["per_pair"])
+    assert np.allclose(res["per_pair"], per_pair, rtol=1e-5), (res["per_pair"], per_pair)
     for a, p in zip(res["pose_grads"], atlas.rot + atlas.tra):
         ref = p.grad if p.grad is not None else torch.zeros_like(p)
         assert torch.allclose(a, ref, rtol=1e-4, atol=1e-6)
