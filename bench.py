@@ -40,7 +40,14 @@ LOSS_CFG = dict(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, t
 BYTES_PER_POINT = 12 + 8 + 4 + 1 + 4 + 4 + 256 + 256
 SURVEY_BYTES_PER_POINT = 1068   # SURVEY.md section 8d two-pass figure (fwd + bwd re-gather + eikonal scatter)
 FLOPS_PER_POINT = 2 * (2 * (8 * 64 + 64 * 64) + 64)  # MLP forward + Jacobian backward, FMA = 2 flops
-NCU_DRAM_BYTES_PER_LAUNCH = 119318016 + 11839488     # profiles/r01_ncu_mapping_step_tc.csv (2^20 points)
+if os.environ.get("MISO_MLP", "").lower().startswith("s"):
+    KERNEL_NAME = "mapping_step_kernel<2,4> (SIMT decoder) (+finalize)"
+elif os.environ.get("MISO_TC", "") == "1":
+    KERNEL_NAME = "mapping_step_tc_kernel<2,4> (one thread per point) (+finalize)"
+else:
+    KERNEL_NAME = "mapping_step_tc2_kernel<2,4,%s,%s> (two threads per point) (+finalize)" % (
+        os.environ.get("MISO_TC2_GROUPS", "4"), "unpaired" if os.environ.get("MISO_PAIR", "1") == "0" else "paired")
+NCU_DRAM_BYTES_PER_LAUNCH = 120513536 + 11079168     # profiles/r01_ncu_mapping_step_tc2.csv (2^20 points)
 
 
 def measured_hbm_peak():
@@ -252,15 +259,17 @@ def run_ours(args):
         "e2e": {"value": world * N_POINTS / (e2e_ms / args.steps * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "mapping_step_tc_kernel<2,4> (+finalize)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                       "kernel at this size (profiles/r01_ncu_mapping_step_tc.csv); below the algorithmic "
+                                       "kernel at this size (profiles/r01_ncu_mapping_step_tc2.csv); below the algorithmic "
                                        "bytes because the 64 MB grid and its gradient stay L2-resident",
                      "bytes_per_point": BYTES_PER_POINT, "survey_bytes_per_point": SURVEY_BYTES_PER_POINT,
                      "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
                      "fp32_equiv_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12,
-                     "decoder": os.environ.get("MISO_MLP", "tcgen05 3xTF32")},
+                     "decoder": os.environ.get("MISO_MLP", "tcgen05 3xTF32"),
+                     "floors_ms": {"red_v4_scatter_only": 0.121, "gather_only": 0.041,
+                                   "source": "profiles/r01_scatter_probe.json (benchmarks/scatter_probe.py, same batch)"}},
         "final_loss_terms": final_loss,
         "extra": {"align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
                   "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "

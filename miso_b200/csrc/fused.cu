@@ -581,6 +581,9 @@ struct MapArgs {
   const int32_t* eik_count;
   float* partials;
   float* sdf_out;
+  float inv_len[3];                       // 1/(bmax-bmin), computed on the host with the device's fp32 ops
+  float lvl_scale[MISO_MAX_LEVELS][3];    // (float)dim * inv_len: index-space -> world-space derivative scale
+  int dbg;   // MISO_DBG ablation bits (profiling only): 1 = no reductions, 2 = no corner loads, 4 = no g1 TMEM loads
 };
 
 template <int L, int C>
@@ -1026,7 +1029,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (int l = 0; l < L; ++l) {
       cells[l] = make_cell_lite(fl.level[l], xn);
       if (!active || ((fl.ignore_mask >> l) & 1u)) cells[l].valid = 0u;   // contributes zeros, scatters nothing
-      gather_level_lite<C, true>(fl.level[l], cells[l], f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+      CellLite cg = cells[l];
+      if (m.dbg & 2) cg.valid = 0u;
+      gather_level_lite<C, true>(fl.level[l], cg, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
     }
     float J[F];
     const float pred = decoder_tc<F, true>(t, f, J);
@@ -1073,7 +1078,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const float k = (use && nrm > 0.f) ? m.cfg.weight_eik * m.cfg.grad_scale * 2.f * e * inv_neik / nrm : 0.f;
       v[0] = k * gx, v[1] = k * gy, v[2] = k * gz;
     }
-    const unsigned nz = (a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) ? 1u : 0u;
+    const unsigned nz = ((a != 0.f || v[0] != 0.f || v[1] != 0.f || v[2] != 0.f) && !(m.dbg & 1)) ? 1u : 0u;
 #pragma unroll
     for (int l = 0; l < L; ++l) {
       const miso_level_t& lv = fl.level[l];
@@ -1149,6 +1154,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   tc_teardown<F>(t);
 }
+
+}  // namespace miso
+#include "fused_tc2.cuh"
+namespace miso {
 
 __global__ void mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
                                         miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out) {
@@ -1283,6 +1292,54 @@ static bool use_tensor_cores() {
   return cached == 1;
 }
 
+// MISO_TC=1 keeps the one-thread-per-point tensor-core kernel; default is the two-threads-per-point kernel
+// with MISO_TC2_GROUPS (3 or 4, default 4) tiles in flight per SM
+static int tc2_groups() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MISO_TC");
+    if (e && e[0] == '1') cached = 0;
+    else {
+      const char* g = getenv("MISO_TC2_GROUPS");
+      cached = (g && g[0] == '3') ? 3 : 4;
+    }
+  }
+  return cached;
+}
+
+#define MISO_DISPATCH_LC_TC2(L_, C_, ...)                                          \
+  do {                                                                             \
+    const int key_ = (L_)*100 + (C_);                                              \
+    switch (key_) {                                                                \
+      case 204: { constexpr int L = 2, C = 4; __VA_ARGS__; } break;                \
+      case 404: { constexpr int L = 4, C = 4; __VA_ARGS__; } break;                \
+      case 108: { constexpr int L = 1, C = 8; __VA_ARGS__; } break;                \
+      case 208: { constexpr int L = 2, C = 8; __VA_ARGS__; } break;                \
+      case 116: { constexpr int L = 1, C = 16; __VA_ARGS__; } break;               \
+      default: break;                                                              \
+    }                                                                              \
+  } while (0)
+
+static bool tc2_paired() {   // MISO_PAIR=0 keeps one corner per lane (profiling comparison)
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MISO_PAIR");
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+template <int L, int C, int G>
+static int launch_tc2(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t& fr, const MapArgs& m,
+                      cudaStream_t s) {
+  constexpr size_t smem = sizeof(Tc2Smem<L * C, G>) + 128;
+  auto k = tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true> : mapping_step_tc2_kernel<L, C, G, false>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nblocks = grid_for((m.N + G * 128 - 1) / (G * 128), 1, sm_count());
+  k<<<nblocks, G * 256, smem, s>>>(*field, *dec, fr, m);
+  return nblocks;
+}
+
 static miso_frames_t frames_or_none(const miso_frames_t* fr) {
   miso_frames_t z;
   z.ids = nullptr, z.R = nullptr, z.t = nullptr, z.num_frames = 0;
@@ -1398,8 +1455,30 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   MapArgs m;
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
+  for (int d = 0; d < 3; ++d) {
+    m.inv_len[d] = 1.0f / (field->bound[2 * d + 1] - field->bound[2 * d]);
+    for (int l = 0; l < field->num_levels; ++l) {
+      const miso_level_t& lv = field->level[l];
+      m.lvl_scale[l][d] = (float)(d == 0 ? lv.X : (d == 1 ? lv.Y : lv.Z)) * m.inv_len[d];
+    }
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("MISO_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    m.dbg = dbg;
+  }
   int nblocks = 0;
-  if (use_tensor_cores() && fits_int32(field)) {
+  const int F_ = field->num_levels * field->level[0].C;
+  if (use_tensor_cores() && fits_int32(field) && tc2_groups() != 0 && F_ % 8 == 0 && N < ((int64_t)1 << 31) - ((int64_t)1 << 26)) {
+    const int G_ = tc2_groups();
+    MISO_DISPATCH_LC_TC2(field->num_levels, field->level[0].C, {
+      nblocks = G_ == 3 ? launch_tc2<L, C, 3>(field, dec, fr, m, s) : launch_tc2<L, C, 4>(field, dec, fr, m, s);
+    });
+    MISO_REQUIRE(nblocks > 0, "mapping_step(tc2): unsupported (levels=%d, channels=%d)", field->num_levels, field->level[0].C);
+  } else if (use_tensor_cores() && fits_int32(field)) {
     MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
       constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
       auto k = mapping_step_tc_kernel<L, C>;
