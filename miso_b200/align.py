@@ -1,5 +1,6 @@
 """Latent-space submap alignment on the B200 path.  Same names / arguments as the reference:
 
+    pairwise_loss_sdf                     grid_opt/align/miso.py:14-113
     pairwise_loss_latent                  grid_opt/align/miso.py:116-211
     generic_align_multiple_submaps        grid_opt/align/base.py:89-163
     align_multiple_submaps_hierarchical   grid_opt/align/miso.py:217-322
@@ -230,6 +231,78 @@ def pairwise_loss_latent(grid_atlas: GridAtlas, data_loader, src_id: int, dst_id
     return {loss_key: batch.losses(align_weight)[0]}
 
 
+def get_batch(data_loader, device="cuda:0"):
+    """utils.py:495-498: first batch of the loader, moved to the device."""
+    for model_input, gt in data_loader:
+        model_input = {k: v.to(device) for k, v in model_input.items()}
+        gt = {k: v.to(device) for k, v in gt.items()}
+        return model_input, gt
+    raise RuntimeError("empty data loader")
+
+
+def pairwise_loss_sdf(grid_atlas: GridAtlas, data_loader, src_id: int, dst_id: int, align_weight=3000,
+                      align_loss="L2", use_bound=True, stability_thresh=0, covariance_thresh=None,
+                      subsample_points=None, gm_scale_sdf=0.1, device="cuda:0"):
+    """miso.py:14-113: SDF-space alignment residual of one pair on the SOURCE submap's dataset samples.
+
+    Samples of the batch whose keyframe belongs to `src_id` are taken to the submap frame (one batched gather of
+    the keyframe poses instead of the per-keyframe loop at :44-53), to the world and into `dst_id`; both submaps are
+    evaluated by the fused grid+decoder kernel (GridNet.forward, differentiable w.r.t. the coordinates), so the
+    pose gradients flow through d sdf / d x exactly as in the reference.  L2 / L1 / GM as in :100-110."""
+    assert src_id < grid_atlas.num_submaps
+    assert dst_id < grid_atlas.num_submaps
+    if covariance_thresh is not None:
+        raise NotImplementedError
+    if stability_thresh > 0:
+        raise NotImplementedError("stability pruning needs the stability grids, which are outside the hot path "
+                                  "(SURVEY.md section 8: unused unless the stability loss is on)")
+    model_input, gt = get_batch(data_loader, device)
+    submap_from = grid_atlas.get_submap(src_id)
+    submap_to = grid_atlas.get_submap(dst_id)
+    loss_dict = {}
+    kf_all = model_input["sample_frame_ids"][0, :, 0]
+    submap_idxs = grid_atlas.submap_id_for_kf_batch(kf_ids=kf_all)
+    sample_indices = torch.nonzero(submap_idxs == src_id, as_tuple=False).squeeze(1)
+    if sample_indices.numel() == 0:
+        return {}
+    coords_kf = model_input["coords_frame"][0, sample_indices, :]
+    kf_local = kf_all[sample_indices] - grid_atlas.anchor_kf_for_submap(src_id)
+    R_kf, t_kf = submap_from.all_kf_poses()                       # (K,3,3), (K,3,1): updated_kf_pose of every keyframe
+    coords_from = torch.einsum("nij,nj->ni", R_kf[kf_local], coords_kf) + t_kf[kf_local].squeeze(-1)
+    mask_valid = gt["sdf_valid"][0][sample_indices, :]
+    R_world_from, t_world_from = grid_atlas.updated_submap_pose(src_id, device)
+    R_world_to, t_world_to = grid_atlas.updated_submap_pose(dst_id, device)
+    coords_world = utils_geometry.transform_points_to(coords_from, R_world_from, t_world_from)
+    coords_to = utils_geometry.transfrom_points_from(coords_world, R_world_to, t_world_to)
+    if subsample_points is not None:
+        down_points = min(subsample_points, coords_from.shape[0])
+        down_indices = torch.from_numpy(np.random.choice(coords_from.shape[0], down_points, replace=False)).to(
+            coords_from.device)
+        coords_from = coords_from[down_indices, :]
+        coords_to = coords_to[down_indices, :]
+        mask_valid = mask_valid[down_indices, :]
+    if use_bound:
+        mask_bnd = utils_geometry.coords_in_bound(coords_to, submap_to.bound.to(coords_to.device))
+        assert mask_bnd.shape == mask_valid.shape
+        mask_valid = torch.logical_and(mask_bnd, mask_valid)
+    valid_indices = torch.nonzero(mask_valid, as_tuple=False)[:, 0]
+    p_from = coords_from[valid_indices, :]
+    p_to = coords_to[valid_indices, :]
+    align_constraint = submap_from(p_from) - submap_to(p_to)
+    loss_key = f"align_sdf_{src_id}_{dst_id}"
+    if align_loss == "L2":
+        loss_dict[loss_key] = torch.mean(align_constraint ** 2) * align_weight
+    elif align_loss == "L1":
+        loss_dict[loss_key] = torch.mean(torch.linalg.vector_norm(align_constraint, dim=1)) * align_weight
+    elif align_loss == "GM":
+        e = align_constraint.clone().detach()
+        w = gm_scale_sdf / (gm_scale_sdf + e ** 2) ** 2
+        loss_dict[loss_key] = torch.mean(w * align_constraint ** 2) * align_weight
+    else:
+        raise ValueError(f"Invalid align loss: {align_loss}!")
+    return loss_dict
+
+
 def relative_param_change(params_curr, params_prev=None):
     """utils.py:507-516 without the per-iteration .item() host sync: returns a 0-dim tensor (inf first)."""
     if params_prev is None:
@@ -272,6 +345,11 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
         for submap_id in range(1, grid_atlas.num_submaps):  # submap 0 stays fixed (base.py:104-108)
             params += list(grid_atlas.params_for_submap_pose(submap_id))
         return params
+
+    if pairwise_loss_tuple is not None and callable(pairwise_loss_tuple[1]):
+        return _generic_align_with_loss_func(grid_atlas, dataset, pairwise_loss_tuple, pose_params, num_iters, lr,
+                                             rel_change_thresh, submap_pairs, check_intersection, pose_reg_weight,
+                                             pose_thresh_rad, pose_thresh_m, save_iterations, pair_filter, allreduce)
 
     optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr, capturable=bool(use_cuda_graph))
     if submap_pairs is None:
@@ -358,6 +436,69 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
     return info
 
 
+def _make_loader(dataset):
+    """base.py:112: DataLoader(dataset, shuffle=True, batch_size=1); plain iterables of (model_input, gt) pass."""
+    if dataset is None:
+        return None
+    if hasattr(dataset, "__getitem__") and hasattr(dataset, "__len__") and not isinstance(dataset, (list, tuple)):
+        return torch.utils.data.DataLoader(dataset, shuffle=True, batch_size=1, num_workers=0)
+    return dataset
+
+
+def _generic_align_with_loss_func(grid_atlas, dataset, pairwise_loss_tuple, pose_params, num_iters, lr,
+                                  rel_change_thresh, submap_pairs, check_intersection, pose_reg_weight,
+                                  pose_thresh_rad, pose_thresh_m, save_iterations, pair_filter, allreduce):
+    """base.py:89-163 verbatim in structure: a caller-supplied `loss_func(grid_atlas, loader, src, dst) -> dict`
+    per pair (used by the SDF-space fine-tune, which is off in the shipped configs)."""
+    loss_name, loss_func = pairwise_loss_tuple
+    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr)
+    loader = _make_loader(dataset)
+    if submap_pairs is None:
+        submap_pairs = [(s, d) for s in range(grid_atlas.num_submaps) for d in range(s + 1, grid_atlas.num_submaps)]
+    my_pairs = list(submap_pairs) if pair_filter is None else [p for i, p in enumerate(submap_pairs) if pair_filter(i, p)]
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    iteration_results, losses_hist, params_prev, it = dict(), [], None, 0
+    while it <= num_iters:
+        if save_iterations:
+            with torch.no_grad():
+                iteration_results[it] = torch.stack([utils_geometry.pose_matrix(*grid_atlas.updated_submap_pose(i))
+                                                     for i in range(grid_atlas.num_submaps)], 0)
+        optimizer.zero_grad()
+        loss_dict = {}
+        for src_id, dst_id in my_pairs:
+            if check_intersection:
+                with torch.no_grad():
+                    if not bool(grid_atlas.check_submap_intersection(src_id, dst_id)):   # base.py:133-135
+                        continue
+            pair_loss_dict = loss_func(grid_atlas, loader, src_id, dst_id)
+            for key, val in pair_loss_dict.items():
+                pair_loss_dict[key] = torch.nan_to_num(val)
+            loss_dict.update(pair_loss_dict)
+        if pose_reg_weight > 0:
+            loss_dict.update(grid_atlas_pose_trust_region_loss(grid_atlas, thresh_rad=pose_thresh_rad,
+                                                               thresh_m=pose_thresh_m, weight=pose_reg_weight))
+        total_loss = sum(loss_dict.values()) if loss_dict else None
+        if isinstance(total_loss, torch.Tensor) and total_loss.requires_grad and not torch.isnan(total_loss):
+            total_loss.backward()
+            if allreduce is not None:
+                allreduce([p.grad for p in pose_params() if p.grad is not None])
+            optimizer.step()
+        losses_hist.append(total_loss.detach() if isinstance(total_loss, torch.Tensor) else torch.zeros((), device=grid_atlas.device))
+        params_curr = [p.clone().detach() for p in pose_params()]
+        relchange = relative_param_change(params_curr, params_prev)
+        params_prev = params_curr
+        if rel_change_thresh > 0 and relchange is not None and float(relchange) < rel_change_thresh:
+            break
+        it += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    return {"cpu_time_sec": time.perf_counter() - t0, "gpu_time_sec": ev0.elapsed_time(ev1) / 1e3,
+            "iteration_results": iteration_results, "losses": torch.stack(losses_hist).cpu() if losses_hist else None,
+            "iterations": it if it <= num_iters else num_iters + 1}
+
+
 def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, level_iters=10, finetune_iters=10,
                                         level_thresh=0.0, lr=1e-2, align_weight=3000, align_loss="L2",
                                         use_bound=True, stability_thresh=0, subsample_points=None,
@@ -365,13 +506,12 @@ def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, lev
                                         pose_reg_weight=0, pose_thresh_m=1.0, pose_thresh_rad=1.0, gm_scale_sdf=0.1,
                                         device="cuda:0", verbose=True, save_iterations=False, pair_filter=None,
                                         allreduce=None):
-    """miso.py:217-322.  The SDF-space fine-tune (pairwise_loss_sdf) is off in the shipped configs
-    (skip_finetune: True, scannet.yaml:63) and is not part of this path."""
+    """miso.py:217-322: latent-space levels (one batched launch per iteration), then -- unless `skip_finetune`
+    (True in the shipped configs, scannet.yaml:63) -- the SDF-space fine-tune with pairwise_loss_sdf on `dataset`."""
     if align_loss != "L2" or not use_bound or stability_thresh > 0:
         raise NotImplementedError("fused alignment implements align_loss='L2', use_bound=True, stability_thresh=0")
-    if not skip_finetune:
-        raise NotImplementedError("SDF-space fine-tune (pairwise_loss_sdf) is outside the fused path; "
-                                  "pass skip_finetune=True as the shipped configs do")
+    if not skip_finetune and dataset is None:
+        raise ValueError("the SDF-space fine-tune needs a dataset of (model_input, gt) batches")
     grid_atlas.precompute_coordinates_for_alignment()
     info = dict()
     cpu_total, gpu_total = 0.0, 0.0
@@ -388,6 +528,19 @@ def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, lev
         cpu_total += level_dict["cpu_time_sec"]
         gpu_total += level_dict["gpu_time_sec"]
         info[loss_name] = level_dict
+    if not skip_finetune:
+        def loss_func(atlas, loader, src_id, dst_id):
+            return pairwise_loss_sdf(atlas, loader, src_id, dst_id, align_weight=align_weight, align_loss=align_loss,
+                                     use_bound=use_bound, stability_thresh=stability_thresh,
+                                     subsample_points=subsample_points, gm_scale_sdf=gm_scale_sdf, device=device)
+        loss_name = f"hier_sdf_{align_loss}"
+        final_dict = generic_align_multiple_submaps(
+            grid_atlas, dataset, (loss_name, loss_func), lr=lr, num_iters=finetune_iters, submap_pairs=submap_pairs,
+            pose_reg_weight=pose_reg_weight, pose_thresh_m=pose_thresh_m, pose_thresh_rad=pose_thresh_rad,
+            verbose=verbose, save_iterations=save_iterations, pair_filter=pair_filter, allreduce=allreduce)
+        cpu_total += final_dict["cpu_time_sec"]
+        gpu_total += final_dict["gpu_time_sec"]
+        info[loss_name] = final_dict
     info["cpu_time_sec"] = cpu_total
     info["gpu_time_sec"] = gpu_total
     return info

@@ -611,6 +611,13 @@ class GridAtlas(BaseNet):
         table = torch.tensor(self._kf_id_to_submap_id, device=kf_ids.device)
         return table[kf_ids]
 
+    def updated_kf_pose_in_submap(self, kf_id: int, submap_id: int):
+        """grid_atlas.py:286-300."""
+        expect_submap_id = self.submap_id_for_kf(kf_id)
+        assert expect_submap_id == submap_id, f"Wrong submap for KF {kf_id}! Expect {expect_submap_id}, got {submap_id}."
+        kf_id_submap = kf_id - self.anchor_kf_for_submap(submap_id)
+        return self.get_submap(submap_id).updated_kf_pose(kf_id_submap)
+
     def initial_submap_pose(self, submap_id: int):
         return self.R_world_submap_list[submap_id], self.t_world_submap_list[submap_id]
 

@@ -140,6 +140,100 @@ def gen_align():
     np.savez_compressed(os.path.join(OUT, "align.npz"), **out)
 
 
+def gen_align_sdf():
+    """pairwise_loss_sdf (miso.py:14-113) on a 2-submap atlas with two keyframes per submap; L2 / L1 / GM."""
+    from grid_opt.models.grid_atlas import GridAtlas
+    import grid_opt.align.miso as amiso
+    from oracle import oracle as O
+    cfg = ref_loader.reference_model_cfg(ABOUND, base_cell_size=1.0, per_level_scale=2, num_poses=2)
+    Rt, tt = synth.submap_layout(2, spacing=(4.0, 3.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=4.0, trans_m=0.3)
+    atlas = GridAtlas(cfg, device="cpu")
+    shapes = O.level_shapes(ABOUND, 1.0, 2, 2, 4)
+    Rk, tk = synth.keyframe_poses(4, ABOUND, seed=3, margin=1.0)
+    out = {"bound": np.asarray(ABOUND, np.float32), "kf.R": _np(Rk), "kf.t": _np(tk)}
+    dec_sd = synth.decoder_weights(8, seed=0)
+    for i in range(2):
+        atlas.add_submap(torch.tensor(ABOUND), Rp[i], tp[i], num_poses=2)
+        for k in range(2):
+            atlas.add_kf(Rk[2 * i + k], tk[2 * i + k])
+        feats = synth.fill_submap_from_field(shapes, ABOUND, Rt[i], tt[i])
+        sm = atlas.get_submap(i)
+        sm.decoder.load_state_dict(dec_sd)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(feats[l] * 0.3)
+                out[f"sm{i}.feat{l}"] = _np(feats[l] * 0.3)
+        out[f"sm{i}.R"], out[f"sm{i}.t"] = _np(Rp[i]), _np(tp[i])
+    for k, v in dec_sd.items():
+        out["dec." + k] = _np(v)
+    mi, gt, _ = synth.rgbd_batch(1500, num_kf=4, bound=ABOUND, seed=9, poses=(Rk, tk), wall_margin=0.5)
+    for k, v in {**mi, **gt}.items():
+        out["in." + k] = _np(v)
+    loader = [(mi, gt)]
+    for loss in ("L2", "L1", "GM"):
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        ld = amiso.pairwise_loss_sdf(atlas, loader, 0, 1, align_loss=loss, device="cpu")
+        (key, val), = ld.items()
+        val.backward()
+        out[f"{loss}.loss"] = _np(val)
+        out[f"{loss}.key"] = np.asarray(key)
+        for i in range(2):
+            out[f"{loss}.grad_rot{i}"] = _np(atlas.rotation_corrections[i].grad)
+            out[f"{loss}.grad_tra{i}"] = _np(atlas.translation_corrections[i].grad)
+    np.savez_compressed(os.path.join(OUT, "align_sdf.npz"), **out)
+
+
+def gen_variants():
+    """Loss variants of the other trainers + dense queries: TsdfLoss3D (loss.py:71-144, finite-difference eikonal on
+    uniform points), iSDF sdf_loss/tot_loss (loss_isdf.py:280-365), extract_fields (utils_sdf.py:69-86)."""
+    import grid_opt.loss as rloss
+    import grid_opt.loss_isdf as risdf
+    import grid_opt.diff as rdiff
+    import packaging.version  # noqa: F401  (utils_sdf.py:63 uses packaging.version without importing the submodule)
+    import grid_opt.utils.utils_sdf as rsdf
+    out = {"bound": np.asarray(BOUND, np.float32)}
+    net = make_ref_gridnet(BOUND)
+    net.unlock_feature()
+    for l in range(2):
+        out[f"feat{l}"] = _np(net.features[l].feature)
+    for k, v in net.decoder.state_dict().items():
+        out["dec." + k] = _np(v)
+    g = torch.Generator().manual_seed(21)
+    N = 300
+    coords = (torch.rand(N, 3, generator=g) * 2 - 1) * torch.tensor([1.9, 0.95, 1.9])
+    gt_sdf = torch.randn(N, 1, generator=g) * 0.1
+    valid = (torch.rand(N, 1, generator=g) > 0.3)
+    sign = torch.where(gt_sdf > 0.05, torch.ones_like(gt_sdf), torch.where(gt_sdf < -0.05, -torch.ones_like(gt_sdf),
+                                                                         torch.zeros_like(gt_sdf)))
+    out["tsdf.in_coords"], out["tsdf.in_sdf"], out["tsdf.in_valid"], out["tsdf.in_sign"] = _np(coords), _np(gt_sdf), _np(valid), _np(sign)
+    np.random.seed(123)
+    L = rloss.TsdfLoss3D(grad_method="finitediff", finite_diff_eps=0.024)
+    ld = L.compute(net, {"coords": coords[None]}, {"sdf": gt_sdf[None], "sdf_valid": valid[None], "sdf_sign": sign[None]})
+    sum(ld.values()).backward()
+    for k, v in ld.items():
+        out[f"tsdf.{k}"] = _np(v)
+    for l in range(2):
+        out[f"tsdf.grad_feat{l}"] = _np(net.features[l].feature.grad)
+        net.features[l].feature.grad = None
+    # iSDF: shapes as in compute_default (pc (1,N,3), bounds (1,N,1), sdf (N,1), grad (1,N,3))
+    bounds = torch.rand(N, 1, generator=g) * 0.4
+    pc = coords.clone()
+    sdf = net(pc)
+    gradv = rdiff.gradient3d(pc, net, "finitediff", finite_diff_eps=0.024)
+    mat, fs = risdf.sdf_loss(sdf, bounds[None], 0.15, loss_type="L1")
+    eik = torch.abs(gradv[None].norm(2, dim=-1) - 1)
+    total, _, _ = risdf.tot_loss(mat, None, eik, fs, bounds[None], 0.1, 5.38, 0.0, 0.268)
+    total.backward()
+    out["isdf.bounds"], out["isdf.total"] = _np(bounds), _np(total)
+    for l in range(2):
+        out[f"isdf.grad_feat{l}"] = _np(net.features[l].feature.grad)
+    bt = torch.tensor(BOUND)
+    out["fields.u"] = rsdf.extract_fields(bt[:, 0], bt[:, 1], 20, lambda p: net(p))
+    np.savez_compressed(os.path.join(OUT, "variants.npz"), **out)
+
+
 def main():
     ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -148,6 +242,8 @@ def main():
     gen_gridnet()
     gen_mapping()
     gen_align()
+    gen_align_sdf()
+    gen_variants()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

@@ -118,3 +118,103 @@ def test_alignment_against_reference_outputs():
         for i in range(2):
             assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"L{level}.grad_rot{i}"])) < 1e-4
             assert rel_err(atlas.translation_corrections[i].grad, T(z[f"L{level}.grad_tra{i}"])) < 1e-4
+
+
+def _sdf_atlas(z):
+    from miso_b200.models import GridAtlas
+    bound = z["bound"].tolist()
+    atlas = GridAtlas(synth.model_cfg(bound, base_cell_size=1.0, per_level_scale=2, num_poses=2), device="cuda")
+    Rk, tk = T(z["kf.R"]), T(z["kf.t"])
+    dec_sd = {k[len("dec."):]: T(z[k]) for k in z.files if k.startswith("dec.")}
+    for i in range(2):
+        atlas.add_submap(torch.tensor(bound), T(z[f"sm{i}.R"]), T(z[f"sm{i}.t"]), num_poses=2)
+        for k in range(2):
+            atlas.add_kf(Rk[2 * i + k], tk[2 * i + k])
+        sm = atlas.get_submap(i)
+        sm.decoder.load_state_dict(dec_sd)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(T(z[f"sm{i}.feat{l}"]).cuda())
+    mi = {k: T(z["in." + k]) for k in ("coords_frame", "sample_frame_ids", "weights")}
+    gt = {k: T(z["in." + k]) for k in ("sdf", "sdf_valid", "sdf_signs")}
+    return atlas, [(mi, gt)]
+
+
+@pytest.mark.parametrize("loss", ["L2", "L1", "GM"])
+def test_alignment_sdf_against_reference_outputs(loss):
+    """pairwise_loss_sdf (miso.py:14-113) through the fused grid+decoder kernel vs the reference's outputs."""
+    from miso_b200.align import pairwise_loss_sdf
+    z = load("align_sdf.npz")
+    atlas, loader = _sdf_atlas(z)
+    assert atlas.get_submap(0).fused_spec() is not None
+    (key, val), = pairwise_loss_sdf(atlas, loader, 0, 1, align_loss=loss, device="cuda").items()
+    assert key == str(z[f"{loss}.key"])
+    val.backward()
+    # the residual is a DIFFERENCE of two forward values that are each within 1e-5: allow 5e-5 on the loss
+    assert rel_err(val, T(z[f"{loss}.loss"])) < 5e-5
+    for i in range(2):
+        assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"{loss}.grad_rot{i}"])) < 1e-4
+        assert rel_err(atlas.translation_corrections[i].grad, T(z[f"{loss}.grad_tra{i}"])) < 1e-4
+
+
+def test_hierarchical_alignment_with_sdf_finetune_runs():
+    """align_multiple_submaps_hierarchical with skip_finetune=False: latent levels + SDF-space fine-tune reduce the
+    SDF alignment loss of the perturbed pair."""
+    from miso_b200.align import align_multiple_submaps_hierarchical, pairwise_loss_sdf
+    z = load("align_sdf.npz")
+    atlas, loader = _sdf_atlas(z)
+    with torch.no_grad():
+        before = float(list(pairwise_loss_sdf(atlas, loader, 0, 1, device="cuda").values())[0])
+    info = align_multiple_submaps_hierarchical(atlas, loader, level_iters=15, finetune_iters=15, lr=1e-2,
+                                               latent_levels=[0, 1], skip_finetune=False, device="cuda", verbose=False)
+    assert "hier_sdf_L2" in info and info["hier_sdf_L2"]["iterations"] == 16
+    with torch.no_grad():
+        after = float(list(pairwise_loss_sdf(atlas, loader, 0, 1, device="cuda").values())[0])
+    assert after < before
+
+
+def test_loss_variants_and_dense_queries_against_reference_outputs():
+    """TsdfLoss3D, the iSDF loss epilogues and extract_fields on the fused kernels vs the reference's outputs
+    (finite-difference eikonal, which the reference can run on CPU), then the analytic (fused, second-order)
+    eikonal against the oracle's gather restatement."""
+    from miso_b200.loss_variants import TsdfLoss3D, isdf_loss
+    from miso_b200.utils_sdf import extract_fields
+    from oracle import oracle as O
+    z = load("variants.npz")
+    net = gpu_net(z, z)
+    net.unlock_feature()
+    coords, gts = T(z["tsdf.in_coords"]).cuda(), T(z["tsdf.in_sdf"]).cuda()
+    valid, sign = T(z["tsdf.in_valid"]).cuda(), T(z["tsdf.in_sign"]).cuda()
+    np.random.seed(123)
+    L = TsdfLoss3D(grad_method="finitediff", finite_diff_eps=0.024)
+    ld = L.compute(net, {"coords": coords[None]}, {"sdf": gts[None], "sdf_valid": valid[None], "sdf_sign": sign[None]})
+    sum(ld.values()).backward()
+    for k in ("sdf", "pos_space", "neg_space", "eik"):
+        assert rel_err(ld[k], T(z[f"tsdf.{k}"])) < 2e-5, k
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, T(z[f"tsdf.grad_feat{l}"])) < 1e-4
+        net.features[l].feature.grad = None
+    total, _ = isdf_loss(net, coords, T(z["isdf.bounds"]).cuda(), 0.15, 5.38, 0.268, 0.1, grad_method="finitediff",
+                         finite_diff_eps=0.024)
+    total.backward()
+    assert rel_err(total, T(z["isdf.total"])) < 1e-5
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, T(z[f"isdf.grad_feat{l}"])) < 1e-4
+        net.features[l].feature.grad = None
+    b = T(z["bound"])
+    u = extract_fields(b[:, 0], b[:, 1], 20, net, device="cuda", max_points=3000)   # several slabs
+    assert rel_err(T(u), T(z["fields.u"])) < 1e-5
+    # analytic eikonal (one fused launch, double backward in the scatter) vs the oracle's second-order restatement
+    feats = [T(z[f"feat{l}"]) for l in range(2)]
+    dec = O.make_decoder(8)
+    dec.load_state_dict({k[len("dec.network."):]: T(z[k]) for k in z.files if k.startswith("dec.network.")})
+    onet = O.OracleGridNet(z["bound"].tolist(), feats, dec, second_order=True)
+    xo = coords.cpu().clone().requires_grad_(True)
+    go = O.gradient3d(xo, onet, "autograd", create_graph=True)
+    want = O.isdf_total_loss(onet(xo), T(z["isdf.bounds"]), go, 0.15, 5.38, 0.268, 0.1)
+    want.backward()
+    total, _ = isdf_loss(net, coords, T(z["isdf.bounds"]).cuda(), 0.15, 5.38, 0.268, 0.1, grad_method="autograd")
+    total.backward()
+    assert rel_err(total, want) < 1e-5
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, onet.features[l].grad) < 1e-4
