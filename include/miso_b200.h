@@ -221,6 +221,14 @@ int miso_morton_keys(const float* x, int64_t N, const float bound[6], uint32_t* 
 int miso_transform_points(const float* x, const int64_t* ids, const float* R, const float* t, int32_t num_frames,
                           int64_t N, float* y, miso_stream_t stream);
 
+/* Compact host batches: the reference's dataset emits sample_frame_ids as int64 and the two masks
+ * sdf_valid = |sdf| < trunc, sdf_signs = +-1 beyond +-trunc as separate tensors (sdf_rgbd.py:452-455,
+ * submap_dataset.py:57-76): 33 B/point over PCIe.  A dataset that ships int16 ids and only the sdf moves
+ * 18 B/point; this entry rebuilds the int64 ids and both masks on the device (bit-identical to the
+ * reference's host-side expressions). */
+int miso_expand_batch(const int16_t* ids16, const float* sdf, float trunc_dist, int64_t N, int64_t* ids64,
+                      uint8_t* valid, float* sign, miso_stream_t stream);
+
 /* torch.optim.Adam (no amsgrad, no weight decay) single-tensor step; optionally zeroes g in the
  * same pass so the next scatter starts from a clean buffer (trainer.py:216-217 + zero_grad). */
 int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -124,7 +124,32 @@ __global__ void __launch_bounds__(kThreads)
 
 }  // namespace miso
 
+namespace miso {
+// compact host batch -> the tensors the mapping step consumes (see miso_expand_batch in the header)
+__global__ void expand_batch_kernel(const int16_t* __restrict__ ids16, const float* __restrict__ sdf, float trunc,
+                                    int64_t N, int64_t* __restrict__ ids64, uint8_t* __restrict__ valid,
+                                    float* __restrict__ sign) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    if (ids64) ids64[n] = (int64_t)ids16[n];
+    const float s = sdf[n];
+    valid[n] = fabsf(s) < trunc ? 1 : 0;                      // sdf_rgbd.py:452
+    sign[n] = s > trunc ? 1.0f : (s < -trunc ? -1.0f : 0.0f);  // sdf_rgbd.py:453-455
+  }
+}
+}  // namespace miso
+
 using namespace miso;
+
+extern "C" int miso_expand_batch(const int16_t* ids16, const float* sdf, float trunc_dist, int64_t N, int64_t* ids64,
+                                 uint8_t* valid, float* sign, miso_stream_t stream) {
+  MISO_REQUIRE(N >= 0 && (N == 0 || (sdf && valid && sign)), "expand_batch: null argument");
+  MISO_REQUIRE(!ids64 || ids16, "expand_batch: ids64 requested without ids16");
+  MISO_REQUIRE(trunc_dist > 0.f, "expand_batch: trunc_dist must be positive");
+  if (N == 0) return MISO_OK;
+  expand_batch_kernel<<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, (cudaStream_t)stream>>>(
+      ids16, sdf, trunc_dist, N, ids64, valid, sign);
+  return check_launch("expand_batch");
+}
 
 extern "C" const char* miso_last_error_string(void) { return g_err; }
 extern "C" int miso_abi_version(void) { return MISO_ABI_VERSION; }

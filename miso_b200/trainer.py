@@ -29,6 +29,69 @@ def prepare_batch(model_input, gt, device="cuda:0"):
     return {k: mv(v) for k, v in model_input.items()}, {k: mv(v) for k, v in gt.items()}
 
 
+class CompactBatch:
+    """Host batch in the compact wire format (18 B/point instead of the reference dict's 33 B/point):
+    coords_frame (N,3) f32, sample_frame_ids as int16, sdf (N,) f32 and -- only when they are not all ones --
+    weights (N,) f32.  `sdf_valid` / `sdf_signs` are NOT shipped: the reference's datasets define them as
+    |sdf| < trunc and +-1 beyond +-trunc (sdf_rgbd.py:452-455) and `miso_expand_batch` rebuilds them (and the
+    int64 ids) on the device, bit-identically.  Build with `CompactBatch.from_reference` -- it verifies that the
+    masks of the given batch really are those functions of the sdf and refuses otherwise."""
+
+    def __init__(self, coords, ids16, sdf, weights, trunc_dist):
+        self.coords, self.ids16, self.sdf, self.weights, self.trunc_dist = coords, ids16, sdf, weights, float(trunc_dist)
+
+    @staticmethod
+    def from_reference(model_input, gt, trunc_dist, pin=True):
+        coords = model_input["coords_frame"][0].contiguous().float()
+        ids = model_input["sample_frame_ids"][0, :, 0]
+        sdf = gt["sdf"][0, :, 0].contiguous().float()
+        if int(ids.max()) > 32767 or int(ids.min()) < 0:
+            raise ValueError("compact batches carry keyframe ids as int16")
+        valid = torch.abs(sdf) < trunc_dist
+        signs = torch.zeros_like(sdf)
+        signs[sdf < -trunc_dist] = -1
+        signs[sdf > trunc_dist] = 1
+        if not torch.equal(valid, gt["sdf_valid"][0, :, 0].bool()) or not torch.equal(signs, gt["sdf_signs"][0, :, 0].float()):
+            raise ValueError("sdf_valid / sdf_signs of this batch are not the dataset's functions of sdf and "
+                             "trunc_dist; ship the reference format instead")
+        w = model_input["weights"][0, :, 0].contiguous().float()
+        w = None if bool((w == 1).all()) else w
+        out = [coords, ids.to(torch.int16).contiguous(), sdf, w]
+        if pin:
+            out = [t.pin_memory() if t is not None else None for t in out]
+        return CompactBatch(*out, trunc_dist)
+
+    def tensors(self):
+        d = {"coords": self.coords, "ids16": self.ids16, "sdf": self.sdf}
+        if self.weights is not None:
+            d["weights"] = self.weights
+        return d
+
+
+def expand_compact_on_device(dev_tensors: Dict[str, torch.Tensor], trunc_dist: float, cache: dict) -> Batch:
+    """Device-side inverse of CompactBatch.from_reference: one `miso_expand_batch` launch; output buffers are
+    allocated once per shape (`cache`) and laid out as the reference's batch dict."""
+    from . import _lib
+    lib = _lib.load()
+    coords, ids16, sdf = dev_tensors["coords"], dev_tensors["ids16"], dev_tensors["sdf"]
+    N, dev = coords.shape[0], coords.device
+    key = (N, dev)
+    if cache.get("key") != key:
+        cache.clear()
+        cache.update(key=key, ids=torch.empty((1, N, 1), dtype=torch.int64, device=dev),
+                     valid=torch.empty((1, N, 1), dtype=torch.uint8, device=dev),
+                     sign=torch.empty((1, N, 1), dtype=torch.float32, device=dev),
+                     ones=torch.ones((1, N, 1), dtype=torch.float32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(lib.miso_expand_batch(ids16.data_ptr(), sdf.data_ptr(), float(trunc_dist), N, cache["ids"].data_ptr(),
+                                         cache["valid"].data_ptr(), cache["sign"].data_ptr(), _lib.stream_ptr(dev)),
+                   "expand_batch")
+    w = dev_tensors["weights"].view(1, N, 1) if "weights" in dev_tensors else cache["ones"]
+    model_input = {"coords_frame": coords.view(1, N, 3), "sample_frame_ids": cache["ids"], "weights": w}
+    gt = {"sdf": sdf.view(1, N, 1), "sdf_valid": cache["valid"].view(torch.bool), "sdf_signs": cache["sign"]}
+    return model_input, gt
+
+
 class HostBatchStager:
     """Double-buffered host -> device staging of (model_input, gt) batches on a copy stream.
 
@@ -45,9 +108,13 @@ class HostBatchStager:
         self.free = [None] * slots       # compute-stream event: consumer enqueued
         self.h2d_bytes = 0
         self._next = 0
+        self.compact = [None] * slots    # trunc_dist of a CompactBatch staged in the slot (None: reference format)
+        self._expand_cache = [dict() for _ in range(slots)]
 
     def _buffers(self, slot, batch):
         bufs = self.slots[slot]
+        if isinstance(batch, CompactBatch):
+            batch = (batch.tensors(), {})
         model_input, gt = batch
         ok = bufs is not None and all(k in bufs[0] and bufs[0][k].shape == v.shape and bufs[0][k].dtype == v.dtype
                                       for k, v in model_input.items()) and \
@@ -63,6 +130,9 @@ class HostBatchStager:
         slot = self._next
         self._next = (self._next + 1) % len(self.slots)
         bufs = self._buffers(slot, batch)
+        self.compact[slot] = batch.trunc_dist if isinstance(batch, CompactBatch) else None
+        if isinstance(batch, CompactBatch):
+            batch = (batch.tensors(), {})
         nbytes = 0
         with torch.cuda.stream(self.stream):
             if self.free[slot] is not None:
@@ -79,6 +149,8 @@ class HostBatchStager:
 
     def acquire(self, slot: int) -> Batch:
         torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        if self.compact[slot] is not None:
+            return expand_compact_on_device(self.slots[slot][0], self.compact[slot], self._expand_cache[slot])
         return self.slots[slot]
 
     def release(self, slot: int):

@@ -208,7 +208,23 @@ def gen_variants():
     sign = torch.where(gt_sdf > 0.05, torch.ones_like(gt_sdf), torch.where(gt_sdf < -0.05, -torch.ones_like(gt_sdf),
                                                                          torch.zeros_like(gt_sdf)))
     out["tsdf.in_coords"], out["tsdf.in_sdf"], out["tsdf.in_valid"], out["tsdf.in_sign"] = _np(coords), _np(gt_sdf), _np(valid), _np(sign)
-    np.random.seed(123)
+    # pick a numpy seed whose eikonal points keep every ReLU pre-activation of every finite-difference evaluation
+    # away from 0: at a kink (|h| ~ 1 ulp) the mask, hence the gradient, is decided by rounding noise and no two
+    # implementations agree (seed 123 has one h2 = 7.5e-9)
+    lin = [m for m in net.decoder.modules() if isinstance(m, torch.nn.Linear)]
+    b = np.asarray(BOUND)
+    for np_seed in range(124, 400):
+        np.random.seed(np_seed)
+        pts = torch.from_numpy(np.stack([np.random.uniform(b[d, 0], b[d, 1], N) for d in range(3)], 1)).float()
+        offs = torch.cat([torch.zeros(1, 3), 0.024 * torch.eye(3), -0.024 * torch.eye(3)], 0)
+        allp = torch.cat([pts + o for o in offs] + [coords], 0)
+        with torch.no_grad():
+            h1 = lin[0](net.query_feature(allp))
+            h2 = lin[1](torch.relu(h1))
+        if min(float(h1.abs().min()), float(h2.abs().min())) > 1e-6:
+            break
+    out["tsdf.np_seed"] = np.asarray(np_seed)
+    np.random.seed(np_seed)
     L = rloss.TsdfLoss3D(grad_method="finitediff", finite_diff_eps=0.024)
     ld = L.compute(net, {"coords": coords[None]}, {"sdf": gt_sdf[None], "sdf_valid": valid[None], "sdf_sign": sign[None]})
     sum(ld.values()).backward()

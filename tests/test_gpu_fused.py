@@ -277,3 +277,72 @@ def test_inference_forward_and_atlas_query():
         sw = sw + m
     sw = torch.where(sw == 0, torch.ones_like(sw), sw).float()
     assert rel_err(got, sf / sw) < TOL_F
+
+
+def test_compact_host_batches_match_reference_format():
+    """CompactBatch (int16 ids, masks rebuilt by miso_expand_batch) through train_host_batches gives the same losses
+    and the same parameters as the reference-format batches -- bit-exact masks/ids, so only atomics order differs --
+    and refuses batches whose masks are not the dataset's functions of the sdf."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import CompactBatch, GridTrainer, expand_compact_on_device
+
+    mi, gt, (R, t) = synth.rgbd_batch(3000, num_kf=4, bound=SMALL_BOUND, seed=9, wall_margin=0.3)
+    cb = CompactBatch.from_reference(mi, gt, 0.15, pin=False)
+    dev = {k: v.cuda() for k, v in cb.tensors().items()}
+    mi_d, gt_d = expand_compact_on_device(dev, 0.15, {})
+    assert torch.equal(mi_d["sample_frame_ids"].cpu(), mi["sample_frame_ids"])           # bit-exact
+    assert torch.equal(gt_d["sdf_valid"].cpu(), gt["sdf_valid"])
+    assert torch.equal(gt_d["sdf_signs"].cpu(), gt["sdf_signs"])
+    assert torch.equal(mi_d["weights"].cpu(), mi["weights"])
+    bad = {k: v.clone() for k, v in gt.items()}
+    bad["sdf_valid"][0, 0, 0] = ~bad["sdf_valid"][0, 0, 0]
+    with pytest.raises(ValueError):
+        CompactBatch.from_reference(mi, bad, 0.15, pin=False)
+
+    losses, params = [], []
+    for fmt in ("reference", "compact"):
+        net, _, _ = make_pair(num_poses=4)
+        for k in range(4):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        net.lock_pose()
+        loss = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                               grad_method="autograd", eik_trunc_dist=None)
+        tr = GridTrainer({"epochs": 3, "learning_rate": 1e-3, "grid_training_mode": "joint"}, net, loss, lambda e: (mi, gt),
+                         device="cuda")
+        tr.pre_epoch(0)
+        sink = torch.zeros(3, 4).pin_memory()
+        batch = (mi, gt) if fmt == "reference" else cb
+        tr.train_host_batches([batch] * 3, loss_sink=sink)
+        torch.cuda.synchronize()
+        losses.append(sink.clone())
+        params.append([f.detach().clone() for f in net.level_tensors()])
+    assert rel_err(losses[1], losses[0]) < 1e-5
+    for a, b in zip(params[1], params[0]):
+        assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("n_levels,fdim,scale", [(1, 8, 5), (2, 8, 3), (4, 4, 2), (1, 16, 5), (3, 4, 2), (1, 4, 5)])
+def test_mapping_step_other_level_channel_shapes(n_levels, fdim, scale):
+    """The fused step on every (levels, channels) instantiation: even numbers of 4-channel groups run the
+    two-threads-per-point kernel (halves split by level, or by channel group inside one level), odd ones the
+    one-thread kernel.  L1 + free space + second-order eikonal against the oracle."""
+    from miso_b200.loss import MisoLossMapping
+    net, _, o2 = make_pair(n_levels=n_levels, fdim=fdim, scale=scale, base_cell=0.5)
+    mi, gt, (R, t) = _batch(5000)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    assert net.fused_spec() is not None
+    L = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=0.1)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    sum(v.mean() for v in ld.values()).backward()
+    lo = O.mapping_loss(o2, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, "L1", 1.0, 0.5, 0.1, 0.15,
+                        grad_method="autograd", eik_trunc_dist=0.1)
+    sum(lo.values()).backward()
+    for k in lo:
+        assert rel_err(ld[k], lo[k]) < TOL_G, k
+    for l in range(n_levels):
+        assert rel_err(net.features[l].feature.grad, o2.features[l].grad) < TOL_G, l

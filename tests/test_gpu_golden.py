@@ -185,7 +185,7 @@ def test_loss_variants_and_dense_queries_against_reference_outputs():
     net.unlock_feature()
     coords, gts = T(z["tsdf.in_coords"]).cuda(), T(z["tsdf.in_sdf"]).cuda()
     valid, sign = T(z["tsdf.in_valid"]).cuda(), T(z["tsdf.in_sign"]).cuda()
-    np.random.seed(123)
+    np.random.seed(int(z["tsdf.np_seed"]))
     L = TsdfLoss3D(grad_method="finitediff", finite_diff_eps=0.024)
     ld = L.compute(net, {"coords": coords[None]}, {"sdf": gts[None], "sdf_valid": valid[None], "sdf_sign": sign[None]})
     sum(ld.values()).backward()
