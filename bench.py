@@ -382,14 +382,27 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
     atlas = build_align_atlas(device)
     atlas.precompute_coordinates_for_alignment()
     pairs = [(s, d) for s in range(ALIGN_SUBMAPS) for d in range(s + 1, ALIGN_SUBMAPS)]
-    mine = [p for i, p in enumerate(pairs) if i % world == rank]
     out = {}
     for level in (0, 1):
+        if world > 1:
+            # cost-balanced ownership: samples of the pair if the submaps intersect at the initial poses, else 0
+            # (same deterministic assignment on every rank)
+            probe = AlignBatch(atlas, pairs, level, check_intersection=True, cache_src_features=False)
+            probe.update_intersections(probe.pair_poses())
+            en = probe.enabled[:len(pairs)].tolist()
+            costs = [probe._coords[s].shape[0] * (1 if e else 0) for (s, d), e in zip(pairs, en)]
+            owner = mdist.balanced_pair_owner(costs, world)
+            mine = [p for p, o in zip(pairs, owner) if o == rank]
+            del probe
+        else:
+            mine = pairs
         batch = AlignBatch(atlas, mine, level, check_intersection=True)
         params = []
         for i in range(1, ALIGN_SUBMAPS):
             params += list(atlas.params_for_submap_pose(i))
-        use_graph = world == 1      # the pair-sharded run keeps the NCCL all_reduce outside a graph
+        # one whole iteration as a CUDA graph; with world > 1 the NCCL all_reduce of the pose gradients is captured
+        # inside it (MISO_ALIGN_GRAPH_NCCL=0 keeps it eager)
+        use_graph = world == 1 or os.environ.get("MISO_ALIGN_GRAPH_NCCL", "1") != "0"
         opt = optim.Adam([{"params": params, "lr": 1e-2}], lr=1e-2, capturable=use_graph)
 
         def one_iter():
@@ -414,7 +427,7 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
         if use_graph:
             # one whole iteration (poses, intersections, alignment kernel, backward, Adam) as a CUDA graph
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = one_iter().detach()
             graph.replay()
             torch.cuda.synchronize()

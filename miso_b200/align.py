@@ -365,7 +365,8 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
     losses_hist = []
     it = 0
     graph, static_loss = None, None
-    can_graph = use_cuda_graph and not save_iterations and rel_change_thresh <= 0 and allreduce is None
+    # an NCCL all_reduce is capturable: with `allreduce` given the collective becomes a node of the graph
+    can_graph = use_cuda_graph and not save_iterations and rel_change_thresh <= 0
 
     def one_iteration():
         optimizer.zero_grad(set_to_none=False) if graph_params_ready[0] else optimizer.zero_grad()
@@ -378,6 +379,8 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
                                                     weight=pose_reg_weight)
             total = total + sum(reg.values())
         total.backward()
+        if allreduce is not None:
+            allreduce([p.grad for p in pose_params() if p.grad is not None])
         optimizer.step()
         return total.detach()
 
@@ -393,7 +396,7 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
         graph_params_ready[0] = True
         if it <= num_iters:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = one_iteration()
             # the capture itself does not execute: every replay is one iteration
             while it <= num_iters:

@@ -7,7 +7,7 @@ torchrun, `torch.distributed` (NCCL over NVLink/NVSwitch on the box, gloo in the
   * large single-grid fit: points sharded per rank, loss = mean over ALL points (loss.py:634) -> every rank
     scales by N_local/N_total and the dense grid gradients are summed with one all_reduce per level
     before Adam (every rank then applies the identical update).
-  * alignment: total_loss = sum over pairs (base.py:146) -> pairs round-robin over ranks, one all_reduce of
+  * alignment: total_loss = sum over pairs (base.py:146) -> pairs round-robin (or cost-balanced) over ranks, one all_reduce of
     the per-submap pose gradients (<= 16 x 6 floats) per iteration.
 """
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -52,6 +52,30 @@ def pair_filter(rank: Optional[int] = None, world_size: Optional[int] = None) ->
     rank = r if rank is None else rank
     world_size = w if world_size is None else world_size
     return lambda i, pair: i % world_size == rank
+
+
+def balanced_pair_owner(costs: Sequence[float], world_size: Optional[int] = None) -> List[int]:
+    """Cost-balanced pair ownership ("or cost-balanced by M_valid"): longest-processing-time
+    greedy -- pairs sorted by decreasing cost (e.g. alignment samples of the pair, 0 when the submaps do not
+    intersect) go to the currently lightest rank.  Deterministic (ties by pair index), identical on every rank.
+    Returns owner[i] for every pair."""
+    _, w = world()
+    world_size = w if world_size is None else world_size
+    load = [0.0] * world_size
+    owner = [0] * len(costs)
+    for i in sorted(range(len(costs)), key=lambda k: (-float(costs[k]), k)):
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += float(costs[i])
+    return owner
+
+
+def balanced_pair_filter(costs: Sequence[float], rank: Optional[int] = None,
+                         world_size: Optional[int] = None) -> Callable[[int, Tuple[int, int]], bool]:
+    r, _ = world()
+    rank = r if rank is None else rank
+    owner = balanced_pair_owner(costs, world_size)
+    return lambda i, pair: owner[i] == rank
 
 
 def allreduce_sum_(tensors: Sequence[torch.Tensor]) -> None:

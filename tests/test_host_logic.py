@@ -140,3 +140,18 @@ def test_partition_helpers():
     owned = [[p for i, p in enumerate(pairs) if mdist.pair_filter(r, 8)(i, p)] for r in range(8)]
     assert sorted(sum(owned, [])) == pairs and len(pairs) == 120
     assert mdist.sharded_loss_scale(250, 1000) == 0.25
+
+
+def test_balanced_pair_owner_is_deterministic_and_balanced():
+    """Cost-balanced alignment-pair ownership: disjoint cover, deterministic, max load <= LPT bound."""
+    from miso_b200 import dist as mdist
+    rng = np.random.RandomState(0)
+    costs = [float(c) for c in rng.randint(0, 4_000_000, size=120) * (rng.rand(120) < 0.35)]
+    for w in (1, 2, 4, 8):
+        owner = mdist.balanced_pair_owner(costs, w)
+        assert owner == mdist.balanced_pair_owner(costs, w)
+        assert set(owner) <= set(range(w)) and len(owner) == 120
+        loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(w)]
+        assert max(loads) <= sum(costs) / w + max(costs) + 1e-6          # LPT guarantee
+        mine = [[i for i in range(120) if mdist.balanced_pair_filter(costs, r, w)(i, None)] for r in range(w)]
+        assert sorted(sum(mine, [])) == list(range(120))
