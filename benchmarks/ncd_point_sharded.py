@@ -69,12 +69,16 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        from miso_b200 import loss as mloss
+        mloss.PROFILE_EVENTS = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_steps):
             terms = step()
         e1.record()
         torch.cuda.synchronize()
+        run.kernel_ms = sum(a.elapsed_time(b_) for a, b_ in mloss.PROFILE_EVENTS) / max(len(mloss.PROFILE_EVENTS), 1)
+        mloss.PROFILE_EVENTS = None
         ms = e0.elapsed_time(e1) / n_steps
         if world > 1:
             tms = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -86,7 +90,10 @@ def main():
     out = {"workload": "NCD quad grid, 2^22 LiDAR points/step, point-sharded + all_reduce of grid gradients",
            "n_gpus": world, "ms_per_step": ms_s, "points_per_s": N_TOTAL / (ms_s * 1e-3),
            "loss_terms": [float(v) for v in terms_s.tolist()],
-           "allreduce_bytes_per_step": sum(p.numel() * 4 for p in net_s.level_tensors())}
+           "allreduce_bytes_per_step": sum(p.numel() * 4 for p in net_s.level_tensors()),
+           "mapping_kernel_ms_per_rank": run.kernel_ms,
+           # no eikonal term in this config (ncd_quad.yaml:42-46): same 545 B/point model as bench.py
+           "kernel_roofline_frac": 545 * (e - b) / (run.kernel_ms * 1e-3) / 1e9 / 6535.7}
     if world > 1:
         # parity of the sharded run against the same 13 steps on one GPU (rank 0 recomputes unsharded)
         params_s = [p.detach().clone() for p in net_s.level_tensors()]
