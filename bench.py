@@ -378,7 +378,7 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
     Adam step on the 15 free submap poses (generic_align_multiple_submaps body, align/base.py:127-159)."""
     import torch.optim as optim
     from miso_b200 import dist as mdist
-    from miso_b200.align import AlignBatch
+    from miso_b200.align import AlignBatch, FusedPoseAligner
     atlas = build_align_atlas(device)
     atlas.precompute_coordinates_for_alignment()
     pairs = [(s, d) for s in range(ALIGN_SUBMAPS) for d in range(s + 1, ALIGN_SUBMAPS)]
@@ -390,45 +390,34 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
             probe = AlignBatch(atlas, pairs, level, check_intersection=True, cache_src_features=False)
             probe.update_intersections(probe.pair_poses())
             en = probe.enabled[:len(pairs)].tolist()
-            costs = [probe._coords[s].shape[0] * (1 if e else 0) for (s, d), e in zip(pairs, en)]
+            # + the pair's share of the per-iteration intersection test (one transform + bound test per finest-level
+            # vertex of the source, ~5 % of the cost of an alignment sample)
+            costs = [probe._coords[s].shape[0] * (1 if e else 0) + 0.05 * probe._verts[s].shape[0]
+                     for (s, d), e in zip(pairs, en)]
             owner = mdist.balanced_pair_owner(costs, world)
             mine = [p for p, o in zip(pairs, owner) if o == rank]
             del probe
         else:
             mine = pairs
         batch = AlignBatch(atlas, mine, level, check_intersection=True)
-        params = []
-        for i in range(1, ALIGN_SUBMAPS):
-            params += list(atlas.params_for_submap_pose(i))
-        # one whole iteration as a CUDA graph; with world > 1 the NCCL all_reduce of the pose gradients is captured
-        # inside it (MISO_ALIGN_GRAPH_NCCL=0 keeps it eager)
+        # whole iteration = compose poses, intersection test, alignment kernel, pose gradients, Adam: five launches
+        # (csrc/poseopt.cu), captured as one CUDA graph; with world > 1 the NCCL all_reduce of the (S,6) pose gradients
+        # is a node of the same graph (MISO_ALIGN_GRAPH_NCCL=0 keeps the multi-GPU iteration eager)
         use_graph = world == 1 or os.environ.get("MISO_ALIGN_GRAPH_NCCL", "1") != "0"
-        opt = optim.Adam([{"params": params, "lr": 1e-2}], lr=1e-2, capturable=use_graph)
-
-        def one_iter():
-            opt.zero_grad(set_to_none=False)
-            poses = batch.pair_poses()
-            batch.update_intersections(poses)
-            loss = torch.nan_to_num(batch.losses(3000.0, poses)).sum()
-            loss.backward()
-            if world > 1:
-                mdist.allreduce_sum_([p.grad for p in params])
-            opt.step()
-            return loss
-
+        aligner = FusedPoseAligner(batch, lr=1e-2, align_weight=3000.0, max_iters=4 * (iters + warmup) + 64,
+                                   allreduce=mdist.allreduce_sum_ if world > 1 else None)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 3)):
-                one_iter()
+                aligner.iteration()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = None
         if use_graph:
-            # one whole iteration (poses, intersections, alignment kernel, backward, Adam) as a CUDA graph
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                static_loss = one_iter().detach()
+                aligner.iteration()
             graph.replay()
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -436,17 +425,19 @@ def bench_align(device, iters=10, warmup=2, world=1, rank=0):
         for _ in range(iters):
             if graph is not None:
                 graph.replay()
-                last = static_loss
             else:
-                last = one_iter()
+                aligner.iteration()
         e1.record()
         torch.cuda.synchronize()
+        last = aligner.loss_hist[int(aligner.iter_counter.item()) - 1].clone()
+        if world > 1:
+            mdist.allreduce_sum_([last])
         ms = e0.elapsed_time(e1) / iters
         n_on = int(batch.enabled[:len(mine)].sum().item()) if mine else 0
         samples = sum(batch._coords[s].shape[0] for (s, d), en in zip(mine, batch.enabled.tolist()) if en)
         bytes_pp = 12 + (level + 1) * 16 + (level + 1) * 8 * 16      # coords + cached src feats + dst corners
         out[f"level{level}"] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "pairs": len(mine), "pairs_overlapping": n_on,
-                                "samples_per_iter": samples, "loss": float(last), "cuda_graph": graph is not None,
+                                "samples_per_iter": samples, "loss": float(last), "cuda_graph": graph is not None, "launches_per_iter": 5,
                                 "hbm_gbs_algorithmic": samples * bytes_pp / (ms * 1e-3) / 1e9}
     return out
 

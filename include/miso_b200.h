@@ -211,6 +211,26 @@ int miso_align_intersections(const miso_field_t* fields, int32_t num_fields, con
                              const float* poses, float overlap_thresh, int32_t* enabled_out,
                              unsigned long long* counts_out, miso_stream_t stream);
 
+/* Pose glue of one alignment iteration (grid_opt/align/base.py:127-159 around the loss) as three single-block
+ * kernels: (1) R = R0 Exp(w), t = t0 + tau for every submap (grid_atlas.py:250-268; Exp = pytorch3d so3_exp_map
+ * with its 1e-4 clamp) and the per-pair (A1,b1,A2,b2) rows; (2) from miso_align_batch's reductions to
+ * loss_i = mean(r^2)*weight (nan_to_num), total -> loss_hist[*iter_counter], and d total/d(w_s, tau_s) -> grads
+ * (S,6) through the transforms and the closed-form derivative of Exp; (3) torch.optim.Adam on (w_s, tau_s),
+ * s >= 1 (submap 0 fixed, base.py:104-108), state in exp_avg / exp_avg_sq (S,6), step = ++*iter_counter.
+ * w_ptrs / tau_ptrs are DEVICE arrays of S device pointers to the (1,3) / (3,1) correction tensors, which are
+ * updated in place.  A multi-GPU run all-reduces `grads` between (2) and (3).  Rt (S,12) = [R row-major, t]. */
+int miso_align_compose_poses(const float* R0, const float* t0, float* const* w_ptrs, float* const* tau_ptrs,
+                             int32_t num_submaps, const int32_t* src, const int32_t* dst, int32_t num_pairs,
+                             float* poses24, float* Rt_out, miso_stream_t stream);
+int miso_align_pose_grads(const float* R0, const float* t0, float* const* w_ptrs, float* const* tau_ptrs,
+                          int32_t num_submaps, const int32_t* src, const int32_t* dst, int32_t num_pairs,
+                          const double* align_out, const float* poses24, const float* Rt, int32_t channels_used,
+                          float align_weight, float* grads, float* loss_hist, int32_t* iter_counter,
+                          float* pair_loss, miso_stream_t stream);
+int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t num_submaps, const float* grads,
+                         float* exp_avg, float* exp_avg_sq, int32_t* iter_counter, float lr, float beta1,
+                         float beta2, float eps, miso_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Helpers around the path.
  * ------------------------------------------------------------------------------------------ */

@@ -210,6 +210,110 @@ class _AlignBatchFn(torch.autograd.Function):
         return grad.to(poses24.dtype), None, None
 
 
+class FusedPoseAligner:
+    """One alignment iteration (base.py:127-159, latent L2 loss) as FIVE launches: compose poses, intersection
+    test, alignment kernel, pose gradients, Adam -- no torch ops, no autograd graph (csrc/poseopt.cu).  The torch
+    path (`AlignBatch.losses` + autograd + torch.optim.Adam) needs ~100 small launches for the same iteration,
+    which bounds level-0 alignment (32 k samples per pair) at ~1 ms per iteration even inside a CUDA graph.
+
+    The submap pose corrections (GridAtlas.rotation_corrections / translation_corrections) are updated in place
+    through a device table of their addresses; submap 0 stays fixed; Adam state lives here.  `allreduce` (multi-GPU,
+    pair-sharded) sums the (S,6) gradient buffer over ranks between the gradient and the Adam kernel."""
+
+    def __init__(self, batch: AlignBatch, lr: float = 1e-2, align_weight: float = 3000.0, betas=(0.9, 0.999),
+                 eps: float = 1e-8, max_iters: int = 4096, allreduce=None):
+        a = batch.atlas
+        dev = batch.device
+        self.batch, self.lr, self.align_weight, self.betas, self.eps = batch, float(lr), float(align_weight), betas, float(eps)
+        self.allreduce = allreduce
+        S = a.num_submaps
+        self.S, self.P = S, len(batch.pairs)
+        self.R0 = torch.stack([r.detach().float() for r in a.R_world_submap_list], 0).reshape(S, 9).contiguous().to(dev)
+        self.t0 = torch.stack([t.detach().float() for t in a.t_world_submap_list], 0).reshape(S, 3).contiguous().to(dev)
+        for q in list(a.rotation_corrections) + list(a.translation_corrections):
+            if not (q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()):
+                raise RuntimeError("pose corrections must be contiguous float32 CUDA tensors")
+        self.w_ptrs = torch.tensor([q.data_ptr() for q in a.rotation_corrections], dtype=torch.int64, device=dev)
+        self.tau_ptrs = torch.tensor([q.data_ptr() for q in a.translation_corrections], dtype=torch.int64, device=dev)
+        self.src = batch.src_idx.to(torch.int32).contiguous()
+        self.dst = batch.dst_idx.to(torch.int32).contiguous()
+        self.poses24 = torch.zeros((max(self.P, 1), 24), dtype=torch.float32, device=dev)
+        self.Rt = torch.zeros((S, 12), dtype=torch.float32, device=dev)
+        self.out = torch.zeros((max(self.P, 1), _lib.MISO_ALIGN_OUT), dtype=torch.float64, device=dev)
+        self.grads = torch.zeros((S, 6), dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros((S, 6), dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros((S, 6), dtype=torch.float32, device=dev)
+        self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_hist = torch.zeros(max_iters, dtype=torch.float32, device=dev)
+        self.pair_loss = torch.zeros(max(self.P, 1), dtype=torch.float32, device=dev)
+        self.max_iters = max_iters
+
+    def compose(self):
+        lib, b = _lib.load(), self.batch
+        with torch.cuda.device(b.device):
+            _lib.check(lib.miso_align_compose_poses(
+                self.R0.data_ptr(), self.t0.data_ptr(), self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S,
+                self.src.data_ptr(), self.dst.data_ptr(), self.P, self.poses24.data_ptr(), self.Rt.data_ptr(),
+                _lib.stream_ptr(b.device)), "align_compose_poses")
+        return self.poses24
+
+    def iteration(self):
+        """Everything is enqueued on the current stream; nothing is synchronised (CUDA-graph capturable)."""
+        lib, b = _lib.load(), self.batch
+        stream = _lib.stream_ptr(b.device)
+        self.compose()
+        if b.check_intersection:
+            b.update_intersections(self.poses24)
+        with torch.cuda.device(b.device):
+            if self.P:
+                _lib.check(lib.miso_align_batch(b.fields_dev.data_ptr(), b.num_fields, b.pairs_dev.data_ptr(), self.P,
+                                                b.max_M, self.poses24.data_ptr(), self.out.data_ptr(), 0, stream),
+                           "align_batch")
+            _lib.check(lib.miso_align_pose_grads(
+                self.R0.data_ptr(), self.t0.data_ptr(), self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S,
+                self.src.data_ptr(), self.dst.data_ptr(), self.P, self.out.data_ptr(), self.poses24.data_ptr(),
+                self.Rt.data_ptr(), b.K, self.align_weight, self.grads.data_ptr(), self.loss_hist.data_ptr(),
+                self.iter_counter.data_ptr(), self.pair_loss.data_ptr(), stream), "align_pose_grads")
+            if self.allreduce is not None:
+                self.allreduce([self.grads])
+            _lib.check(lib.miso_align_pose_adam(
+                self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S, self.grads.data_ptr(),
+                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.iter_counter.data_ptr(), self.lr,
+                float(self.betas[0]), float(self.betas[1]), self.eps, stream), "align_pose_adam")
+
+    def run(self, num_iters: int, use_cuda_graph: bool = True):
+        """`num_iters` iterations; returns the per-iteration total losses (device tensor).  With a CUDA graph the
+        first iteration runs eagerly (module loading, NCCL warm-up), the rest are replays of one captured iteration."""
+        if int(self.iter_counter.item()) + num_iters > self.max_iters:
+            raise RuntimeError("FusedPoseAligner: loss history too short for this many iterations")
+        start = int(self.iter_counter.item())
+        done = 0
+        if use_cuda_graph and num_iters > 2:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.iteration()
+            torch.cuda.current_stream().wait_stream(side)
+            done = 1
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self.iteration()
+            while done < num_iters:
+                graph.replay()
+                done += 1
+        while done < num_iters:
+            self.iteration()
+            done += 1
+        with torch.no_grad():   # the kernels wrote through raw pointers: bump the tensors' version counters
+            for q in list(self.batch.atlas.rotation_corrections) + list(self.batch.atlas.translation_corrections):
+                q.add_(0.0)
+        if self.allreduce is not None:
+            total = self.loss_hist[start:start + num_iters].clone()
+            self.allreduce([total])
+            return total
+        return self.loss_hist[start:start + num_iters]
+
+
 # ------------------------------------------------------------------------------------------------
 # reference-named entry points
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +434,8 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
                                    lr=1e-2, rel_change_thresh=0, submap_pairs=None, check_intersection=True,
                                    pose_reg_weight=0, pose_thresh_rad=1.0, pose_thresh_m=1.0, verbose=True,
                                    save_iterations=False, *, level: int = 0, align_weight=3000.0,
-                                   subsample_points=None, pair_filter=None, allreduce=None, use_cuda_graph=False):
+                                   subsample_points=None, pair_filter=None, allreduce=None, use_cuda_graph=False,
+                                   fused_pose_glue=True):
     """base.py:89-163 with the pair loop replaced by one batched launch per iteration.
 
     `pairwise_loss_tuple` is accepted for signature compatibility; the loss is the latent L2 loss at
@@ -339,7 +444,10 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
     Runs `num_iters + 1` iterations like the reference (`while iter <= num_iters`, base.py:127).
     `use_cuda_graph=True` captures one whole iteration (pose composition, intersection test, alignment
     kernel, backward, Adam) into a CUDA graph after 3 eager warm-up iterations and replays it: level 0 has
-    only ~32 k samples per pair, so the iteration is launch-bound without it."""
+    only ~32 k samples per pair, so the iteration is launch-bound without it.
+    `fused_pose_glue=True` (default; needs pose_reg_weight == 0, no relative-change stop, no saved iterations) runs the
+    pose composition, its backward and the Adam step as three single-block kernels (FusedPoseAligner) instead of
+    torch ops; `False` keeps the reference's own torch glue (so3_exp_map autograd + torch.optim.Adam)."""
     def pose_params():
         params = []
         for submap_id in range(1, grid_atlas.num_submaps):  # submap 0 stays fixed (base.py:104-108)
@@ -351,7 +459,6 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
                                              rel_change_thresh, submap_pairs, check_intersection, pose_reg_weight,
                                              pose_thresh_rad, pose_thresh_m, save_iterations, pair_filter, allreduce)
 
-    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr, capturable=bool(use_cuda_graph))
     if submap_pairs is None:
         submap_pairs = [(s, d) for s in range(grid_atlas.num_submaps) for d in range(s + 1, grid_atlas.num_submaps)]
     my_pairs = list(submap_pairs) if pair_filter is None else [p for i, p in enumerate(submap_pairs) if pair_filter(i, p)]
@@ -360,6 +467,15 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    if fused_pose_glue and pose_reg_weight == 0 and rel_change_thresh <= 0 and not save_iterations:
+        # whole iteration as five launches (csrc/poseopt.cu): no autograd graph, Adam state held by the aligner
+        aligner = FusedPoseAligner(batch, lr=lr, align_weight=align_weight, max_iters=num_iters + 1, allreduce=allreduce)
+        losses = aligner.run(num_iters + 1, use_cuda_graph=use_cuda_graph)
+        ev1.record()
+        torch.cuda.synchronize()
+        return {"cpu_time_sec": time.perf_counter() - t0, "gpu_time_sec": ev0.elapsed_time(ev1) / 1e3,
+                "iteration_results": dict(), "losses": losses.cpu(), "iterations": num_iters + 1}
+    optimizer = optim.Adam([{"params": pose_params(), "lr": lr}], lr=lr, capturable=bool(use_cuda_graph))
     iteration_results = dict()
     params_prev = None
     losses_hist = []

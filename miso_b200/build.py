@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libmiso_b200.so")
 STAMP_PATH = os.path.join(HERE, "libmiso_b200.stamp")
-SOURCES = ["misc.cu", "interp.cu", "fused.cu", "align.cu", "tc_test.cu"]
+SOURCES = ["misc.cu", "interp.cu", "fused.cu", "align.cu", "poseopt.cu", "tc_test.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DNDEBUG",
