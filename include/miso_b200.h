@@ -202,7 +202,8 @@ int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_
                      miso_stream_t stream);
 
 /* check_submap_intersection (grid_atlas.py:405-420) for all pairs in one launch.  Here pairs[i].p / M are
- * the SOURCE submap's finest-level vertex positions, pairs[i].reserved is the pair's output slot (also its
+ * the SOURCE submap's finest-level vertex positions, pairs[i].levels_used describes the lattice: X | (Y << 16) when p is
+ * FeatureGrid.vertex_positions() of an (Z,Y,X) grid (x fastest; a per-axis outer product), 0 = unstructured point list, pairs[i].reserved is the pair's output slot (also its
  * row in `poses`), and the array is sorted so pairs that share a source are contiguous; groups (num_groups x 2
  * int32: first pair, count <= 32) lets a block read each vertex once and test it against every destination
  * paired with that source.  enabled_out[slot] = (count / M > overlap_thresh); counts_out (num_pairs) uint64. */

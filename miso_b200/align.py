@@ -42,7 +42,7 @@ class AlignBatch:
 
     def __init__(self, grid_atlas: GridAtlas, pairs: Sequence[Tuple[int, int]], level: int, fdim: int = 4,
                  subsample_points: Optional[int] = None, cache_src_features: bool = True, want_masks: bool = False,
-                 check_intersection: bool = True):
+                 check_intersection: bool = True, lattice_rows: bool = True):
         self.atlas = grid_atlas
         self.pairs = list(pairs)
         self.level = level
@@ -106,7 +106,14 @@ class AlignBatch:
                 v = self._verts[src]
                 self.max_V = max(self.max_V, v.shape[0])
                 ip = _lib.AlignPair()
-                ip.src, ip.dst, ip.levels_used, ip.reserved = src, dst, 0, i
+                # vertex_positions() lists the finest lattice row by row (x fastest, grid_modules.py:111-123): tell the
+                # kernel the row length so it can decide whole row segments from their end points (exact count)
+                shp = grid_atlas.get_submap(src).features[-1].feature.shape          # (1,C,Z,Y,X)
+                X_, Y_, Z_ = int(shp[-1]), int(shp[-2]), int(shp[-3])
+                lattice = X_ | (Y_ << 16)
+                if v.shape[0] != X_ * Y_ * Z_ or X_ >= 65536 or Y_ >= 32768 or not lattice_rows:
+                    lattice = 0
+                ip.src, ip.dst, ip.levels_used, ip.reserved = src, dst, lattice, i
                 ip.p, ip.M = v.data_ptr(), v.shape[0]
                 isect_structs.append(ip)
         self.check_intersection = check_intersection

@@ -284,6 +284,11 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ float s_pose[kMaxGroup][24];
   __shared__ float s_bound[kMaxGroup][6];
   __shared__ int s_slot[kMaxGroup];
+  __shared__ float s_eps[kMaxGroup][3];   // lattice path: decision margin per destination and axis
+  for (int i = threadIdx.x; i < np * 3; i += blockDim.x) {
+    const float* b = fields[pairs[first + i / 3].dst].bound + 2 * (i % 3);
+    s_eps[i / 3][i % 3] = 1e-3f + 1e-5f * fmaxf(fabsf(b[0]), fabsf(b[1]));
+  }
   for (int i = threadIdx.x; i < np * 24; i += blockDim.x) {
     const int j = i / 24;
     s_pose[j][i % 24] = poses[(int64_t)pairs[first + j].reserved * 24 + i % 24];
@@ -291,7 +296,6 @@ __global__ void __launch_bounds__(kThreads)
   for (int i = threadIdx.x; i < np * 6; i += blockDim.x) s_bound[i / 6][i % 6] = fields[pairs[first + i / 6].dst].bound[i % 6];
   for (int i = threadIdx.x; i < np; i += blockDim.x) s_slot[i] = pairs[first + i].reserved;
   __syncthreads();
-  // lane j of every warp accumulates the count of pair j (ballot + popc), so no per-thread count array
   const int lane = threadIdx.x & 31;
   unsigned my_cnt = 0;
   float A1[9], b1[3];
@@ -300,22 +304,127 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int i = 0; i < 3; ++i) b1[i] = s_pose[0][9 + i];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_iter = (pr0.M + stride - 1) / stride;
+  // levels_used > 0: p is a lattice listed row by row -- X = low 16 bits vertices per row (collinear, equispaced),
+  // Y = high 16 bits rows per z-plane; vertex (iz,iy,ix) = (p[3 ix], p[3 iy X + 1], p[3 iz X Y + 2]) exactly, because
+  // vertex_positions() is a per-axis outer product (grid_modules.py:111-123, utils.py:294-307)
+  const int row_len = pr0.levels_used & 0xffff;
+  const int rows_per_plane = pr0.levels_used >> 16;
+  if (row_len > 0) {
+    // Lattice path.  A thread takes a segment of kS consecutive vertices of one row.  The map vertex -> q is affine
+    // along the row (up to fp32 rounding) and the destination bound is convex, so
+    //   * both end points inside the bound shrunk by a margin  => every vertex of the segment is inside,
+    //   * both end points outside the SAME face grown by the margin => every vertex is outside,
+    //   * otherwise the interior vertices are tested one by one, with the very same arithmetic as the plain path.
+    // The margin (1e-3 + 1e-5 |bound|) is two orders above the rounding error of the two chained transforms, so the
+    // count is the exact per-vertex count; ~85 % of the segments of two overlapping room-sized submaps are decided
+    // by their end points alone.
+    constexpr int kS = 8;
+    const int segs_per_row = (row_len + kS - 1) / kS;
+    const int64_t rows = pr0.M / row_len;
+    const int64_t nseg = rows * segs_per_row;
+    // whole warps stay in the loop together (the reduction below is warp-wide): iterate on the warp's first segment
+    for (int64_t sg0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); sg0 < nseg; sg0 += stride) {
+      const int64_t sg = sg0 + lane;
+      const bool live = sg < nseg;
+      const int64_t row = live ? sg / segs_per_row : 0;
+      const int x0 = live ? (int)(sg - row * segs_per_row) * kS : 0;
+      const int len = live ? min(kS, row_len - x0) : 0;
+      // coordinates from the three per-axis tables inside p (a few KB, cache-resident) instead of streaming the
+      // 12 B/vertex list: the kernel no longer touches HBM at all
+      const int64_t iz = row / rows_per_plane, iy = row - iz * rows_per_plane;
+      const float py = __ldg(pr0.p + 3 * (iy * row_len) + 1);
+      const float pz = __ldg(pr0.p + 3 * (iz * row_len * rows_per_plane) + 2);
+      float u[kS][3];
+#pragma unroll
+      for (int v = 0; v < kS; ++v) {
+        float p[3] = {0.f, py, pz};
+        if (v < len) p[0] = __ldg(pr0.p + 3 * (x0 + v));
+        xform(A1, b1, p, u[v]);
+      }
+      // last live vertex of the segment (len is almost always kS; the selects keep the code branch-free)
+      float ul[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ul[i] = u[0][i];
+#pragma unroll
+        for (int v = 1; v < kS; ++v) ul[i] = (v == len - 1) ? u[v][i] : ul[i];
+      }
+      for (int j = 0; j < np; ++j) {
+        float A2[9], b2[3], bd[6];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A2[i] = s_pose[j][12 + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) b2[i] = s_pose[j][21 + i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) bd[i] = s_bound[j][i];
+        unsigned hits = 0;
+        float qa[3], qb[3];
+        xform(A2, b2, u[0], qa);
+        xform(A2, b2, ul, qb);
+        bool all_in = true, all_out = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float lo = bd[2 * k], hi = bd[2 * k + 1];
+          const float eps = s_eps[j][k];
+          all_in = all_in && fminf(qa[k], qb[k]) >= lo + eps && fmaxf(qa[k], qb[k]) <= hi - eps;
+          all_out = all_out || fmaxf(qa[k], qb[k]) < lo - eps || fminf(qa[k], qb[k]) > hi + eps;
+        }
+        // decide per WARP (32 adjacent segments = 256 lattice vertices) so the branch never diverges
+        if (__all_sync(0xffffffffu, all_in || len == 0)) {
+          hits = (unsigned)len;
+        } else if (!__all_sync(0xffffffffu, all_out || len == 0)) {
+          if (len > 0) hits = (in_bound(qa, bd) ? 1u : 0u) + ((len > 1 && in_bound(qb, bd)) ? 1u : 0u);
+#pragma unroll
+          for (int v = 1; v < kS - 1; ++v) {
+            float q[3];
+            xform(A2, b2, u[v], q);
+            hits += (v < len - 1 && in_bound(q, bd)) ? 1u : 0u;
+          }
+        }
+        const unsigned tot = __reduce_add_sync(0xffffffffu, hits);
+        if (lane == j) my_cnt += tot;
+      }
+    }
+    if (lane < np && my_cnt) atomicAdd(counts + s_slot[lane], (unsigned long long)my_cnt);
+    return;
+  }
+  // Plain path (arbitrary point lists).  Each thread carries
+
+  // kV vertices through the destination loop so one shared-memory read of a destination's (A2, b2, bound) serves
+  // kV transforms (the loop used to be bound by those reads: 18 floats per vertex and destination), and the kV hit
+  // bits are summed over the warp with ONE redux per destination.
+  constexpr int kV = 4;
+  const int64_t n_iter = (pr0.M + stride * kV - 1) / (stride * kV);
   for (int64_t it = 0; it < n_iter; ++it) {
-    const int64_t n = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = n < pr0.M;
-    float p[3] = {0.f, 0.f, 0.f}, u[3];
-    if (live) p[0] = pr0.p[3 * n], p[1] = pr0.p[3 * n + 1], p[2] = pr0.p[3 * n + 2];
-    xform(A1, b1, p, u);
+    float u[kV][3];
+    unsigned live = 0;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const int64_t n = (it * kV + v) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      float p[3] = {0.f, 0.f, 0.f};
+      if (n < pr0.M) {
+        live |= 1u << v;
+        p[0] = pr0.p[3 * n], p[1] = pr0.p[3 * n + 1], p[2] = pr0.p[3 * n + 2];
+      }
+      xform(A1, b1, p, u[v]);
+    }
     for (int j = 0; j < np; ++j) {
-      float A2[9], b2[3], q[3];
+      float A2[9], b2[3], bd[6];
 #pragma unroll
       for (int i = 0; i < 9; ++i) A2[i] = s_pose[j][12 + i];
 #pragma unroll
       for (int i = 0; i < 3; ++i) b2[i] = s_pose[j][21 + i];
-      xform(A2, b2, u, q);
-      const unsigned hit = __ballot_sync(0xffffffffu, live && in_bound(q, s_bound[j]));
-      if (lane == j) my_cnt += __popc(hit);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) bd[i] = s_bound[j][i];
+      unsigned hits = 0;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        float q[3];
+        xform(A2, b2, u[v], q);
+        hits += (((live >> v) & 1u) && in_bound(q, bd)) ? 1u : 0u;
+      }
+      const unsigned tot = __reduce_add_sync(0xffffffffu, hits);
+      if (lane == j) my_cnt += tot;
     }
   }
   if (lane < np && my_cnt) atomicAdd(counts + s_slot[lane], (unsigned long long)my_cnt);

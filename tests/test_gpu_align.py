@@ -224,3 +224,33 @@ def test_fused_pose_glue_matches_torch_glue(level, graph):
         assert rel_err(atlases[1].translation_corrections[i], atlases[0].translation_corrections[i]) < 1e-4
     assert torch.count_nonzero(atlases[1].rotation_corrections[0]) == 0
     assert torch.count_nonzero(atlases[1].translation_corrections[0]) == 0
+
+
+def test_intersection_counts_lattice_path_equals_per_vertex_path():
+    """The lattice-row path of miso_align_intersections (whole row segments decided by their end points, margin two
+    orders above the rounding error) must give EXACTLY the per-vertex counts, for overlapping, barely touching and
+    disjoint pairs, and agree with torch's count up to vertices that sit on the bound within rounding."""
+    from miso_b200 import geometry as G
+    from miso_b200.align import AlignBatch
+    atlas, _ = build_atlases(4, base_cell=0.5, scale=4, spacing=(5.0, 3.5))
+    atlas.precompute_coordinates_for_alignment()
+    with torch.no_grad():
+        atlas.rotation_corrections[3].copy_(torch.tensor([[0.4, -0.3, 0.2]]))      # a strongly rotated submap
+        atlas.translation_corrections[2].copy_(torch.tensor([[30.0], [0.0], [0.0]]))  # far away: disjoint from the rest
+        atlas.translation_corrections[1].copy_(torch.tensor([[2.9], [0.0], [0.0]]))   # a thin sliver of overlap with 0
+    pairs = [(s, d) for s in range(4) for d in range(4) if s != d]
+    counts = []
+    for lattice in (True, False):
+        b = AlignBatch(atlas, pairs, level=0, check_intersection=True, lattice_rows=lattice)
+        b.update_intersections(b.pair_poses())
+        torch.cuda.synchronize()
+        counts.append(b.counts[:len(pairs)].clone())
+    assert torch.equal(counts[0], counts[1]), (counts[0], counts[1])
+    assert int((counts[0] > 0).sum()) >= 4 and int((counts[0] == 0).sum()) >= 1
+    for i, (s, d) in enumerate(pairs):
+        v = atlas.get_submap(s).features[-1].vertex_positions().cuda()
+        Rs, ts = atlas.updated_submap_pose(s)
+        Rd, td = atlas.updated_submap_pose(d)
+        q = G.transfrom_points_from(G.transform_points_to(v, Rs, ts), Rd, td)
+        ref = int(G.coords_in_bound(q, atlas.get_submap(d).bound.cuda()).sum())
+        assert abs(int(counts[0][i]) - ref) <= max(4, ref // 20000), (s, d, int(counts[0][i]), ref)
