@@ -147,6 +147,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_node = None
+    if world > 1 and os.environ.get("MISO_NUMA_BIND", "1") != "0":
+        from miso_b200 import dist as mdist
+        numa_node = mdist.bind_to_gpu_numa_node(local)   # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
@@ -284,6 +288,7 @@ def run_ours(args):
                         "format": "CompactBatch: coords f32x3 + keyframe id int16 + sdf f32 (+weights when not all "
                                   "ones); sdf_valid / sdf_signs / int64 ids rebuilt on the device by miso_expand_batch "
                                   "(the reference's datasets define them as functions of sdf and trunc_dist)"},
+        "host_numa_node_rank0": numa_node,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,

@@ -16,6 +16,7 @@
 // corner fetches as 128-bit read-only loads from the channels-last grid, scatter as 128-bit
 // red.global.add.v4.f32.  Persistent CTAs (grid = SMs x occupancy) loop over 256-point tiles.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -581,6 +582,9 @@ struct MapArgs {
   const int32_t* eik_count;
   float* partials;
   float* sdf_out;
+  float* jac;      // forward modes of the two-thread kernel: (N,F) Jacobian, (N,3) grad_x sdf, (N,3) world coordinates
+  float* gradx;
+  float* xw;
   float inv_len[3];                       // 1/(bmax-bmin), computed on the host with the device's fp32 ops
   float lvl_scale[MISO_MAX_LEVELS][3];    // (float)dim * inv_len: index-space -> world-space derivative scale
   int dbg;   // MISO_DBG ablation bits (profiling only): 1 = no reductions, 2 = no corner loads, 4 = no g1 TMEM loads
@@ -1333,7 +1337,30 @@ template <int L, int C, int G>
 static int launch_tc2(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t& fr, const MapArgs& m,
                       cudaStream_t s) {
   constexpr size_t smem = sizeof(Tc2Smem<L * C, G>) + 128;
-  auto k = tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true> : mapping_step_tc2_kernel<L, C, G, false>;
+  auto k = tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true, 0> : mapping_step_tc2_kernel<L, C, G, false, 0>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nblocks = grid_for((m.N + G * 128 - 1) / (G * 128), 1, sm_count());
+  k<<<nblocks, G * 256, smem, s>>>(*field, *dec, fr, m);
+  return nblocks;
+}
+
+static void fill_scales(const miso_field_t* field, MapArgs& m) {
+  for (int d = 0; d < 3; ++d) {
+    m.inv_len[d] = 1.0f / (field->bound[2 * d + 1] - field->bound[2 * d]);
+    for (int l = 0; l < field->num_levels; ++l) {
+      const miso_level_t& lv = field->level[l];
+      m.lvl_scale[l][d] = (float)(d == 0 ? lv.X : (d == 1 ? lv.Y : lv.Z)) * m.inv_len[d];
+    }
+  }
+}
+
+// forward modes of the two-thread kernel (miso_sdf_forward): kMode 1 = with Jacobian / grad_x, 2 = values only
+template <int L, int C, int kMode>
+static int launch_tc2_forward(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t& fr,
+                              const MapArgs& m, cudaStream_t s) {
+  constexpr int G = 4;
+  constexpr size_t smem = sizeof(Tc2Smem<L * C, G>) + 128;
+  auto k = mapping_step_tc2_kernel<L, C, G, true, kMode>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nblocks = grid_for((m.N + G * 128 - 1) / (G * 128), 1, sm_count());
   k<<<nblocks, G * 256, smem, s>>>(*field, *dec, fr, m);
@@ -1382,6 +1409,24 @@ extern "C" int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t*
   cudaStream_t s = (cudaStream_t)stream;
   const miso_frames_t fr = frames_or_none(frames);
   const bool want_jac = jac || gradx;
+  const int F_ = field->num_levels * field->level[0].C;
+  // with Jacobian / grad_x outputs the two-threads-per-point kernel is faster (0.17 vs 0.20 ms per 2^20 points);
+  // values only: the one-thread kernel wins on lattice-ordered dense queries (0.73 vs 0.80 ms per 2^23), so mode 2
+  // is only taken when MISO_FWD_TC2=1 asks for it
+  static const bool fwd_tc2 = getenv("MISO_FWD_TC2") && getenv("MISO_FWD_TC2")[0] == '1';
+  if (use_tensor_cores() && N >= 4096 && tc2_groups() != 0 && F_ % 8 == 0 && fits_int32(field) &&
+      N < ((int64_t)1 << 31) - ((int64_t)1 << 26) && (want_jac || fwd_tc2)) {
+    MapArgs m;
+    memset(&m, 0, sizeof(m));
+    m.x = x, m.N = N, m.sdf_out = sdf, m.jac = jac, m.gradx = gradx, m.xw = xw;
+    fill_scales(field, m);
+    int nblocks = 0;
+    MISO_DISPATCH_LC_TC2(field->num_levels, field->level[0].C, {
+      nblocks = want_jac ? launch_tc2_forward<L, C, 1>(field, dec, fr, m, s) : launch_tc2_forward<L, C, 2>(field, dec, fr, m, s);
+    });
+    MISO_REQUIRE(nblocks > 0, "sdf_forward(tc2): unsupported (levels=%d, channels=%d)", field->num_levels, field->level[0].C);
+    return check_launch("sdf_forward(tc2)");
+  }
   if (use_tensor_cores() && N >= 4096) {
     MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
       constexpr size_t smem = sizeof(TcSmem<L * C>) + 128;
@@ -1455,13 +1500,8 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   MapArgs m;
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
-  for (int d = 0; d < 3; ++d) {
-    m.inv_len[d] = 1.0f / (field->bound[2 * d + 1] - field->bound[2 * d]);
-    for (int l = 0; l < field->num_levels; ++l) {
-      const miso_level_t& lv = field->level[l];
-      m.lvl_scale[l][d] = (float)(d == 0 ? lv.X : (d == 1 ? lv.Y : lv.Z)) * m.inv_len[d];
-    }
-  }
+  m.jac = nullptr, m.gradx = nullptr, m.xw = nullptr;
+  fill_scales(field, m);
   {
     static int dbg = -1;
     if (dbg < 0) {

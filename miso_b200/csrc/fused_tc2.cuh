@@ -272,7 +272,9 @@ __device__ __forceinline__ void scatter_group4_paired(const miso_level_t& lv, co
                 h ? J[2] : pJ2, h ? J[3] : pJ3);
 }
 
-template <int L, int C, int G, bool kPaired>
+// kMode: 0 = whole mapping step (losses + scatter), 1 = forward with Jacobian / grad_x outputs (miso_sdf_forward with
+// jac / gradx), 2 = forward only (dense queries: no derivative gather, no backward products)
+template <int L, int C, int G, bool kPaired, int kMode>
 __global__ void __launch_bounds__(G * 256, 1)
     mapping_step_tc2_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
                             const __grid_constant__ miso_frames_t fr, const __grid_constant__ MapArgs m) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(G * 256, 1)
   uint64_t* const bar = &s->bar[grp];
   uint32_t parity = 0;
 
-  const bool eik_on = m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f;
+  const bool eik_on = kMode == 1 ? true : (m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f);
   const bool eik_filter = m.cfg.eik_trunc_dist >= 0.f;
 
   // this half's slice of the feature vector
@@ -377,7 +379,12 @@ __global__ void __launch_bounds__(G * 256, 1)
   auto stage_point = [&](int t2) {
     const int n2 = t2 * 128 + pt;
     float p[3] = {0.f, 0.f, 0.f};
-    if (n2 < N32) load_point_smem(m.x, fr, n2, poses_in_smem ? s->poses : nullptr, p);
+    if (n2 < N32) {
+      load_point_smem(m.x, fr, n2, poses_in_smem ? s->poses : nullptr, p);
+      if constexpr (kMode != 0) {
+        if (m.xw) m.xw[3 * (int64_t)n2] = p[0], m.xw[3 * (int64_t)n2 + 1] = p[1], m.xw[3 * (int64_t)n2 + 2] = p[2];
+      }
+    }
     float4 q;
     q.x = normalize_coord(p[0], fl.bound[0], fl.bound[1]);
     q.y = normalize_coord(p[1], fl.bound[2], fl.bound[3]);
@@ -537,6 +544,15 @@ __global__ void __launch_bounds__(G * 256, 1)
       }
       s->ppx[grp * 256 + gtid] = pp;
     }
+    if constexpr (kMode == 2) {
+      // forward only: next tile's points, partial-sdf exchange, store
+      if (half == 1) stage_point(tile + tile_stride);
+      tc::wait_st();
+      tc::fence_before_sync();   // the next tile's MMA overwrites D only after every thread has read h2
+      group_barrier(grp);
+      if (half == 0 && active) m.sdf_out[n] = (pp + s->ppx[grp * 256 + (gtid ^ 128)]) + s->b3[0];
+      continue;
+    }
     tc::wait_st();
     tc::fence_before_sync();
     group_barrier(grp);
@@ -560,7 +576,7 @@ __global__ void __launch_bounds__(G * 256, 1)
     // loss inputs: fetched here so their latency hides behind the MMA round trip
     float gt = 0.f, wgt = 1.f, sgn = 0.f;
     unsigned vld = 0;
-    if (active) {
+    if (kMode == 0 && active) {
       gt = ldg_early_f32(m.gt_sdf + n);
       vld = ldg_early_u8(m.gt_valid + n);
       sgn = ldg_early_f32(m.gt_sign + n);
@@ -645,10 +661,12 @@ __global__ void __launch_bounds__(G * 256, 1)
         prefetch_l1(m.x + 3 * (int64_t)n3);
         prefetch_l1(m.x + 3 * (int64_t)n3 + 2);
         if (fr.ids) prefetch_l1(fr.ids + n3);
-        prefetch_l1(m.gt_sdf + n3);
-        prefetch_l1(m.gt_sign + n3);
-        prefetch_l1(m.gt_valid + n3);
-        if (m.weights) prefetch_l1(m.weights + n3);
+        if constexpr (kMode == 0) {
+          prefetch_l1(m.gt_sdf + n3);
+          prefetch_l1(m.gt_sign + n3);
+          prefetch_l1(m.gt_valid + n3);
+          if (m.weights) prefetch_l1(m.weights + n3);
+        }
       }
     }
     // ---- this half's share of grad_x sdf; exchange with the partner ---------------------------------
@@ -684,6 +702,21 @@ __global__ void __launch_bounds__(G * 256, 1)
     const float gy = (half == 0 ? gyh : other.z) + (half == 0 ? other.z : gyh);
     const float gz = (half == 0 ? gzh : other.w) + (half == 0 ? other.w : gzh);
 
+    if constexpr (kMode == 1) {
+      if (active) {
+        if (half == 0) {
+          m.sdf_out[n] = pred;
+          if (m.gradx) m.gradx[3 * (int64_t)n] = gx, m.gradx[3 * (int64_t)n + 1] = gy, m.gradx[3 * (int64_t)n + 2] = gz;
+        }
+        if (m.jac) {
+#pragma unroll
+          for (int j = 0; j < GH; ++j)
+            *reinterpret_cast<float4*>(m.jac + (int64_t)n * F + half * FH + 4 * j) =
+                make_float4(J[4 * j], J[4 * j + 1], J[4 * j + 2], J[4 * j + 3]);
+        }
+      }
+      continue;
+    }
     // ---- loss terms (both partners derive a and v; only half 0 accumulates the sums) -------------------
     const float lw = half == 0 ? 1.f : 0.f;
     if (active && half == 0 && m.sdf_out) m.sdf_out[n] = pred;
@@ -728,14 +761,16 @@ __global__ void __launch_bounds__(G * 256, 1)
         scatter_group4(lv, cells[ci], ch, (nz && lv.grad) ? 1u : 0u, a, v[0] * kx, v[1] * ky, v[2] * kz, J + 4 * j);
     }
   }
-  float s0 = block_sum(acc_sdf, red);
-  float s1 = block_sum(acc_fs, red);
-  float s2 = block_sum(acc_eik, red);
-  if (threadIdx.x == 0) {
-    m.partials[blockIdx.x * 4 + 0] = s0;
-    m.partials[blockIdx.x * 4 + 1] = s1;
-    m.partials[blockIdx.x * 4 + 2] = s2;
-    m.partials[blockIdx.x * 4 + 3] = 0.f;
+  if constexpr (kMode == 0) {
+    float s0 = block_sum(acc_sdf, red);
+    float s1 = block_sum(acc_fs, red);
+    float s2 = block_sum(acc_eik, red);
+    if (threadIdx.x == 0) {
+      m.partials[blockIdx.x * 4 + 0] = s0;
+      m.partials[blockIdx.x * 4 + 1] = s1;
+      m.partials[blockIdx.x * 4 + 2] = s2;
+      m.partials[blockIdx.x * 4 + 3] = 0.f;
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
