@@ -112,9 +112,12 @@ def test_world2_gloo_partitions_match_single_process():
     poses = {k: (R[k], t[k]) for k in range(3)}
     full = sum(O.mapping_loss(model, mi, gt, poses, "L1", 1.0, 0.0, 0.1, 0.15).values())
     full.backward()
-    assert abs(float(res["loss"]) - float(full)) < 1e-6 * max(1.0, abs(float(full)))
+    # worker processes run torch with 2 threads, this process with all cores: reductions differ in the last bits (a
+    # 4e-5 relative difference between the two was observed once), so the cross-process comparisons use 2e-4 / 1e-3;
+    # the partition logic itself is checked exactly below (sum of the per-rank terms == all-reduced total)
+    assert abs(float(res["loss"]) - float(full)) < 2e-4 * max(1.0, abs(float(full)))
     for a, b in zip(res["grads"], [p.grad for p in model.features]):
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-9)
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-7)
     Rt, tt = synth.submap_layout(3, spacing=(2.0, 1.5))
     Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=3.0, trans_m=0.2)
     shapes = O.level_shapes(BOUND, 0.5, 2, 2, 4)
@@ -133,9 +136,9 @@ def test_world2_gloo_partitions_match_single_process():
     total.backward()
     # the host logic under test: the all-reduced total is the sum of the per-pair terms the ranks computed
     assert abs(float(res["align"]) - sum(res["per_pair"])) < 1e-5 * abs(float(total)), (res["align"], res["per_pair"])
-    assert np.allclose(res["per_pair"], per_pair, rtol=1e-5), (res["per_pair"], per_pair)
+    assert np.allclose(res["per_pair"], per_pair, rtol=2e-4), (res["per_pair"], per_pair)
     for a, p in zip(res["pose_grads"], atlas.rot + atlas.tra):
         ref = p.grad if p.grad is not None else torch.zeros_like(p)
-        assert torch.allclose(a, ref, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(a, ref, rtol=1e-3, atol=1e-5)
     assert res["gathered"] == [0, 1, 2, 3, 4] and res["owners"] == [0, 1, 0, 1, 0]
     assert res["mine"] == [(0, 1), (1, 2)]
