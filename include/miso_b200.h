@@ -165,6 +165,16 @@ int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, cons
                       const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
                       miso_stream_t stream);
 
+/* Gauss-Newton / LM normal equations of one keyframe in ONE launch (Tracker.lm_step, grid_opt/slam/tracker.py:148-212):
+ * x_w = R x + t, r = sdf(x_w) - gt, g = grad_x sdf(x_w), J = [((R x) x g)^T R, g^T], w = 1 (loss_type 0, L2) or
+ * gm_scale/(gm_scale + r^2)^2 (loss_type 1, Geman-McClure :139-146); samples with |gt| >= trunc_dist are skipped when
+ * trunc_dist >= 0 (:158-164).  Rt = device pointer to 12 floats (R row-major, t).  out (45 doubles, overwritten):
+ * H = J^T W J row-major [0,36), b = J^T W r [36,42), in-bound count [42] (fov_overlap numerator :176), used samples [43],
+ * sum w r^2 [44]. */
+int miso_track_normal_equations(const miso_field_t* field, const miso_decoder_t* dec, const float* x_frame,
+                                const float* gt_sdf, int64_t N, const float* Rt, int32_t loss_type, float gm_scale,
+                                float trunc_dist, double* out, miso_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3. Latent-space submap alignment (pairwise_loss_latent, grid_opt/align/miso.py:116-211),
  *    batched over all submap pairs of one iteration of generic_align_multiple_submaps

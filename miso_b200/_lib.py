@@ -86,6 +86,8 @@ _SIGNATURES = {
     "miso_morton_keys": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "miso_transform_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                         C.c_void_p, C.c_void_p]),
+    "miso_track_normal_equations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                              C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "miso_expand_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "miso_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -500,6 +500,115 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel: Gauss-Newton / LM normal equations of one keyframe (Tracker.lm_step, grid_opt/slam/tracker.py:148-212)
+//   x_w = R x + t ; r = sdf(x_w) - gt ; g = grad_x sdf(x_w) ; J = [ ((R x) x g)^T R , g^T ] (N,6)
+//   w = 1 (L2) or c / (c + r^2)^2 (Geman-McClure, :139-146) ; H = J^T W J ; b = J^T W r
+// in ONE launch: transform, interpolation of every level, decoder + analytic gradient, residual weight, the 6-vector
+// J and the 21 + 6 reductions (per-thread partials -> warp shuffle -> float64 atomics), plus the in-bound count the
+// reference reports as fov_overlap (:176) and the number of samples that passed the |gt| < trunc filter (:158-164).
+// out (double[45]): H row-major [0,36) (both triangles), b [36,42), in-bound count [42], used count [43], sum w r^2 [44]
+// ---------------------------------------------------------------------------------------------
+template <int L, int C>
+__global__ void __launch_bounds__(kThreads)
+    track_normal_equations_kernel(const __grid_constant__ miso_field_t fl, const __grid_constant__ miso_decoder_t dec,
+                                  const float* __restrict__ x, const float* __restrict__ gt_sdf, int64_t N,
+                                  const float* __restrict__ Rt, int loss_type, float gm_scale, float trunc_dist,
+                                  double* __restrict__ out) {
+  constexpr int F = L * C;
+  constexpr int kAcc = 21 + 6 + 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecoderSmem<F>* s = reinterpret_cast<DecoderSmem<F>*>(smem_raw);
+  __shared__ float s_part[kThreads / 32][kAcc];
+  load_decoder<F>(s, dec);
+  const FieldGeom g = field_geom(fl);
+  float R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = Rt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = Rt[9 + i];
+  float acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const float gtv = gt_sdf[n];
+    if (trunc_dist >= 0.f && !(fabsf(gtv) < trunc_dist)) continue;
+    const float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
+    float xr[3], p[3], xn[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      xr[j] = fmaf(c, R[3 * j + 2], fmaf(b, R[3 * j + 1], a * R[3 * j]));   // x R^T (transform_points_to, t = 0)
+      p[j] = xr[j] + t[j];
+      xn[j] = normalize_coord(p[j], g.bmin[j], g.bmax[j]);
+    }
+    const bool inb = p[0] >= g.bmin[0] && p[0] <= g.bmax[0] && p[1] >= g.bmin[1] && p[1] <= g.bmax[1] &&
+                     p[2] >= g.bmin[2] && p[2] <= g.bmax[2];
+    float f[F], dfx[F], dfy[F], dfz[F];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if ((fl.ignore_mask >> l) & 1u) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) f[l * C + i] = dfx[l * C + i] = dfy[l * C + i] = dfz[l * C + i] = 0.f;
+      } else {
+        Cell cl = level_cell(fl.level[l], xn);
+        gather_level<C, true>(fl.level[l], cl, f + l * C, dfx + l * C, dfy + l * C, dfz + l * C);
+        const float kx = (float)fl.level[l].X * g.inv_len[0], ky = (float)fl.level[l].Y * g.inv_len[1],
+                    kz = (float)fl.level[l].Z * g.inv_len[2];
+#pragma unroll
+        for (int i = 0; i < C; ++i) dfx[l * C + i] *= kx, dfy[l * C + i] *= ky, dfz[l * C + i] *= kz;
+      }
+    }
+    float Jf[F];
+    const float sdf = mlp_eval<F, true>(s, f, Jf);
+    float gw[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < F; ++i) gw[0] = fmaf(Jf[i], dfx[i], gw[0]), gw[1] = fmaf(Jf[i], dfy[i], gw[1]), gw[2] = fmaf(Jf[i], dfz[i], gw[2]);
+    // hat(R x) g = (R x) x g ; J_R = (that)^T R ; J_t = g
+    const float cx = xr[1] * gw[2] - xr[2] * gw[1], cy = xr[2] * gw[0] - xr[0] * gw[2], cz = xr[0] * gw[1] - xr[1] * gw[0];
+    float J[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) J[j] = cx * R[j] + cy * R[3 + j] + cz * R[6 + j];
+    J[3] = gw[0], J[4] = gw[1], J[5] = gw[2];
+    const float r = sdf - gtv;
+    const float w = loss_type == 0 ? 1.0f : gm_scale / ((gm_scale + r * r) * (gm_scale + r * r));
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) acc[k++] += w * J[i] * J[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[21 + i] += w * J[i] * r;
+    acc[27] += inb ? 1.f : 0.f;
+    acc[28] += 1.f;
+    acc[29] += w * r * r;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double v = 0.0;
+    for (int w2 = 0; w2 < kThreads / 32; ++w2) v += (double)s_part[w2][threadIdx.x];
+    if (v != 0.0) {
+      const int i = threadIdx.x;
+      if (i < 21) {
+        int a2 = 0, tt = i;
+        while (tt >= 6 - a2) tt -= 6 - a2, ++a2;
+        const int b2 = a2 + tt;
+        atomicAdd(out + a2 * 6 + b2, v);
+        if (a2 != b2) atomicAdd(out + b2 * 6 + a2, v);
+      } else {
+        atomicAdd(out + 36 + (i - 21), v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel: scatter backward given per-point J, a, v  (+ optional Hessian-vector product wrt x)
 // ---------------------------------------------------------------------------------------------
 template <int L, int C>
@@ -1454,6 +1563,25 @@ extern "C" int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t*
     }
   });
   return check_launch("sdf_forward");
+}
+
+extern "C" int miso_track_normal_equations(const miso_field_t* field, const miso_decoder_t* dec, const float* x_frame,
+                                           const float* gt_sdf, int64_t N, const float* Rt, int32_t loss_type,
+                                           float gm_scale, float trunc_dist, double* out, miso_stream_t stream) {
+  if (int e = validate_field(field, false)) return e;
+  if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
+  MISO_REQUIRE(out && Rt && N >= 0 && (N == 0 || (x_frame && gt_sdf)), "track_normal_equations: null argument");
+  MISO_REQUIRE(loss_type == 0 || loss_type == 1, "track_normal_equations: loss_type must be 0 (L2) or 1 (GM)");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double) * 45, s);
+  if (N == 0) return check_launch("track_normal_equations(memset)");
+  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+    constexpr size_t smem = sizeof(DecoderSmem<L * C>);
+    auto k = track_normal_equations_kernel<L, C>;
+    k<<<grid_for(N, kThreads, sm_count()), kThreads, smem, s>>>(*field, *dec, x_frame, gt_sdf, N, Rt, loss_type, gm_scale,
+                                                                 trunc_dist, out);
+  });
+  return check_launch("track_normal_equations");
 }
 
 extern "C" int miso_sdf_backward(const miso_field_t* field, const float* xw, int64_t N, const float* jac,

@@ -3,13 +3,17 @@
 J = [ ((R x) x g)^T R , g^T ] with g = grad_x sdf, Geman-McClure weights, H = J^T W J + lambda I,
 b = J^T W r, delta = solve(H, -b), w += delta[:3], tau += delta[3:].
 
-On the B200 path the SDF and its spatial gradient come from ONE fused launch (`miso_sdf_forward`,
-analytic gradient instead of an autograd backward pass); the 6x6 normal equations are a handful of
-tiny torch ops on (N,6) tensors (N <= 2^14 in the reference's configs, ncd_quad.yaml:30)."""
+On the B200 path the whole right-hand side is ONE launch (`miso_track_normal_equations`): transform,
+interpolation, decoder + analytic spatial gradient (no autograd backward pass), the |gt| < trunc sample filter,
+Geman-McClure weights, the 6-vector J and the float64 reductions H = J^T W J, b = J^T W r and the in-bound count.
+What is left on the torch side is the 6x6 solve and the pose update.  `normal_equations_torch` keeps the previous
+formulation (fused sdf+gradient launch, then torch ops on (N,6) tensors) as the in-repo cross-check."""
+import ctypes as C
 import math
 
 import torch
 
+from . import _lib
 from . import field as _field
 from . import geometry as utils_geometry
 from .models import GridNet
@@ -35,8 +39,34 @@ class Tracker:
             return self.gm_scale_sdf / (self.gm_scale_sdf + r ** 2) ** 2
         raise ValueError(f"Unknown loss type: {self.loss_type}.")
 
-    def normal_equations(self, coords_frame, gt_sdf, Rwf, twf):
-        """(H (6,6), g (6,1), fov_overlap tensor) for one keyframe; coords_frame (N,3), gt_sdf (N,1)."""
+    def normal_equations(self, coords_frame, gt_sdf, Rwf, twf, trunc_dist=None):
+        """(H (6,6), g (6,1), fov_overlap tensor) for one keyframe from ONE kernel launch; coords_frame (N,3),
+        gt_sdf (N,1).  `trunc_dist` applies the |gt| < trunc filter of lm_step (tracker.py:158-164) inside the kernel."""
+        grid = self.grid
+        spec = grid.fused_spec()
+        if spec is None:
+            raise RuntimeError("Tracker needs the fused field (fixed decoder)")
+        lib = _lib.load()
+        x = _field._prep_x(coords_frame)
+        gt = gt_sdf.detach().reshape(-1).contiguous().float()
+        dev = x.device
+        Rt = torch.cat([Rwf.detach().reshape(9), twf.detach().reshape(3)]).contiguous().float()
+        out = torch.empty(45, dtype=torch.float64, device=dev)
+        fld = _field.make_field(grid.level_tensors(), spec.bound, None, spec.ignore_mask)
+        dec = spec.decoder.struct()
+        with torch.cuda.device(dev):
+            _lib.check(lib.miso_track_normal_equations(
+                C.byref(fld), C.byref(dec), x.data_ptr(), gt.data_ptr(), x.shape[0], Rt.data_ptr(),
+                {"L2": 0, "GM": 1}[self.loss_type], float(self.gm_scale_sdf),
+                float(trunc_dist) if trunc_dist is not None else -1.0, out.data_ptr(), _lib.stream_ptr(dev)),
+                "track_normal_equations")
+        H = out[:36].reshape(6, 6).float() + self.lm_lambda * torch.eye(6, device=dev)
+        g = out[36:42].reshape(6, 1).float()
+        fov = (out[42] / out[43].clamp(min=1.0)).float()
+        return H, g, fov
+
+    def normal_equations_torch(self, coords_frame, gt_sdf, Rwf, twf):
+        """Same quantities from the fused sdf+gradient launch and torch ops on (N,6) tensors (cross-check)."""
         grid = self.grid
         spec = grid.fused_spec()
         if spec is None:
@@ -62,14 +92,11 @@ class Tracker:
         frame_ids = model_input["sample_frame_ids"][0]
         gt_sdf = gt["sdf"][0]
         gt_sdf_valid = gt["sdf_valid"][0]
-        if self.trunc_dist is not None:
-            valid_idxs = torch.nonzero(torch.abs(gt_sdf[:, 0]) < self.trunc_dist, as_tuple=False).squeeze(1)
-            coords_frame, frame_ids = coords_frame[valid_idxs, :], frame_ids[valid_idxs, :]
-            gt_sdf, gt_sdf_valid = gt_sdf[valid_idxs, :], gt_sdf_valid[valid_idxs, :]
         grid = self.grid
         Rwf, twf = grid.updated_kf_pose_from_key(f"KF{optimize_kf}")
         Rwf, twf = Rwf.detach(), twf.detach()
-        H, g, fov = self.normal_equations(coords_frame, gt_sdf, Rwf, twf)
+        # the |gt| < trunc selection (tracker.py:158-164) happens inside the kernel: no nonzero() / gather passes
+        H, g, fov = self.normal_equations(coords_frame, gt_sdf, Rwf, twf, trunc_dist=self.trunc_dist)
         delta = torch.linalg.solve(H, -g)
         delta_R, delta_t = delta[:3], delta[3:]
         kf_id = grid.pose_key_to_id(f"KF{optimize_kf}")

@@ -244,6 +244,15 @@ def test_tracker_lm_normal_equations_and_step():
     assert rel_err(net.rotation_corrections[0], do[:3, 0]) < 1e-3
     assert rel_err(net.translation_corrections[0], do[3:]) < 1e-3
     assert 0.0 <= info["fov_overlap"] <= 1.0
+    # one-launch normal equations vs the torch formulation on the same fused sdf+gradient, incl. the in-kernel
+    # |gt| < trunc filter against an explicit nonzero()/gather selection (tracker.py:158-164), and fov_overlap
+    for loss_type in ("L2", "GM"):
+        tr = Tracker(net, loss_type=loss_type, gm_scale_sdf=0.1, lm_lambda=1e-4)
+        sel = torch.nonzero(torch.abs(gt_sdf[:, 0]) < 0.04, as_tuple=False).squeeze(1)
+        H1, b1, f1 = tr.normal_equations(xf.cuda(), gt_sdf.cuda(), Rwf.cuda(), twf.cuda(), trunc_dist=0.04)
+        H2, b2, f2 = tr.normal_equations_torch(xf[sel].cuda(), gt_sdf[sel].cuda(), Rwf.cuda(), twf.cuda())
+        assert rel_err(H1, H2) < TOL_G and rel_err(b1, b2) < TOL_G
+        assert abs(float(f1) - float(f2)) < 1e-6
 
 
 def test_inference_forward_and_atlas_query():
