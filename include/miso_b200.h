@@ -222,6 +222,13 @@ int miso_align_intersections(const miso_field_t* fields, int32_t num_fields, con
                              const float* poses, float overlap_thresh, int32_t* enabled_out,
                              unsigned long long* counts_out, miso_stream_t stream);
 
+/* GridAtlas.query_feature (grid_opt/models/grid_atlas.py:374-391) for all submaps in one launch: feats (N, levels*4) =
+ * in-bound-masked mean over the `active` submaps (device int32 indices into fields[], visited in order) of each
+ * submap's multi-level feature at the world points x.  poses (num_fields,12) = per submap (R^T row-major, -R^T t). */
+int miso_atlas_features(const miso_field_t* fields, int32_t num_fields, const int32_t* active, int32_t num_active,
+                        const float* poses, const float* x, int64_t N, int32_t levels, float* feats,
+                        miso_stream_t stream);
+
 /* Pose glue of one alignment iteration (grid_opt/align/base.py:127-159 around the loss) as three single-block
  * kernels: (1) R = R0 Exp(w), t = t0 + tau for every submap (grid_atlas.py:250-268; Exp = pytorch3d so3_exp_map
  * with its 1e-4 clamp) and the per-pair (A1,b1,A2,b2) rows; (2) from miso_align_batch's reductions to

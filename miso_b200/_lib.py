@@ -76,6 +76,8 @@ _SIGNATURES = {
                                    C.c_int32, C.c_void_p]),
     "miso_align_intersections": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                            C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "miso_atlas_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int32, C.c_void_p, C.c_void_p]),
     "miso_align_compose_poses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "miso_align_pose_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

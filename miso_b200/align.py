@@ -31,9 +31,7 @@ from . import geometry as utils_geometry
 from .models import GridAtlas
 
 
-def _structs_to_device(structs, device) -> torch.Tensor:
-    raw = b"".join(bytes(s) for s in structs)
-    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+_structs_to_device = _field.structs_to_device
 
 
 class AlignBatch:

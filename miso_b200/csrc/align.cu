@@ -442,6 +442,56 @@ __global__ void align_intersection_finalize(const miso_align_pair_t* __restrict_
   enabled[slot] = frac > thresh ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// GridAtlas.query_feature (grid_opt/models/grid_atlas.py:374-391): in-bound-masked MEAN over the active submaps
+// of each submap's multi-level feature at a world point, in ONE launch over all submaps (the reference loops over
+// submaps with a transform, a mask, L grid_sample launches and two accumulations each).  poses (S,12) = per submap
+// (A = R^T row-major, b = -R^T t), composed by the caller exactly as transfrom_points_from does.  Submaps are visited
+// in index order so the fp32 sums match the reference's accumulation order.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+    atlas_features_kernel(const miso_field_t* __restrict__ fields, const int32_t* __restrict__ active, int num_active,
+                          const float* __restrict__ poses, const float* __restrict__ x, int64_t N, int levels,
+                          float* __restrict__ out) {
+  const int F = levels * C;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const float p[3] = {x[3 * n], x[3 * n + 1], x[3 * n + 2]};
+    float sum[MISO_MAX_LEVELS * C];
+#pragma unroll
+    for (int i = 0; i < MISO_MAX_LEVELS * C; ++i) sum[i] = 0.f;
+    float wsum = 0.f;
+    for (int a = 0; a < num_active; ++a) {
+      const int sidx = active[a];
+      const miso_field_t& fld = fields[sidx];
+      float A[9], b[3], q[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A[i] = poses[sidx * 12 + i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b[i] = poses[sidx * 12 + 9 + i];
+      xform(A, b, p, q);
+      if (!in_bound(q, fld.bound)) continue;     // mask_bnd * feats: out-of-bound submaps add exactly zero
+      wsum += 1.f;
+      float qn[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) qn[d] = normalize_coord(q[d], fld.bound[2 * d], fld.bound[2 * d + 1]);
+#pragma unroll
+      for (int l = 0; l < MISO_MAX_LEVELS; ++l) {
+        if (l >= levels || ((fld.ignore_mask >> l) & 1u)) continue;
+        const miso_level_t& lv = fld.level[l];
+        Cell c = make_cell(unnormalize_nc(qn[0], lv.X), unnormalize_nc(qn[1], lv.Y), unnormalize_nc(qn[2], lv.Z), lv);
+        float f[C];
+        gather4<C>(lv, c, f, nullptr, nullptr, nullptr, false);
+#pragma unroll
+        for (int i = 0; i < C; ++i) sum[l * C + i] += f[i];
+      }
+    }
+    const float den = wsum == 0.f ? 1.0f : wsum;   // torch.where(sum_weights == 0, 1, sum_weights)
+    for (int i = 0; i < F; ++i) out[n * F + i] = sum[i] / den;
+  }
+}
+
 }  // namespace miso
 
 using namespace miso;
@@ -486,4 +536,17 @@ extern "C" int miso_align_intersections(const miso_field_t* fields, int32_t num_
   align_intersection_finalize<<<(num_pairs + 127) / 128, 128, 0, s>>>(pairs, num_pairs, counts_out, overlap_thresh,
                                                                        enabled_out);
   return check_launch("align_intersections");
+}
+
+extern "C" int miso_atlas_features(const miso_field_t* fields, int32_t num_fields, const int32_t* active,
+                                   int32_t num_active, const float* poses, const float* x, int64_t N, int32_t levels,
+                                   float* feats, miso_stream_t stream) {
+  MISO_REQUIRE(fields && active && poses && num_fields > 0 && num_active >= 0, "atlas_features: null argument");
+  MISO_REQUIRE(levels >= 1 && levels <= MISO_MAX_LEVELS, "atlas_features: levels %d not in [1,%d]", levels, MISO_MAX_LEVELS);
+  MISO_REQUIRE(N >= 0 && (N == 0 || (x && feats)), "atlas_features: null x/feats");
+  if (N == 0) return MISO_OK;
+  // fields live on the device: the ABI fixes C = 4 per level here, as for alignment (fdim=4, miso.py:122)
+  atlas_features_kernel<4><<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, (cudaStream_t)stream>>>(
+      fields, active, num_active, poses, x, N, levels, feats);
+  return check_launch("atlas_features");
 }

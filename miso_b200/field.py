@@ -55,6 +55,12 @@ def make_field(feats: Sequence[torch.Tensor], bound: Sequence[float], grads: Opt
     return f
 
 
+def structs_to_device(structs, device) -> torch.Tensor:
+    """Pack ctypes structs (miso_field_t, miso_align_pair_t ...) into one device byte buffer."""
+    raw = b"".join(bytes(s) for s in structs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
 def bound_to_list(bound) -> List[float]:
     """(3,2) tensor / array / nested list -> [xmin,xmax,ymin,ymax,zmin,zmax] python floats.
     Done once at module construction: reading a CUDA tensor here would be a host sync."""

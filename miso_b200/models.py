@@ -637,8 +637,52 @@ class GridAtlas(BaseNet):
         assert submap_id >= 0 and submap_id < self.num_submaps
         return self.submaps[submap_id]
 
+    def _fused_query_ok(self, x_world):
+        if not x_world.is_cuda or len(self.active_submaps) == 0:
+            return False
+        if torch.is_grad_enabled() and (x_world.requires_grad or any(
+                f.requires_grad for i in self.active_submaps for f in self.get_submap(i).level_tensors())):
+            return False
+        subs = [self.get_submap(i) for i in range(self.num_submaps)]
+        return all(sm.fdim == 4 and sm.num_levels == subs[0].num_levels and sm.num_levels <= 4 and
+                   sm.features[0].feature.is_cuda for sm in subs)
+
     def query_feature(self, x_world: torch.Tensor):
-        """grid_atlas.py:374-391: in-bound-masked mean of the submaps' features at world points."""
+        """grid_atlas.py:374-391: in-bound-masked mean of the submaps' features at world points.  Without autograd
+        (fusion / meshing queries) every submap is visited inside ONE launch (miso_atlas_features)."""
+        if self._fused_query_ok(x_world):
+            import ctypes as C
+            from . import _lib
+            lib = _lib.load()
+            dev = x_world.device
+            key = tuple((f.data_ptr(), tuple(f.stride())) for i in range(self.num_submaps)
+                        for f in self.get_submap(i).level_tensors()) + tuple(
+                tuple(self.get_submap(i).ignore_level_) for i in range(self.num_submaps))
+            cache = getattr(self, "_atlas_fields_cache", None)
+            if cache is None or cache[0] != key:
+                fields = []
+                for i in range(self.num_submaps):
+                    sm = self.get_submap(i)
+                    mask = sum((1 << l) for l in range(sm.num_levels) if sm.ignore_level_[l])
+                    fields.append(_field.make_field(sm.level_tensors(), sm._bound_host, None, mask))
+                cache = (key, _field.structs_to_device(fields, dev))
+                self._atlas_fields_cache = cache
+            with torch.no_grad():
+                poses = []
+                for i in range(self.num_submaps):
+                    R, t = self.updated_submap_pose(i)
+                    Rt_ = R.T                                        # transfrom_points_from (utils_geometry.py:227-240)
+                    poses.append(torch.cat([Rt_.reshape(9), (-Rt_ @ t).reshape(3)]))
+                poses = torch.stack(poses, 0).contiguous().float()
+            active = torch.tensor(list(self.active_submaps), dtype=torch.int32, device=dev)
+            x = _field._prep_x(x_world)
+            L = self.get_submap(0).num_levels
+            out = torch.empty((x.shape[0], 4 * L), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.miso_atlas_features(cache[1].data_ptr(), self.num_submaps, active.data_ptr(),
+                                                   int(active.numel()), poses.data_ptr(), x.data_ptr(), x.shape[0], L,
+                                                   out.data_ptr(), _lib.stream_ptr(dev)), "atlas_features")
+            return out
         sum_feats = 0
         sum_weights = 0
         for submap_id in self.active_submaps:

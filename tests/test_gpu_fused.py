@@ -286,6 +286,17 @@ def test_inference_forward_and_atlas_query():
         sw = sw + m
     sw = torch.where(sw == 0, torch.ones_like(sw), sw).float()
     assert rel_err(got, sf / sw) < TOL_F
+    # the one-launch atlas query (miso_atlas_features, taken under no_grad) vs the per-submap torch path (taken
+    # when autograd is needed), incl. a three-submap atlas with one inactive submap
+    xg = xw.cuda().requires_grad_(True)
+    per_submap = atlas.query_feature(xg)
+    assert rel_err(got, per_submap) < TOL_F
+    atlas.add_submap(torch.tensor(SMALL_BOUND), torch.eye(3), torch.tensor([[-1.0], [0.2], [0.0]]))
+    atlas.get_submap(2).randn_features(0.1)
+    atlas.active_submaps = [0, 2]
+    with torch.no_grad():
+        fused = atlas.query_feature(xw.cuda())
+    assert rel_err(fused, atlas.query_feature(xg)) < TOL_F
 
 
 def test_compact_host_batches_match_reference_format():
