@@ -106,6 +106,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(world):
+    """`config` of the JSON line: the same dict for the product arm and for --impl reference."""
+    return {"workload": "build_submaps: 1 ScanNet-submap GridNet per GPU, 2 levels (40x20x40, 200x100x200) x C4, "
+                        "decoder 8-64-64-1 fixed, 2^20 RGB-D-sampled pts/iter, L1 sdf + 0.1 free-space + 0.5 "
+                        "second-order eikonal, Adam joint",
+            "points_per_step_per_gpu": N_POINTS, "submaps": world, "parallelism": f"submap-per-gpu x{world}",
+            "l2_policy": f"{NUM_HOST_BATCHES} distinct batches cycled; grids+grads+Adam state+batch "
+                         "(~360 MB/step touched) exceed the 126 MB L2"}
+
+
 def make_host_batches(seed0):
     from miso_b200 import synth
     batches = []
@@ -273,12 +283,7 @@ def run_ours(args):
         "metric": "SDF train pts/s (grid+MLP fwd/bwd/eikonal)", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "build_submaps: 1 ScanNet-submap GridNet per GPU, 2 levels (40x20x40, 200x100x200) x C4, "
-                               "decoder 8-64-64-1 fixed, 2^20 RGB-D-sampled pts/iter, L1 sdf + 0.1 free-space + 0.5 "
-                               "second-order eikonal, Adam joint",
-                   "points_per_step_per_gpu": N_POINTS, "submaps": world, "parallelism": f"submap-per-gpu x{world}",
-                   "l2_policy": f"{NUM_HOST_BATCHES} distinct batches cycled; grids+grads+Adam state+batch "
-                                "(~360 MB/step touched) exceed the 126 MB L2"},
+        "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": world * N_POINTS / (e2e_ms / args.steps * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / args.steps},
@@ -483,8 +488,9 @@ def run_reference(args):
             "unit": "points/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
             "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "build_submaps (same step as the product arm) on the reference's torch CPU path "
-                                   "(oracle port), bounded sample"},
+            "config": dict(workload_config(int(os.environ.get("WORLD_SIZE", "1"))),
+                           reference_arm="the reference's torch CPU path (oracle port, oracle/oracle.py) on a bounded "
+                                         "sample of this workload, rank 0's host cores"),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
