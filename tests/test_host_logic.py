@@ -155,3 +155,24 @@ def test_balanced_pair_owner_is_deterministic_and_balanced():
         assert max(loads) <= sum(costs) / w + max(costs) + 1e-6          # LPT guarantee
         mine = [[i for i in range(120) if mdist.balanced_pair_filter(costs, r, w)(i, None)] for r in range(w)]
         assert sorted(sum(mine, [])) == list(range(120))
+
+
+def test_compact_batch_host_side():
+    """CompactBatch.from_reference (host side, no GPU): 18 B/point for RGB-D batches (unit weights dropped), weights
+    kept for LiDAR batches, refusal when the masks are not the dataset's functions of the sdf or ids overflow int16."""
+    from miso_b200.trainer import CompactBatch
+    mi, gt, _ = synth.rgbd_batch(3000, num_kf=5, seed=2)
+    cb = CompactBatch.from_reference(mi, gt, 0.15, pin=False)
+    t = cb.tensors()
+    assert set(t) == {"coords", "ids16", "sdf"} and t["ids16"].dtype == torch.int16
+    assert sum(v.numel() * v.element_size() for v in t.values()) == 18 * 3000
+    assert torch.equal(t["ids16"].long(), mi["sample_frame_ids"][0, :, 0])
+    mil, gtl, _ = synth.lidar_batch(4000, num_kf=3, seed=4)
+    cbl = CompactBatch.from_reference(mil, gtl, 0.5, pin=False)
+    assert "weights" in cbl.tensors() and torch.equal(cbl.tensors()["weights"], mil["weights"][0, :, 0])
+    with pytest.raises(ValueError):
+        CompactBatch.from_reference(mi, gt, 0.2, pin=False)          # masks were built with trunc 0.15
+    big = {k: v.clone() for k, v in mi.items()}
+    big["sample_frame_ids"][0, 0, 0] = 40000
+    with pytest.raises(ValueError):
+        CompactBatch.from_reference(big, gt, 0.15, pin=False)
