@@ -272,6 +272,12 @@ int miso_expand_batch(const int16_t* ids16, const float* sdf, float trunc_dist, 
 int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int32_t step, int32_t zero_grad, miso_stream_t stream);
 
+/* Same step with an "ever touched" bitmap (ceil(n/4/32) uint32 words, zero-initialised by the caller, one bit per
+ * 4-float voxel; n % 4 == 0, 16-byte aligned tensors): voxels that no sample has ever touched are skipped after
+ * reading only their gradient.  Bit-identical results to miso_adam_step. */
+int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr, float beta1,
+                           float beta2, float eps, int32_t step, int32_t zero_grad, miso_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the
  *    3xTF32 split, activations in TMEM, weights in shared memory): D (M,64) = A (M,64) * W^T

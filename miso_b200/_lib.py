@@ -93,6 +93,8 @@ _SIGNATURES = {
     "miso_expand_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "miso_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "miso_adam_step_tracked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                         C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "miso_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
 }

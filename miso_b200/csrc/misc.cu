@@ -84,6 +84,46 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Same update with an "ever touched" bitmap (one bit per 4-float voxel): a voxel whose bit is clear has
+// g = m = v = 0 by construction, so when its gradient is zero again NOTHING but the 16-byte gradient (L2-resident right
+// after the scatter) is read -- the plain kernel above still streams m and v (2 x 16 B per voxel) from HBM to find that
+// out.  Thread i <-> voxel i; the 32 voxels of a warp share one bitmap word (broadcast load, ballot, one store).
+__global__ void __launch_bounds__(kThreads)
+    adam_tracked_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                        uint32_t* __restrict__ touched, int64_t n4, float lr, float b1, float b2, float eps,
+                        float step_size, float bc2_sqrt, int zero) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t n4r = (n4 + 31) & ~(int64_t)31;   // whole warps stay in the loop (ballot below)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4r; i += stride) {
+    const bool live = i < n4;
+    const uint32_t word = touched[i >> 5];
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) gv = reinterpret_cast<float4*>(g)[i];
+    const bool gnz = gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f;
+    const bool was = (word >> lane) & 1u;
+    const uint32_t now = __ballot_sync(0xffffffffu, was || gnz);
+    if (lane == 0 && now != word) touched[i >> 5] = now;
+    if (!live || !(was || gnz)) continue;
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
+          va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ma[e] = ma[e] + (ga[e] - ma[e]) * (1.f - b1);
+      va[e] = va[e] * b2 + (1.f - b2) * ga[e] * ga[e];
+      float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] = pa[e] - step_size * (ma[e] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (zero && gnz) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
     transform_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ R,
                      const float* __restrict__ t, int num_frames, int64_t N, float* __restrict__ y) {
@@ -177,6 +217,22 @@ extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n,
   adam_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, step_size,
                                                              bc2_sqrt, zero_grad);
   return check_launch("adam_step");
+}
+
+extern "C" int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
+                                      float beta1, float beta2, float eps, int32_t step, int32_t zero_grad,
+                                      miso_stream_t stream) {
+  MISO_REQUIRE(p && g && m && v && touched, "adam_step_tracked: null tensor");
+  MISO_REQUIRE(n >= 0 && n % 4 == 0 && step >= 1, "adam_step_tracked: n must be a non-negative multiple of 4, step >= 1");
+  MISO_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0, "adam_step_tracked: tensors not 16-byte aligned");
+  if (n == 0) return MISO_OK;
+  const int64_t n4 = n / 4;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int blocks = grid_for(n4, kThreads, sm_count() * 8);
+  adam_tracked_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, touched, n4, lr, beta1, beta2, eps,
+                                                                     (float)((double)lr / bc1), (float)sqrt(bc2), zero_grad);
+  return check_launch("adam_step_tracked");
 }
 
 extern "C" int miso_transform_points(const float* x, const int64_t* ids, const float* R, const float* t,

@@ -13,10 +13,11 @@ from . import _lib
 
 class FusedAdam:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 zero_grad_in_step=True):
+                 zero_grad_in_step=True, track_touched=True):
         self.params = [p for p in params]
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.zero_grad_in_step = zero_grad_in_step
+        self.track_touched = track_touched
         self.state = {}
         self.param_groups = [{"params": self.params, "lr": self.lr}]
 
@@ -24,6 +25,9 @@ class FusedAdam:
         st = self.state.get(p)
         if st is None:
             st = {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+            if self.track_touched and p.numel() % 4 == 0 and p.data_ptr() % 16 == 0:
+                # one bit per 4-float voxel: never-touched voxels are skipped after reading only their gradient
+                st["touched"] = torch.zeros((p.numel() // 4 + 31) // 32, dtype=torch.int32, device=p.device)
             self.state[p] = st
         return st
 
@@ -52,6 +56,13 @@ class FusedAdam:
             m, v = st["exp_avg"], st["exp_avg_sq"]
             if m.stride() != p.stride() or v.stride() != p.stride():
                 raise RuntimeError("FusedAdam: optimizer state layout diverged from the parameter layout")
+            if "touched" in st and g.data_ptr() % 16 == 0:
+                with torch.cuda.device(p.device):
+                    _lib.check(lib.miso_adam_step_tracked(
+                        p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), st["touched"].data_ptr(), p.numel(),
+                        self.lr, self.betas[0], self.betas[1], self.eps, st["step"], int(self.zero_grad_in_step),
+                        _lib.stream_ptr(p.device)), "adam_step")
+                continue
             with torch.cuda.device(p.device):
                 _lib.check(lib.miso_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
                                               self.lr, self.betas[0], self.betas[1], self.eps, st["step"],

@@ -197,6 +197,25 @@ def test_adam_matches_torch():
         o2.step()
     assert rel_err(p1, p2) < 1e-6
     assert torch.count_nonzero(p1.grad) == 0
+    # sparse gradients (most voxels never touched, some touched once and then only decaying): the bitmap-tracked
+    # kernel, the plain kernel and torch.optim.Adam must agree, and the bitmap must mark exactly the touched voxels
+    base = torch.randn(1, 4, 16, 12, 20, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    ps = [torch.nn.Parameter(base.clone()) for _ in range(3)]
+    opts = [FusedAdam([ps[0]], lr=1e-3, track_touched=True), FusedAdam([ps[1]], lr=1e-3, track_touched=False),
+            torch.optim.Adam([ps[2]], lr=1e-3)]
+    ever = torch.zeros(16, 12, 20, dtype=torch.bool, device="cuda")
+    for i in range(5):
+        mask = (torch.rand(16, 12, 20, device="cuda") < 0.1) if i < 3 else torch.zeros_like(ever)
+        ever |= mask
+        g = (torch.randn_like(base) * mask[None, None]).contiguous(memory_format=torch.channels_last_3d)
+        for q, o in zip(ps, opts):
+            q.grad = g.clone()
+            o.step()
+    assert rel_err(ps[0], ps[2]) < 1e-6 and rel_err(ps[1], ps[2]) < 1e-6
+    assert torch.equal(ps[0].detach(), ps[1].detach())                      # bit-identical to the plain kernel
+    words = opts[0].state[ps[0]]["touched"]
+    bits = ((words.view(-1, 1) >> torch.arange(32, device="cuda")) & 1).bool().reshape(-1)[:ever.numel()]
+    assert torch.equal(bits, ever.reshape(-1))                               # channels-last: voxel order = z,y,x
 
 
 def test_full_size_properties():
