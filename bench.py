@@ -47,7 +47,7 @@ elif os.environ.get("MISO_TC", "") == "1":
 else:
     KERNEL_NAME = "mapping_step_tc2_kernel<2,4,%s,%s> (two threads per point) (+finalize)" % (
         os.environ.get("MISO_TC2_GROUPS", "4"), "unpaired" if os.environ.get("MISO_PAIR", "1") == "0" else "paired")
-NCU_DRAM_BYTES_PER_LAUNCH = 122528768 + 19563264     # profiles/r01_ncu_mapping_step_tc2.csv (2^20 points)
+NCU_DRAM_BYTES_PER_LAUNCH = 120334336 + 12498688     # profiles/r01_ncu_mapping_step_tc2.csv (2^20 points)
 
 
 def measured_hbm_peak():

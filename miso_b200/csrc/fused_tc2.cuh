@@ -152,16 +152,20 @@ __device__ __forceinline__ void scatter_group4(const miso_level_t& lv, const Cel
 // ---- lane-paired gather / scatter --------------------------------------------------------------------
 // A 16-byte corner fetch (or reduction) per lane makes the L1TEX tag stage serve one 128-byte line per lane
 // (~2 cycles per line, the kernel's busiest unit).  The two x-neighbours of a corner pair are contiguous in the
-// channels-last grid (32 bytes, same line 7 times out of 8), so lanes l and l^16 cooperate: in one instruction
-// lane l touches corner (dx=0) and lane l^16 corner (dx=1) of the SAME point; a second instruction does the
-// other point.  Each lane therefore always works on dx = hsel (its half-warp index) for its own point and its
+// channels-last grid (32 bytes, same line 7 times out of 8), so lanes l and l^1 cooperate: in one instruction
+// lane l touches corner (dx=0) and lane l^1 corner (dx=1) of the SAME point; a second instruction does the
+// other point.  Each lane therefore always works on dx = hsel (its parity) for its own point and its
 // partner's, and one shuffle per word brings home the neighbour it did not fetch.  Lines per instruction halve.
+// partner lane = lane ^ kPairXor.  Adjacent lanes hold consecutive samples of a batch (in the reference's RGB-D / LiDAR
+// batches: consecutive samples along one ray), which very often sit in the same voxel cell -- the merged
+// reductions below depend on that.
+constexpr int kPairXor = 1;
 __device__ __forceinline__ float4 shfl16_f4(float4 v) {
   float4 r;
-  r.x = __shfl_xor_sync(0xffffffffu, v.x, 16);
-  r.y = __shfl_xor_sync(0xffffffffu, v.y, 16);
-  r.z = __shfl_xor_sync(0xffffffffu, v.z, 16);
-  r.w = __shfl_xor_sync(0xffffffffu, v.w, 16);
+  r.x = __shfl_xor_sync(0xffffffffu, v.x, kPairXor);
+  r.y = __shfl_xor_sync(0xffffffffu, v.y, kPairXor);
+  r.z = __shfl_xor_sync(0xffffffffu, v.z, kPairXor);
+  r.w = __shfl_xor_sync(0xffffffffu, v.w, kPairXor);
   return r;
 }
 __device__ __forceinline__ float4 sel_f4(bool p, float4 a, float4 b) {
@@ -171,18 +175,24 @@ __device__ __forceinline__ float4 sel_f4(bool p, float4 a, float4 b) {
 __device__ __forceinline__ void gather_group4_paired(const miso_level_t& lv, const CellLite& c, int ch, unsigned hsel,
                                                      float* __restrict__ f, float* __restrict__ dfx,
                                                      float* __restrict__ dfy, float* __restrict__ dfz) {
-  const int pbase = __shfl_xor_sync(0xffffffffu, c.base, 16);
-  const unsigned pvalid = __shfl_xor_sync(0xffffffffu, c.valid, 16);
+  const int pbase = __shfl_xor_sync(0xffffffffu, c.base, kPairXor);
+  const unsigned pvalid = __shfl_xor_sync(0xffffffffu, c.valid, kPairXor);
   const int base1 = hsel ? pbase : c.base, base2 = hsel ? c.base : pbase;          // point of the LOW lane first
   const unsigned valid1 = hsel ? pvalid : c.valid, valid2 = hsel ? c.valid : pvalid;
   const float* src = lv.feat + ch + (hsel ? (int)lv.sX : 0);
   float4 l1[4], l2[4];
+  const bool same_cell = base1 == base2 && valid1 == valid2;   // the pair shares all 8 corners: fetch them once
   if (__all_sync(0xffffffffu, c.valid == 0xffu)) {
 #pragma unroll
     for (int yz = 0; yz < 4; ++yz) {
       const int dlt = ((yz & 1) ? (int)lv.sY : 0) + ((yz & 2) ? (int)lv.sZ : 0);
       l1[yz] = ldg_f4(src + (base1 + dlt));
-      l2[yz] = ldg_f4(src + (base2 + dlt));
+    }
+#pragma unroll
+    for (int yz = 0; yz < 4; ++yz) {
+      const int dlt = ((yz & 1) ? (int)lv.sY : 0) + ((yz & 2) ? (int)lv.sZ : 0);
+      l2[yz] = l1[yz];
+      if (!same_cell) l2[yz] = ldg_f4(src + (base2 + dlt));
     }
   } else {
 #pragma unroll
@@ -229,10 +239,9 @@ __device__ __forceinline__ void gather_group4_paired(const miso_level_t& lv, con
   }
 }
 
-// reductions of one point's four (dy,dz) corners with dx = hsel
-__device__ __forceinline__ void scatter_half4(float* __restrict__ gbase, const miso_level_t& lv, unsigned hsel, int base,
-                                              unsigned valid, float a, float vix, float viy, float viz, float fx,
-                                              float fy, float fz, float J0, float J1, float J2, float J3) {
+// coefficients (a*w_c + v . dw_c/di) of one point's four (dy,dz) corners with dx = hsel
+__device__ __forceinline__ void corner_coefs4(unsigned hsel, float a, float vix, float viy, float viz, float fx, float fy,
+                                              float fz, float (&coef)[4]) {
   const float wx = hsel ? fx : 1.0f - fx;
   const float px = fmaf(a, wx, hsel ? vix : -vix);
   float r[2], q[2];
@@ -246,19 +255,20 @@ __device__ __forceinline__ void scatter_half4(float* __restrict__ gbase, const m
   for (int yz = 0; yz < 4; ++yz) {
     const int dy = yz & 1, dz = yz >> 1;
     const float wz = dz ? fz : 1.0f - fz;
-    const float coef = fmaf(wz, r[dy], (dz ? viz : -viz) * q[dy]);
-    const unsigned ok = (valid >> (2u * yz + hsel)) & 1u;
-    const int dlt = (dy ? (int)lv.sY : 0) + (dz ? (int)lv.sZ : 0) + (hsel ? (int)lv.sX : 0);
-    float* dst = gbase + (ok ? base + dlt : 0);
-    red_add_f4_if(ok, dst, coef * J0, coef * J1, coef * J2, coef * J3);
+    coef[yz] = fmaf(wz, r[dy], (dz ? viz : -viz) * q[dy]);
   }
 }
 
+// Lanes l and l^1 hold two consecutive samples A (even lane) and B (odd lane); each lane issues the reductions of the
+// corners with dx = hsel of BOTH points.  When A and B sit in the same cell (same base, same validity -- consecutive
+// ray samples usually do on the coarse level and near surfaces on the fine one) their contributions to a corner are
+// summed in registers and ONE reduction is issued: the SM retires reductions at ~2 cycles per lane, so every merged
+// pair saves real time, and the L2 sees fewer same-address updates.
 __device__ __forceinline__ void scatter_group4_paired(const miso_level_t& lv, const CellLite& c, int ch, unsigned hsel,
                                                       unsigned on, float a, float vix, float viy, float viz,
                                                       const float* __restrict__ J) {
   const unsigned valid = on ? c.valid : 0u;
-#define MISO_X16(v) __shfl_xor_sync(0xffffffffu, (v), 16)
+#define MISO_X16(v) __shfl_xor_sync(0xffffffffu, (v), kPairXor)
   const int pbase = MISO_X16(c.base);
   const unsigned pvalid = MISO_X16(valid);
   const float pa = MISO_X16(a), pvx = MISO_X16(vix), pvy = MISO_X16(viy), pvz = MISO_X16(viz);
@@ -267,13 +277,29 @@ __device__ __forceinline__ void scatter_group4_paired(const miso_level_t& lv, co
 #undef MISO_X16
   float* gbase = lv.grad + ch;
   const bool h = hsel != 0;
-  // first the LOW lane's point (own for hsel = 0, the partner's for hsel = 1), then the HIGH lane's
-  scatter_half4(gbase, lv, hsel, h ? pbase : c.base, h ? pvalid : valid, h ? pa : a, h ? pvx : vix, h ? pvy : viy,
-                h ? pvz : viz, h ? pfx : c.fx, h ? pfy : c.fy, h ? pfz : c.fz, h ? pJ0 : J[0], h ? pJ1 : J[1],
-                h ? pJ2 : J[2], h ? pJ3 : J[3]);
-  scatter_half4(gbase, lv, hsel, h ? c.base : pbase, h ? valid : pvalid, h ? a : pa, h ? vix : pvx, h ? viy : pvy,
-                h ? viz : pvz, h ? c.fx : pfx, h ? c.fy : pfy, h ? c.fz : pfz, h ? J[0] : pJ0, h ? J[1] : pJ1,
-                h ? J[2] : pJ2, h ? J[3] : pJ3);
+  // point 1 = the EVEN lane's (own for hsel = 0, the partner's for hsel = 1), point 2 = the odd lane's
+  const int base1 = h ? pbase : c.base, base2 = h ? c.base : pbase;
+  const unsigned valid1 = h ? pvalid : valid, valid2 = h ? valid : pvalid;
+  float c1[4], c2[4];
+  corner_coefs4(hsel, h ? pa : a, h ? pvx : vix, h ? pvy : viy, h ? pvz : viz, h ? pfx : c.fx, h ? pfy : c.fy,
+                h ? pfz : c.fz, c1);
+  corner_coefs4(hsel, h ? a : pa, h ? vix : pvx, h ? viy : pvy, h ? viz : pvz, h ? c.fx : pfx, h ? c.fy : pfy,
+                h ? c.fz : pfz, c2);
+  const float J1a[4] = {h ? pJ0 : J[0], h ? pJ1 : J[1], h ? pJ2 : J[2], h ? pJ3 : J[3]};
+  const float J2a[4] = {h ? J[0] : pJ0, h ? J[1] : pJ1, h ? J[2] : pJ2, h ? J[3] : pJ3};
+  const bool same = base1 == base2 && valid1 == valid2;
+#pragma unroll
+  for (int yz = 0; yz < 4; ++yz) {
+    const int dy = yz & 1, dz = yz >> 1;
+    const int dlt = (dy ? (int)lv.sY : 0) + (dz ? (int)lv.sZ : 0) + (hsel ? (int)lv.sX : 0);
+    const unsigned k = 2u * yz + hsel;
+    const unsigned ok1 = (valid1 >> k) & 1u;
+    const unsigned ok2 = same ? 0u : (valid2 >> k) & 1u;
+    const float m2 = same ? c2[yz] : 0.f;   // merged: point 2 rides on point 1's reduction
+    red_add_f4_if(ok1, gbase + (ok1 ? base1 + dlt : 0), fmaf(m2, J2a[0], c1[yz] * J1a[0]), fmaf(m2, J2a[1], c1[yz] * J1a[1]),
+                  fmaf(m2, J2a[2], c1[yz] * J1a[2]), fmaf(m2, J2a[3], c1[yz] * J1a[3]));
+    red_add_f4_if(ok2, gbase + (ok2 ? base2 + dlt : 0), c2[yz] * J2a[0], c2[yz] * J2a[1], c2[yz] * J2a[2], c2[yz] * J2a[3]);
+  }
 }
 
 // kMode: 0 = whole mapping step (losses + scatter), 1 = forward with Jacobian / grad_x outputs (miso_sdf_forward with
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(G * 256, 1)
   const int half = (warp_u >> 2) & 1;
   const int gtid = tid & 255;
   const int pt = gtid & 127;
-  const unsigned hsel = (unsigned)(tid >> 4) & 1u;   // half-warp index (lane-paired gather / scatter)
+  const unsigned hsel = (unsigned)tid & (unsigned)kPairXor ? 1u : 0u;   // which x-neighbour this lane fetches for its pair
 
   // ---- one-time CTA setup --------------------------------------------------------------------------
   if (warp_u == 0) tc::tmem_alloc(&s->tmem_base, 512);
