@@ -95,19 +95,27 @@ __global__ void __launch_bounds__(kThreads)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int64_t n4r = (n4 + 31) & ~(int64_t)31;   // whole warps stay in the loop (ballot below)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4r; i += stride) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t word_next = i0 < n4r ? touched[i0 >> 5] : 0u;
+  for (int64_t i = i0; i < n4r; i += stride) {
     const bool live = i < n4;
-    const uint32_t word = touched[i >> 5];
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) gv = reinterpret_cast<float4*>(g)[i];
-    const bool gnz = gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f;
+    const uint32_t word = word_next;                                        // fetched one iteration ahead, so the
+    if (i + stride < n4r) word_next = touched[(i + stride) >> 5];            // data loads below do not wait for it
     const bool was = (word >> lane) & 1u;
+    // a voxel that was touched before needs p, m, v whatever its gradient is now: issue those loads together with
+    // the gradient's instead of after it (one memory round trip per iteration instead of two)
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), mv = gv, vv = gv, pv = gv;
+    if (live) gv = reinterpret_cast<float4*>(g)[i];
+    if (live && was) {
+      mv = reinterpret_cast<float4*>(m)[i];
+      vv = reinterpret_cast<float4*>(v)[i];
+      pv = reinterpret_cast<float4*>(p)[i];
+    }
+    const bool gnz = gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f;
     const uint32_t now = __ballot_sync(0xffffffffu, was || gnz);
     if (lane == 0 && now != word) touched[i >> 5] = now;
     if (!live || !(was || gnz)) continue;
-    float4 mv = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    float4 pv = reinterpret_cast<float4*>(p)[i];
+    if (!was) pv = reinterpret_cast<float4*>(p)[i];   // first touch: m = v = 0 by construction
     float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
           va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
