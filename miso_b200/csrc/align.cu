@@ -322,6 +322,46 @@ __global__ void __launch_bounds__(kThreads)
     const int segs_per_row = (row_len + kS - 1) / kS;
     const int64_t rows = pr0.M / row_len;
     const int64_t nseg = rows * segs_per_row;
+    // Whole-lattice pre-test per destination: every vertex lies in the hull of the lattice's 8 extreme corners (first
+    // and last vertex give the per-axis extremes); if all 8 are beyond the same face of the destination bound (same
+    // margin as below) the pair's count is exactly 0 and the destination drops out of the loops.  Most pairs of a
+    // 16-submap atlas do not overlap at all.
+    __shared__ int s_act[kMaxGroup];
+    __shared__ int s_nact;
+    if (threadIdx.x < 32) {
+      const int j = threadIdx.x;
+      bool keep = false;
+      if (j < np) {
+        const float* pl = pr0.p + 3 * (pr0.M - 1);
+        unsigned common = 0x3fu;
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+          const float cp[3] = {(cidx & 1) ? pl[0] : pr0.p[0], (cidx & 2) ? pl[1] : pr0.p[1], (cidx & 4) ? pl[2] : pr0.p[2]};
+          float cu[3], cq[3], A2[9], b2[3];
+          xform(A1, b1, cp, cu);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) A2[i] = s_pose[j][12 + i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) b2[i] = s_pose[j][21 + i];
+          xform(A2, b2, cu, cq);
+          unsigned faces = 0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float lo = s_bound[j][2 * k], hi = s_bound[j][2 * k + 1], eps = s_eps[j][k];
+            faces |= (cq[k] < lo - eps ? 1u : 0u) << (2 * k);
+            faces |= (cq[k] > hi + eps ? 1u : 0u) << (2 * k + 1);
+          }
+          common &= faces;
+        }
+        keep = common == 0u;
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) s_act[__popc(km & ((1u << j) - 1u))] = j;
+      if (j == 0) s_nact = __popc(km);
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (nact == 0) return;
     // whole warps stay in the loop together (the reduction below is warp-wide): iterate on the warp's first segment
     for (int64_t sg0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); sg0 < nseg; sg0 += stride) {
       const int64_t sg = sg0 + lane;
@@ -349,7 +389,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int v = 1; v < kS; ++v) ul[i] = (v == len - 1) ? u[v][i] : ul[i];
       }
-      for (int j = 0; j < np; ++j) {
+      for (int ja = 0; ja < nact; ++ja) {
+        const int j = s_act[ja];
         float A2[9], b2[3], bd[6];
 #pragma unroll
         for (int i = 0; i < 9; ++i) A2[i] = s_pose[j][12 + i];
