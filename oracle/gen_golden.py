@@ -250,6 +250,46 @@ def gen_variants():
     np.savez_compressed(os.path.join(OUT, "variants.npz"), **out)
 
 
+def gen_tracker():
+    """Tracker.lm_step (grid_opt/slam/tracker.py:148-212) executed verbatim on CPU with a minimal stand-in for `self`
+    (the method only touches the attributes listed here): pose corrections after ONE LM step, L2 and GM, with and
+    without the |gt| < trunc filter."""
+    import types
+    import grid_opt.slam.tracker as rtr
+    out = {"bound": np.asarray(BOUND, np.float32)}
+    g = torch.Generator().manual_seed(31)
+    N = 1500
+    xf = (torch.rand(N, 3, generator=g) - 0.5) * torch.tensor([2.0, 1.0, 2.0])
+    gt_sdf = torch.randn(N, 1, generator=g) * 0.05
+    from oracle import oracle as O
+    Rwf = O.so3_exp_map(torch.tensor([[0.1, -0.2, 0.05]]))[0]
+    twf = torch.tensor([[0.1], [0.05], [-0.1]])
+    out["coords_frame"], out["gt_sdf"], out["Rwf"], out["twf"] = _np(xf), _np(gt_sdf), _np(Rwf), _np(twf)
+    mi = {"coords_frame": xf[None], "sample_frame_ids": torch.zeros(1, N, 1, dtype=torch.long), "weights": torch.ones(1, N, 1)}
+    gt = {"sdf": gt_sdf[None], "sdf_valid": torch.ones(1, N, 1, dtype=torch.bool), "sdf_signs": torch.zeros(1, N, 1)}
+    first = True
+    for loss_type in ("L2", "GM"):
+        for trunc in (None, 0.04):
+            net = make_ref_gridnet(BOUND, num_poses=1)
+            net.set_initial_kf_pose(0, Rwf, twf, kf_key="KF0")
+            if first:
+                for l in range(2):
+                    out[f"feat{l}"] = _np(net.features[l].feature)
+                for k, v in net.decoder.state_dict().items():
+                    out["dec." + k] = _np(v)
+                first = False
+            fake = types.SimpleNamespace(dataset=types.SimpleNamespace(select_keyframes=lambda kfs: None),
+                                         train_loader=[(mi, gt)], cfg={"device": "cpu"}, trunc_dist=trunc, grid=net,
+                                         loss_type=loss_type, gm_scale_sdf=0.1, lm_lambda=1e-4)
+            fake.residual_weights = types.MethodType(rtr.Tracker.residual_weights, fake)
+            info = rtr.Tracker.lm_step(fake, 0)
+            tag = f"{loss_type}.{'trunc' if trunc else 'all'}"
+            out[f"{tag}.delta_R"] = _np(net.rotation_corrections[0])
+            out[f"{tag}.delta_t"] = _np(net.translation_corrections[0])
+            out[f"{tag}.info"] = np.asarray([info["delta_R_deg"], info["delta_t_norm"], info["grad_norm"], info["fov_overlap"]])
+    np.savez_compressed(os.path.join(OUT, "tracker.npz"), **out)
+
+
 def main():
     ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -260,6 +300,7 @@ def main():
     gen_align()
     gen_align_sdf()
     gen_variants()
+    gen_tracker()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

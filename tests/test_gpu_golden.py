@@ -218,3 +218,23 @@ def test_loss_variants_and_dense_queries_against_reference_outputs():
     assert rel_err(total, want) < 1e-5
     for l in range(2):
         assert rel_err(net.features[l].feature.grad, onet.features[l].grad) < 1e-4
+
+
+@pytest.mark.parametrize("loss_type", ["L2", "GM"])
+def test_tracker_lm_step_against_reference_outputs(loss_type):
+    """Tracker.lm_step through the one-launch normal equations (miso_track_normal_equations) vs the pose update the
+    reference's own lm_step produced (tests/golden/tracker.npz).  The 6x6 solve amplifies by cond(H): 1e-3."""
+    from miso_b200.tracker import Tracker
+    z = load("tracker.npz")
+    N = z["coords_frame"].shape[0]
+    mi = {"coords_frame": T(z["coords_frame"])[None].cuda(), "sample_frame_ids": torch.zeros(1, N, 1, dtype=torch.long).cuda()}
+    gt = {"sdf": T(z["gt_sdf"])[None].cuda(), "sdf_valid": torch.ones(1, N, 1, dtype=torch.bool).cuda()}
+    for tag, trunc in (("all", None), ("trunc", 0.04)):
+        net = gpu_net(z, z, num_poses=1)
+        net.set_initial_kf_pose(0, T(z["Rwf"]), T(z["twf"]), kf_key="KF0")
+        tr = Tracker(net, loss_type=loss_type, gm_scale_sdf=0.1, lm_lambda=1e-4, trunc_dist=trunc)
+        info = tr.lm_step(0, mi, gt)
+        assert rel_err(net.rotation_corrections[0], T(z[f"{loss_type}.{tag}.delta_R"])) < 1e-3
+        assert rel_err(net.translation_corrections[0], T(z[f"{loss_type}.{tag}.delta_t"])) < 1e-3
+        ref = z[f"{loss_type}.{tag}.info"]
+        assert abs(info["grad_norm"] - ref[2]) < 1e-4 * ref[2] and abs(info["fov_overlap"] - ref[3]) < 1e-6
