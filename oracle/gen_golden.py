@@ -182,6 +182,13 @@ def gen_align_sdf():
         for i in range(2):
             out[f"{loss}.grad_rot{i}"] = _np(atlas.rotation_corrections[i].grad)
             out[f"{loss}.grad_tra{i}"] = _np(atlas.translation_corrections[i].grad)
+    # GridAtlas.query_feature / forward (grid_atlas.py:374-399) at world points around both submaps
+    for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+        p.grad = None
+    g = torch.Generator().manual_seed(17)
+    xw = (torch.rand(3000, 3, generator=g) * 2 - 1) * torch.tensor([7.0, 3.0, 6.0]) + torch.tensor([2.0, 0.0, 1.0])
+    with torch.no_grad():
+        out["atlas.xw"], out["atlas.feat"], out["atlas.sdf"] = _np(xw), _np(atlas.query_feature(xw)), _np(atlas(xw))
     np.savez_compressed(os.path.join(OUT, "align_sdf.npz"), **out)
 
 

@@ -238,3 +238,17 @@ def test_tracker_lm_step_against_reference_outputs(loss_type):
         assert rel_err(net.translation_corrections[0], T(z[f"{loss_type}.{tag}.delta_t"])) < 1e-3
         ref = z[f"{loss_type}.{tag}.info"]
         assert abs(info["grad_norm"] - ref[2]) < 1e-4 * ref[2] and abs(info["fov_overlap"] - ref[3]) < 1e-6
+
+
+def test_atlas_query_against_reference_outputs():
+    """GridAtlas.query_feature / forward (grid_atlas.py:374-399) vs the reference's outputs: the one-launch masked
+    mean over submaps (no_grad) and the per-submap torch path (autograd enabled)."""
+    z = load("align_sdf.npz")
+    atlas, _ = _sdf_atlas(z)
+    xw = T(z["atlas.xw"]).cuda()
+    with torch.no_grad():
+        feat = atlas.query_feature(xw)
+        sdf = atlas(xw)
+    assert rel_err(feat, T(z["atlas.feat"])) < 1e-5
+    assert rel_err(sdf, T(z["atlas.sdf"])) < 1e-5
+    assert rel_err(atlas.query_feature(xw.clone().requires_grad_(True)), T(z["atlas.feat"])) < 1e-5
