@@ -297,6 +297,48 @@ def gen_tracker():
     np.savez_compressed(os.path.join(OUT, "tracker.npz"), **out)
 
 
+def gen_align_loop():
+    """The whole alignment loop run by the reference: align_multiple_submaps_hierarchical (miso.py:217-322) ->
+    generic_align_multiple_submaps (base.py:89-163) with pairwise_loss_latent at levels 0 and 1, 5 iterations each
+    (`while iter <= num_iters`), Adam lr 1e-2, intersection test on, on a 3-submap atlas: final pose corrections."""
+    from grid_opt.models.grid_atlas import GridAtlas
+    import grid_opt.align.miso as amiso
+    from oracle import oracle as O
+    cfg = ref_loader.reference_model_cfg(ABOUND, base_cell_size=1.0, per_level_scale=2, num_poses=1)
+    Rt, tt = synth.submap_layout(3, spacing=(4.0, 3.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=4.0, trans_m=0.3)
+    atlas = GridAtlas(cfg, device="cpu")
+    shapes = O.level_shapes(ABOUND, 1.0, 2, 2, 4)
+    out = {"bound": np.asarray(ABOUND, np.float32)}
+    for i in range(3):
+        atlas.add_submap(torch.tensor(ABOUND), Rp[i], tp[i])
+        feats = synth.fill_submap_from_field(shapes, ABOUND, Rt[i], tt[i])
+        with torch.no_grad():
+            for l in range(2):
+                atlas.get_submap(i).features[l].feature.copy_(feats[l])
+                out[f"sm{i}.feat{l}"] = _np(feats[l])
+        out[f"sm{i}.R"], out[f"sm{i}.t"] = _np(Rp[i]), _np(tp[i])
+    # the loop's PerfTimer records CUDA events (utils.py) -- not part of the algorithm and unusable without a GPU
+    import grid_opt.align.base as rbase
+
+    class _CpuTimer:
+        def __init__(self, activate=True):
+            pass
+
+        def reset(self):
+            pass
+
+        def check(self):
+            return 0.0, 0.0
+    rbase.utils.PerfTimer = _CpuTimer
+    amiso.align_multiple_submaps_hierarchical(atlas, [0], level_iters=4, lr=1e-2, latent_levels=[0, 1], skip_finetune=True,
+                                              device="cpu", verbose=False)
+    for i in range(3):
+        out[f"final.rot{i}"] = _np(atlas.rotation_corrections[i])
+        out[f"final.tra{i}"] = _np(atlas.translation_corrections[i])
+    np.savez_compressed(os.path.join(OUT, "align_loop.npz"), **out)
+
+
 def main():
     ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -308,6 +350,7 @@ def main():
     gen_align_sdf()
     gen_variants()
     gen_tracker()
+    gen_align_loop()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

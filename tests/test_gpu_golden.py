@@ -252,3 +252,26 @@ def test_atlas_query_against_reference_outputs():
     assert rel_err(feat, T(z["atlas.feat"])) < 1e-5
     assert rel_err(sdf, T(z["atlas.sdf"])) < 1e-5
     assert rel_err(atlas.query_feature(xw.clone().requires_grad_(True)), T(z["atlas.feat"])) < 1e-5
+
+
+@pytest.mark.parametrize("fused_glue", [True, False])
+def test_alignment_loop_against_reference_outputs(fused_glue):
+    """align_multiple_submaps_hierarchical on the CUDA path (five-launch iteration with the fused pose kernels, or
+    the torch glue) vs the pose corrections the reference's own loop ended at (tests/golden/align_loop.npz)."""
+    from miso_b200 import align as A
+    from miso_b200.models import GridAtlas
+    z = load("align_loop.npz")
+    bound = z["bound"].tolist()
+    atlas = GridAtlas(synth.model_cfg(bound, base_cell_size=1.0, per_level_scale=2, num_poses=1), device="cuda")
+    for i in range(3):
+        atlas.add_submap(torch.tensor(bound), T(z[f"sm{i}.R"]), T(z[f"sm{i}.t"]))
+        with torch.no_grad():
+            for l in range(2):
+                atlas.get_submap(i).features[l].feature.copy_(T(z[f"sm{i}.feat{l}"]).cuda())
+    atlas.precompute_coordinates_for_alignment()
+    for level in (0, 1):
+        A.generic_align_multiple_submaps(atlas, None, ("latent", None), num_iters=4, lr=1e-2, level=level,
+                                         fused_pose_glue=fused_glue)
+    for i in range(3):
+        assert rel_err(atlas.rotation_corrections[i], T(z[f"final.rot{i}"])) < 1e-3, i
+        assert rel_err(atlas.translation_corrections[i], T(z[f"final.tra{i}"])) < 1e-3, i
