@@ -28,34 +28,35 @@ class TsdfLoss3D:
         self.grad_method = grad_method
         self.finite_diff_eps = finite_diff_eps
 
+    @staticmethod
+    def _hinge_where(mask, value):
+        """mean(max(0, value where mask else 0)) -- the free-space hinge of :105-127."""
+        z = torch.zeros_like(value)
+        return torch.mean(torch.maximum(z, torch.where(mask, value, z)))
+
+    def _uniform_points_in_bound(self, model, n, like):
+        # same draw order as the reference (:128-133: all x, then all y, then all z from numpy's global RNG) so a seeded
+        # RNG reproduces its points
+        b = model.bound.detach().cpu().numpy()
+        cols = [np.random.uniform(b[d, 0], b[d, 1], n).reshape(n, 1) for d in range(3)]
+        return torch.from_numpy(np.concatenate(cols, axis=1)).to(like)
+
     def compute(self, model, model_input, gt):
-        coords = model_input["coords"][0]
-        gt_sdf = gt["sdf"][0]
-        gt_sdf_valid = gt["sdf_valid"][0]
-        gt_sdf_sign = gt["sdf_sign"][0]
-        assert coords.ndim == 2 and gt_sdf.ndim == 2
-        pred_sdf = model(coords)
-        sdf_constraint = torch.where(gt_sdf_valid == 1, pred_sdf - gt_sdf, torch.zeros_like(pred_sdf))
-        loss_dict = {"sdf": torch.mean(sdf_constraint ** 2) * self.sdf_weight}
+        coords, target = model_input["coords"][0], gt["sdf"][0]
+        valid, sign = gt["sdf_valid"][0], gt["sdf_sign"][0]
+        assert coords.ndim == 2 and target.ndim == 2
+        pred = model(coords)                                             # fused grid + decoder launch
+        err = torch.where(valid == 1, pred - target, torch.zeros_like(pred))
+        terms = {"sdf": self.sdf_weight * torch.mean(err ** 2)}
         if self.sign_weight > 0:
             assert self.trunc_dist is not None
-            pos_trunc = torch.where(gt_sdf_sign == 1, self.trunc_dist - pred_sdf, torch.zeros_like(pred_sdf))
-            loss_dict["pos_space"] = torch.mean(torch.maximum(torch.zeros_like(pred_sdf), pos_trunc)) * self.sign_weight
-            neg_trunc = torch.where(gt_sdf_sign == -1, pred_sdf + self.trunc_dist, torch.zeros_like(pred_sdf))
-            loss_dict["neg_space"] = torch.mean(torch.maximum(torch.zeros_like(pred_sdf), neg_trunc)) * self.sign_weight
+            terms["pos_space"] = self.sign_weight * self._hinge_where(sign == 1, self.trunc_dist - pred)
+            terms["neg_space"] = self.sign_weight * self._hinge_where(sign == -1, pred + self.trunc_dist)
         if self.eik_weight > 0:
-            # same draw order as the reference (:128-133) so a seeded numpy RNG gives identical points
-            N = gt_sdf.shape[0]
-            bound = model.bound.detach().cpu().numpy()
-            xs = np.reshape(np.random.uniform(bound[0, 0], bound[0, 1], N), (N, 1))
-            ys = np.reshape(np.random.uniform(bound[1, 0], bound[1, 1], N), (N, 1))
-            zs = np.reshape(np.random.uniform(bound[2, 0], bound[2, 1], N), (N, 1))
-            x = torch.from_numpy(np.concatenate([xs, ys, zs], axis=1)).to(gt_sdf)
-            x.requires_grad_(True)
-            gradient = gradient3d(x, model, method=self.grad_method, finite_diff_eps=self.finite_diff_eps,
-                                  create_graph=True)
-            loss_dict["eik"] = torch.mean((gradient.norm(dim=-1) - 1) ** 2) * self.eik_weight
-        return loss_dict
+            x = self._uniform_points_in_bound(model, target.shape[0], target).requires_grad_(True)
+            g = gradient3d(x, model, method=self.grad_method, finite_diff_eps=self.finite_diff_eps, create_graph=True)
+            terms["eik"] = self.eik_weight * torch.mean((g.norm(dim=-1) - 1) ** 2)
+        return terms
 
 
 def full_sdf_loss(sdf, target_sdf, free_space_factor=5.0):
