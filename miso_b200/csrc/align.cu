@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads)
     // The margin (1e-3 + 1e-5 |bound|) is two orders above the rounding error of the two chained transforms, so the
     // count is the exact per-vertex count; ~85 % of the segments of two overlapping room-sized submaps are decided
     // by their end points alone.
-    constexpr int kS = 8;
+    constexpr int kS = 16;
     const int segs_per_row = (row_len + kS - 1) / kS;
     const int64_t rows = pr0.M / row_len;
     const int64_t nseg = rows * segs_per_row;
