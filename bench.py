@@ -17,6 +17,7 @@ N GPUs = N independent submaps (weak scaling, no data-path collective; SURVEY.md
             Python and /root/reference is absent on the GPU box) on a bounded sample, all host cores.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -229,11 +230,14 @@ def run_ours(args):
 
     e2e_loop(args.warmup, 0)
     barrier()
+    gc.collect()
+    gc.disable()   # the e2e loops are paced by the host thread: keep collector pauses out of the timed region
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     e2e_loop(args.steps, args.warmup)
     t1.record()
     barrier()
+    gc.enable()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the e2e run"
     e2e_loss_ref_format = loss_host[args.warmup + args.steps - 1].clone()
@@ -249,11 +253,14 @@ def run_ours(args):
 
     e2e_compact_loop(args.warmup, 0)
     barrier()
+    gc.collect()
+    gc.disable()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     e2e_compact_loop(args.steps, args.warmup)
     c1.record()
     barrier()
+    gc.enable()
     e2e_compact_ms = max_over_ranks(c0.elapsed_time(c1))
     clocks = sampler.stop() if sampler else None   # sampled across all timed regions (value + e2e + e2e_compact)
     assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the compact e2e run"
