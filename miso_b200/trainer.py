@@ -56,10 +56,36 @@ class CompactBatch:
                              "trunc_dist; ship the reference format instead")
         w = model_input["weights"][0, :, 0].contiguous().float()
         w = None if bool((w == 1).all()) else w
-        out = [coords, ids.to(torch.int16).contiguous(), sdf, w]
+        # one contiguous host buffer [coords | sdf | weights? | ids16] so a batch is ONE host->device copy; the typed
+        # tensors below are views into it
+        N = coords.shape[0]
+        nbytes = 12 * N + 4 * N + (4 * N if w is not None else 0) + 2 * N
+        buf = torch.empty(nbytes, dtype=torch.uint8)
         if pin:
-            out = [t.pin_memory() if t is not None else None for t in out]
-        return CompactBatch(*out, trunc_dist)
+            buf = buf.pin_memory()
+        views = CompactBatch.views_of(buf, N, w is not None)
+        views["coords"].copy_(coords)
+        views["sdf"].copy_(sdf)
+        views["ids16"].copy_(ids.to(torch.int16))
+        if w is not None:
+            views["weights"].copy_(w)
+        cb = CompactBatch(views["coords"], views["ids16"], views["sdf"], views.get("weights"), trunc_dist)
+        cb.buffer = buf
+        return cb
+
+    @staticmethod
+    def views_of(buf: torch.Tensor, N: int, has_weights: bool) -> Dict[str, torch.Tensor]:
+        """Typed views into a packed [coords | sdf | weights? | ids16] byte buffer (host or device)."""
+        o = 0
+        out = {"coords": buf[o:o + 12 * N].view(torch.float32).view(N, 3)}
+        o += 12 * N
+        out["sdf"] = buf[o:o + 4 * N].view(torch.float32)
+        o += 4 * N
+        if has_weights:
+            out["weights"] = buf[o:o + 4 * N].view(torch.float32)
+            o += 4 * N
+        out["ids16"] = buf[o:o + 2 * N].view(torch.int16)
+        return out
 
     def tensors(self):
         d = {"coords": self.coords, "ids16": self.ids16, "sdf": self.sdf}
@@ -114,7 +140,7 @@ class HostBatchStager:
     def _buffers(self, slot, batch):
         bufs = self.slots[slot]
         if isinstance(batch, CompactBatch):
-            batch = (batch.tensors(), {})
+            batch = ({"packed": batch.buffer} if getattr(batch, "buffer", None) is not None else batch.tensors(), {})
         model_input, gt = batch
         ok = bufs is not None and all(k in bufs[0] and bufs[0][k].shape == v.shape and bufs[0][k].dtype == v.dtype
                                       for k, v in model_input.items()) and \
@@ -130,9 +156,10 @@ class HostBatchStager:
         slot = self._next
         self._next = (self._next + 1) % len(self.slots)
         bufs = self._buffers(slot, batch)
-        self.compact[slot] = batch.trunc_dist if isinstance(batch, CompactBatch) else None
+        self.compact[slot] = (batch.trunc_dist, batch.coords.shape[0], batch.weights is not None) \
+            if isinstance(batch, CompactBatch) else None
         if isinstance(batch, CompactBatch):
-            batch = (batch.tensors(), {})
+            batch = ({"packed": batch.buffer} if getattr(batch, "buffer", None) is not None else batch.tensors(), {})
         nbytes = 0
         with torch.cuda.stream(self.stream):
             if self.free[slot] is not None:
@@ -150,7 +177,11 @@ class HostBatchStager:
     def acquire(self, slot: int) -> Batch:
         torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
         if self.compact[slot] is not None:
-            return expand_compact_on_device(self.slots[slot][0], self.compact[slot], self._expand_cache[slot])
+            trunc, n, has_w = self.compact[slot]
+            dev = self.slots[slot][0]
+            if "packed" in dev:
+                dev = CompactBatch.views_of(dev["packed"], n, has_w)
+            return expand_compact_on_device(dev, trunc, self._expand_cache[slot])
         return self.slots[slot]
 
     def release(self, slot: int):
