@@ -278,6 +278,15 @@ int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, 
 int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr, float beta1,
                            float beta2, float eps, int32_t step, int32_t zero_grad, miso_stream_t stream);
 
+/* Kernel-variant switches of the fused step (tests / profiling; defaults come from the MISO_* environment
+ * variables): keys "mlp_tc" (1 tcgen05 decoder | 0 SIMT), "tc2_groups" (4 | 3 tiles in flight of the
+ * two-threads-per-point kernel, 0 = one-thread kernel), "pair" (lane-paired gather/scatter), "fwd_tc2", "dbg"
+ * (ablation bits), "force_int64" (take the 64-bit-offset route the reference selects at
+ * third_party/cuda_gridsample_grad2/gridsample_cuda.cu:628-660 for any grid).  Process-global, not thread-safe
+ * against concurrent launches.  miso_get_tuning returns the value or -1 for an unknown key. */
+int miso_set_tuning(const char* key, int32_t value);
+int miso_get_tuning(const char* key);
+
 /* ------------------------------------------------------------------------------------------
  * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the
  *    3xTF32 split, activations in TMEM, weights in shared memory): D (M,64) = A (M,64) * W^T

@@ -95,6 +95,8 @@ _SIGNATURES = {
     "miso_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "miso_adam_step_tracked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                          C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    "miso_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
+    "miso_get_tuning": (C.c_int, [C.c_char_p]),
     "miso_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -136,6 +138,29 @@ def check(rc: int, what: str = ""):
         msg = load().miso_last_error_string().decode("utf-8", "replace")
         raise RuntimeError(f"miso_b200 {what} failed ({rc}): {msg}")
     LAUNCHES["total"] += KERNELS_PER_CALL.get(what, 1)
+
+
+class tuning:
+    """Context manager over miso_set_tuning: `with _lib.tuning(tc2_groups=3, pair=0): ...` (tests / profiling)."""
+
+    def __init__(self, **kv):
+        self.kv = kv
+        self.old = {}
+
+    def __enter__(self):
+        lib = load()
+        for k, v in self.kv.items():
+            self.old[k] = lib.miso_get_tuning(k.encode())
+            rc = lib.miso_set_tuning(k.encode(), int(v))
+            if rc != 0:
+                raise RuntimeError(lib.miso_last_error_string().decode())
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        for k, v in self.old.items():
+            lib.miso_set_tuning(k.encode(), int(v))
+        return False
 
 
 def stream_ptr(device=None) -> int:

@@ -1386,8 +1386,39 @@ static int blocks_for(K kernel, size_t smem, int64_t N) {
     }                                                                              \
   } while (0)
 
+// Kernel-variant switches.  Defaults come from the environment once (MISO_MLP=simt, MISO_TC=1, MISO_TC2_GROUPS=3,
+// MISO_PAIR=0, MISO_FWD_TC2=1, MISO_DBG=<bits>); miso_set_tuning() overrides them at run time so the parity tests can
+// walk every variant inside one process.
+struct Tuning {
+  int mlp_tc;       // 1: tcgen05 decoder (default), 0: FP32 SIMT decoder
+  int tc2_groups;   // 0: one-thread-per-point tensor-core kernel, 3 | 4: two-threads-per-point kernel, tiles in flight
+  int pair;         // 1: lane-paired gather / scatter (default)
+  int fwd_tc2;      // 1: two-thread kernel also for value-only forwards
+  int dbg;          // ablation bits (profiling only): 1 = no reductions, 2 = no corner loads
+  int force_int64;  // 1: treat every field as not 32-bit addressable (exercises the SIMT / 64-bit-offset route)
+};
+static Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning d;
+    const char* e = getenv("MISO_MLP");
+    d.mlp_tc = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+    e = getenv("MISO_TC");
+    const char* g = getenv("MISO_TC2_GROUPS");
+    d.tc2_groups = (e && e[0] == '1') ? 0 : ((g && g[0] == '3') ? 3 : 4);
+    e = getenv("MISO_PAIR");
+    d.pair = (e && e[0] == '0') ? 0 : 1;
+    e = getenv("MISO_FWD_TC2");
+    d.fwd_tc2 = (e && e[0] == '1') ? 1 : 0;
+    e = getenv("MISO_DBG");
+    d.dbg = e ? atoi(e) : 0;
+    d.force_int64 = 0;
+    return d;
+  }();
+  return t;
+}
 // MISO_MLP=simt forces the FP32 SIMT decoder; default is the tcgen05 (3xTF32) decoder
 static bool fits_int32(const miso_field_t* f) {
+  if (tuning().force_int64) return false;
   for (int l = 0; l < f->num_levels; ++l) {
     const miso_level_t& lv = f->level[l];
     const int64_t span = (int64_t)(lv.Z + 2) * lv.sZ + (int64_t)(lv.Y + 2) * lv.sY + (int64_t)(lv.X + 2) * lv.sX;
@@ -1396,29 +1427,8 @@ static bool fits_int32(const miso_field_t* f) {
   return true;
 }
 
-static bool use_tensor_cores() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MISO_MLP");
-    cached = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
-  }
-  return cached == 1;
-}
-
-// MISO_TC=1 keeps the one-thread-per-point tensor-core kernel; default is the two-threads-per-point kernel
-// with MISO_TC2_GROUPS (3 or 4, default 4) tiles in flight per SM
-static int tc2_groups() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MISO_TC");
-    if (e && e[0] == '1') cached = 0;
-    else {
-      const char* g = getenv("MISO_TC2_GROUPS");
-      cached = (g && g[0] == '3') ? 3 : 4;
-    }
-  }
-  return cached;
-}
+static bool use_tensor_cores() { return tuning().mlp_tc == 1; }
+static int tc2_groups() { return tuning().tc2_groups; }
 
 #define MISO_DISPATCH_LC_TC2(L_, C_, ...)                                          \
   do {                                                                             \
@@ -1433,14 +1443,7 @@ static int tc2_groups() {
     }                                                                              \
   } while (0)
 
-static bool tc2_paired() {   // MISO_PAIR=0 keeps one corner per lane (profiling comparison)
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("MISO_PAIR");
-    cached = (e && e[0] == '0') ? 0 : 1;
-  }
-  return cached == 1;
-}
+static bool tc2_paired() { return tuning().pair == 1; }
 
 template <int L, int C, int G>
 static int launch_tc2(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t& fr, const MapArgs& m,
@@ -1522,7 +1525,7 @@ extern "C" int miso_sdf_forward(const miso_field_t* field, const miso_decoder_t*
   // with Jacobian / grad_x outputs the two-threads-per-point kernel is faster (0.17 vs 0.20 ms per 2^20 points);
   // values only: the one-thread kernel wins on lattice-ordered dense queries (0.73 vs 0.80 ms per 2^23), so mode 2
   // is only taken when MISO_FWD_TC2=1 asks for it
-  static const bool fwd_tc2 = getenv("MISO_FWD_TC2") && getenv("MISO_FWD_TC2")[0] == '1';
+  const bool fwd_tc2 = tuning().fwd_tc2 == 1;
   if (use_tensor_cores() && N >= 4096 && tc2_groups() != 0 && F_ % 8 == 0 && fits_int32(field) &&
       N < ((int64_t)1 << 31) - ((int64_t)1 << 26) && (want_jac || fwd_tc2)) {
     MapArgs m;
@@ -1598,6 +1601,32 @@ extern "C" int miso_sdf_backward(const miso_field_t* field, const float* xw, int
   return check_launch("sdf_backward");
 }
 
+extern "C" int miso_set_tuning(const char* key, int32_t value) {
+  MISO_REQUIRE(key, "set_tuning: null key");
+  Tuning& t = tuning();
+  if (!strcmp(key, "mlp_tc")) t.mlp_tc = value ? 1 : 0;
+  else if (!strcmp(key, "tc2_groups")) {
+    MISO_REQUIRE(value == 0 || value == 3 || value == 4, "set_tuning: tc2_groups must be 0, 3 or 4");
+    t.tc2_groups = value;
+  } else if (!strcmp(key, "pair")) t.pair = value ? 1 : 0;
+  else if (!strcmp(key, "fwd_tc2")) t.fwd_tc2 = value ? 1 : 0;
+  else if (!strcmp(key, "dbg")) t.dbg = value;
+  else if (!strcmp(key, "force_int64")) t.force_int64 = value ? 1 : 0;
+  else MISO_REQUIRE(false, "set_tuning: unknown key '%s'", key);
+  return MISO_OK;
+}
+extern "C" int miso_get_tuning(const char* key) {
+  if (!key) return -1;
+  const Tuning& t = tuning();
+  if (!strcmp(key, "mlp_tc")) return t.mlp_tc;
+  if (!strcmp(key, "tc2_groups")) return t.tc2_groups;
+  if (!strcmp(key, "pair")) return t.pair;
+  if (!strcmp(key, "fwd_tc2")) return t.fwd_tc2;
+  if (!strcmp(key, "dbg")) return t.dbg;
+  if (!strcmp(key, "force_int64")) return t.force_int64;
+  return -1;
+}
+
 extern "C" int64_t miso_mapping_workspace_floats(void) { return (int64_t)sm_count() * 8 * 4; }
 
 extern "C" int miso_mapping_count(const float* gt_sdf, int64_t N, float eik_trunc_dist, int32_t* eik_count,
@@ -1630,14 +1659,7 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
   m.jac = nullptr, m.gradx = nullptr, m.xw = nullptr;
   fill_scales(field, m);
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("MISO_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    m.dbg = dbg;
-  }
+  m.dbg = tuning().dbg;
   int nblocks = 0;
   const int F_ = field->num_levels * field->level[0].C;
   if (use_tensor_cores() && fits_int32(field) && tc2_groups() != 0 && F_ % 8 == 0 && N < ((int64_t)1 << 31) - ((int64_t)1 << 26)) {

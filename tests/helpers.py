@@ -51,3 +51,33 @@ def points_in(bound, n, seed=0, scale=1.1):
     c = (b[:, 0] + b[:, 1]) / 2
     h = (b[:, 1] - b[:, 0]) / 2
     return (torch.rand(n, 3, generator=g) * 2 - 1) * h * scale + c
+
+
+def oracle_mapping_chunked(omodel, mi, gt, poses, loss_type, w_sdf, w_eik, w_fs, trunc, eik_trunc=None,
+                           grad_method="autograd", chunk=1 << 18):
+    """O.mapping_loss evaluated on consecutive chunks of a big batch.  Every term of loss.py:754-813 is a mean
+    over the batch (the eikonal one over the |gt| < eik_trunc subset), so the full-batch value is the
+    count-weighted sum of the chunk values and the full-batch gradient the same weighted sum of the chunk
+    gradients -- accumulated into `omodel.features[l].grad` by backward().  Keeps the gather oracle's
+    intermediates (8 corners x N x C per level, twice for the double backward) at a few hundred MB.
+    Returns {term: python float (weighted, like the dict the reference returns)}."""
+    N = mi["coords_frame"].shape[1]
+    R, t = poses
+    kf = {k: (R[k], t[k]) for k in range(R.shape[0])}
+    n_eik_total = N if eik_trunc is None else int((gt["sdf"][0].abs() < eik_trunc).sum())
+    tot = {}
+    for b in range(0, N, chunk):
+        e = min(N, b + chunk)
+        cmi = {k: v[:, b:e] for k, v in mi.items()}
+        cgt = {k: v[:, b:e] for k, v in gt.items()}
+        n_eik = (e - b) if eik_trunc is None else int((cgt["sdf"][0].abs() < eik_trunc).sum())
+        use_eik = w_eik if n_eik > 0 else 0.0
+        lo = O.mapping_loss(omodel, cmi, cgt, kf, loss_type, w_sdf, use_eik, w_fs, trunc, grad_method=grad_method,
+                            eik_trunc_dist=eik_trunc)
+        total = 0
+        for k, v in lo.items():
+            wgt = (n_eik / max(n_eik_total, 1)) if k == "eik" else (e - b) / N
+            total = total + v * wgt
+            tot[k] = tot.get(k, 0.0) + float(v.detach()) * wgt
+        total.backward()
+    return tot

@@ -1,0 +1,153 @@
+"""GPU parity of the fused mapping step AT BASELINE.json SIZES: the persistent
+multi-tile loop of the headline kernel (`mapping_step_tc2_kernel`: 148 CTAs x 4 groups, so 2^18 points are
+already 3-4 tiles per group and 2^20 points 14), its one-tile-ahead point staging and TMEM / A_lo reuse are
+value-checked against the oracle, not only run for finite losses.
+
+  * configs[0]/[1]: 2^18 and 2^20 RGB-D-sampled points on the ScanNet-submap grid (40x20x40 + 200x100x200),
+    L1 sdf + 0.1 free space + 0.5 second-order eikonal (scannet.yaml:43-49 with grad_method autograd);
+  * configs[3]: 2^22 LiDAR-sampled points on the Newer-College-quad grid (20x90x90 + 100x450x450, 324 MB fine
+    level), L2 sdf + 0.5 free space, trunc 0.5 (ncd_quad.yaml:42-46), plus the eikonal term;
+  * a grid with >= 2^31 elements (the 64-bit-offset route, gridsample_cuda.cu:628-660) against the oracle on the
+    crop of the grid the points touch (trilinear interpolation is local);
+  * every kernel variant (3 tiles in flight, unpaired lanes, one thread per point, SIMT decoder, forced 64-bit
+    offsets) on a multi-tile batch.
+
+Tolerances (BASELINE.json north_star): loss terms 1e-5 relative, grid gradients 1e-4 relative.
+The oracle runs chunked (tests/helpers.py::oracle_mapping_chunked); every chunk is the reference's op sequence."""
+import pytest
+import torch
+
+from helpers import make_pair, oracle_mapping_chunked, rel_err
+from miso_b200 import _lib, synth
+from miso_b200.loss import MisoLossMapping
+
+pytestmark = pytest.mark.gpu
+
+TOL_TERM = 1e-5
+TOL_GRAD = 1e-4
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def _run_fused(net, mi, gt, poses, loss_type, w_eik, w_fs, trunc, eik_trunc):
+    R, t = poses
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    for f in net.level_tensors():
+        f.grad = None
+    L = MisoLossMapping(loss_type=loss_type, weight_sdf=1.0, weight_eik=w_eik, weight_fs=w_fs, trunc_dist=trunc,
+                        grad_method="autograd", eik_trunc_dist=eik_trunc)
+    ld = L.compute(net, _cuda(mi), _cuda(gt))
+    sum(v.mean() for v in ld.values()).backward()
+    torch.cuda.synchronize()
+    return {k: float(v) for k, v in ld.items()}
+
+
+def _check(net, o2, got, want, n_levels=2):
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= TOL_TERM * max(abs(want[k]), 1e-12), (k, got[k], want[k])
+    for l in range(n_levels):
+        e = rel_err(net.features[l].feature.grad, o2.features[l].grad)
+        assert e < TOL_GRAD, ("grid grad level", l, e)
+
+
+@pytest.mark.parametrize("log2n", [18, 20])
+def test_mapping_step_scannet_grid_full_batches(log2n):
+    """BASELINE configs[0] (2^18) and configs[1] (2^20 points / iteration) on the ScanNet-submap grid."""
+    bound = synth.SCANNET_SUBMAP_BOUND
+    N = 1 << log2n
+    net, _, o2 = make_pair(bound=bound, base_cell=0.5, scale=5, std=1e-2, seed=3, num_poses=49)
+    mi, gt, poses = synth.rgbd_batch(N, num_kf=49, bound=bound, seed=55)
+    assert _lib.load().miso_get_tuning(b"tc2_groups") == 4 and N // 128 > 3 * 148 * 4   # several tiles per group
+    got = _run_fused(net, mi, gt, poses, "L1", 0.5, 0.1, 0.15, None)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L1", 1.0, 0.5, 0.1, 0.15, None)
+    _check(net, o2, got, want)
+
+
+def test_mapping_step_scannet_grid_eik_filter_and_ragged_tail():
+    """2^18 + 77 points (last tile ragged, last group idle) with the |gt| < eik_trunc filter and L2."""
+    bound = synth.SCANNET_SUBMAP_BOUND
+    N = (1 << 18) + 77
+    net, _, o2 = make_pair(bound=bound, base_cell=0.5, scale=5, std=1e-2, seed=4, num_poses=49)
+    mi, gt, poses = synth.rgbd_batch(N, num_kf=49, bound=bound, seed=7)
+    got = _run_fused(net, mi, gt, poses, "L2", 0.5, 0.5, 0.15, 0.1)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L2", 1.0, 0.5, 0.5, 0.15, 0.1)
+    _check(net, o2, got, want)
+
+
+def test_mapping_step_ncd_quad_grid_2p22_lidar():
+    """BASELINE configs[3]: 2^22 LiDAR points on the NCD quad grid (fine level 324 MB, not L2 resident)."""
+    bound = synth.NCD_QUAD_BOUND
+    N = 1 << 22
+    net, _, o2 = make_pair(bound=bound, base_cell=1.0, scale=5, std=1e-2, seed=5, num_poses=8)
+    assert tuple(net.features[1].feature.shape) == (1, 4, 100, 450, 450)
+    mi, gt, poses = synth.lidar_batch(N, num_kf=8, seed=3)
+    got = _run_fused(net, mi, gt, poses, "L2", 0.5, 0.5, 0.5, None)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L2", 1.0, 0.5, 0.5, 0.5, None, chunk=1 << 19)
+    _check(net, o2, got, want)
+
+
+VARIANTS = [dict(tc2_groups=3), dict(pair=0), dict(tc2_groups=0), dict(mlp_tc=0), dict(force_int64=1),
+            dict(tc2_groups=3, pair=0)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()))
+def test_mapping_step_kernel_variants_multi_tile(variant):
+    """MISO_TC2_GROUPS=3 / MISO_PAIR=0 / MISO_TC=1 / MISO_MLP=simt / forced 64-bit offsets at 2^18 points."""
+    bound = synth.SCANNET_SUBMAP_BOUND
+    N = 1 << 18
+    net, _, o2 = make_pair(bound=bound, base_cell=0.5, scale=5, std=1e-2, seed=3, num_poses=49)
+    mi, gt, poses = synth.rgbd_batch(N, num_kf=49, bound=bound, seed=55)
+    with _lib.tuning(**variant):
+        got = _run_fused(net, mi, gt, poses, "L1", 0.5, 0.1, 0.15, None)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L1", 1.0, 0.5, 0.1, 0.15, None)
+    _check(net, o2, got, want)
+
+
+def test_mapping_step_grid_beyond_int32_offsets():
+    """A fine level of 2^29 voxels x 4 channels = 2^31 elements (8.6 GB): `fits_int32` is false, element offsets
+    of the touched corners exceed 2^31.  The oracle sees the z-crop [Z-40, Z) of both levels that the points
+    (z in the top 30 coarse cells... of the bound) touch; outside that crop the product's gradient must be exactly zero."""
+    from miso_b200.models import GridNet
+    X, Y, Z = 512, 1024, 1024                      # fine level; coarse level = /4
+    bound = [[0.0, 512.0], [0.0, 1024.0], [0.0, 1024.0]]
+    cfg = synth.model_cfg(bound, base_cell_size=4.0, per_level_scale=4, num_poses=1)
+    net = GridNet(cfg, device="cuda")
+    assert tuple(net.features[1].feature.shape) == (1, 4, Z, Y, X)
+    assert net.features[1].feature.numel() >= 2 ** 31
+    zc_f, zc_c = 64, 16                            # crop depth in fine / coarse voxels: z in [960, 1024)
+    g = torch.Generator().manual_seed(0)
+    crops = [torch.randn(1, 4, zc_c, Y // 4, X // 4, generator=g) * 1e-2, torch.randn(1, 4, zc_f, Y, X, generator=g) * 1e-2]
+    with torch.no_grad():
+        net.features[0].feature[:, :, Z // 4 - zc_c:].copy_(crops[0].cuda())
+        net.features[1].feature[:, :, Z - zc_f:].copy_(crops[1].cuda())
+    sd = synth.decoder_weights(8, seed=0)
+    net.decoder.load_state_dict(sd)
+    from oracle import oracle as O
+    dec = O.make_decoder(8)
+    dec.load_state_dict({k.replace("network.", ""): v for k, v in sd.items()})
+    crop_bound = [[0.0, 512.0], [0.0, 1024.0], [960.0, 1024.0]]
+    o2 = O.OracleGridNet(crop_bound, crops, dec, second_order=True)
+    # points: x,y anywhere (some outside), z in [970, 1030] so every touched corner lies in the crop or above the grid
+    N = 50000
+    x = torch.rand(N, 3, generator=g) * torch.tensor([540.0, 1060.0, 60.0]) + torch.tensor([-14.0, -18.0, 970.0])
+    sdf = torch.randn(N, 1, generator=g) * 0.2
+    mi = {"coords_frame": x[None], "sample_frame_ids": torch.zeros(1, N, 1, dtype=torch.long),
+          "weights": torch.rand(1, N, 1, generator=g) + 0.5}
+    gt = {"sdf": sdf[None], "sdf_valid": (sdf.abs() < 0.15)[None], "sdf_signs": torch.sign(sdf)[None] * (sdf.abs() >= 0.15)[None]}
+    poses = (torch.eye(3)[None], torch.zeros(1, 3, 1))
+    got = _run_fused(net, mi, gt, poses, "L1", 0.5, 0.1, 0.15, None)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L1", 1.0, 0.5, 0.1, 0.15, None)
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= TOL_TERM * max(abs(want[k]), 1e-12), (k, got[k], want[k])
+    gf = net.features[1].feature.grad
+    gc = net.features[0].feature.grad
+    assert rel_err(gf[:, :, Z - zc_f:], o2.features[1].grad) < TOL_GRAD
+    assert rel_err(gc[:, :, Z // 4 - zc_c:], o2.features[0].grad) < TOL_GRAD
+    assert torch.count_nonzero(gf[:, :, :Z - zc_f]) == 0 and torch.count_nonzero(gc[:, :, :Z // 4 - zc_c]) == 0
