@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <cmath>
+#include <string.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -43,10 +44,11 @@ __device__ __forceinline__ void red_add_f4_if(bool ok, float* addr, float a, flo
                ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((unsigned)ok) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_red(float* grid, Dim d, int N, int mode, int levels_red) {
+__global__ void __launch_bounds__(256) k_red(float* grid, Dim d, int N, int mode, int levels_red, int clamp_in = 0) {
   for (int n = blockIdx.x * 256 + threadIdx.x; n < N; n += gridDim.x * 256) {
     int ix, iy, iz;
     cell_of(n, mode, d, ix, iy, iz);
+    if (clamp_in) { ix = max(0, min(d.X - 2, ix)); iy = max(0, min(d.Y - 2, iy)); iz = max(0, min(d.Z - 2, iz)); }
     const float v = 1.0f + (n & 7);
     for (int rep = 0; rep < levels_red; ++rep) {
 #pragma unroll
@@ -154,10 +156,99 @@ static float time_ms(F f, int reps) {
   return ms / reps;
 }
 
+// elected-lane variant: one lane per warp issues the TMA ops of all 32 lanes (explicit uniform issue)
+template <int NSLOT>
+__global__ void __launch_bounds__(256) k_tma_elect(const __grid_constant__ CUtensorMap tmap, Dim d, int N, int mode, int clamp_in,
+                                                   float* red_grid = nullptr, int tma_levels = 1) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* slots = reinterpret_cast<float4*>(smem) + (size_t)threadIdx.x * NSLOT * 8;
+  const int lane = threadIdx.x & 31;
+  int it = 0;
+  for (int n0 = blockIdx.x * 256 + (threadIdx.x & ~31); n0 < N; n0 += gridDim.x * 256, ++it) {
+    const int n = n0 + lane;
+    int ix, iy, iz;
+    cell_of(n, mode, d, ix, iy, iz);
+    if (clamp_in) { ix = max(0, min(d.X - 2, ix)); iy = max(0, min(d.Y - 2, iy)); iz = max(0, min(d.Z - 2, iz)); }
+    const float v = 1.0f + (n & 7);
+    float4* s = slots + (it % NSLOT) * 8;
+    if (it >= NSLOT && lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSLOT - 1) : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = make_float4(v * (k + 1), v, -v, 0.5f * v);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s);
+    for (int l = 0; l < 32; ++l) {
+      const int cx = __shfl_sync(0xffffffffu, ix, l), cy = __shfl_sync(0xffffffffu, iy, l), cz = __shfl_sync(0xffffffffu, iz, l);
+      const uint32_t sa = __shfl_sync(0xffffffffu, saddr, l);
+      if (lane == 0 && n0 + l < N)
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                     ::"l"(&tmap), "r"(cx * 4), "r"(cy), "r"(cz), "r"(sa) : "memory");
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (red_grid != nullptr && n < N) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = ix + (k & 1), y = iy + ((k >> 1) & 1), z = iz + (k >> 2);
+        const bool ok = x >= 0 && x < d.X && y >= 0 && y < d.Y && z >= 0 && z < d.Z;
+        float* p = red_grid + (ok ? (((size_t)z * d.Y + y) * d.X + x) * 4 : 0);
+        red_add_f4_if(ok, p, v * (k + 1), v, -v, 0.5f * v);
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void k_one(const __grid_constant__ CUtensorMap tmap, int ix, int iy, int iz) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* s = reinterpret_cast<float4*>(smem);
+  if (threadIdx.x < 8) s[threadIdx.x] = make_float4(1.f, 2.f, 3.f, 4.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s);
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(&tmap), "r"(ix * 4), "r"(iy), "r"(iz), "r"(sa) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+static void report(const char* what, cudaError_t e) { printf("{\"step\": \"%s\", \"status\": \"%s\"}\n", what, cudaGetErrorString(e)); fflush(stdout); }
+
 int main(int argc, char** argv) {
+  const char* which = argc > 1 ? argv[1] : "all";
   const int N = 1 << 20;
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  constexpr int NS = 2;
+  const size_t smem = 256 * NS * 128;
+  CK(cudaFuncSetAttribute(k_tma<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_tma_elect<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_bulk<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (strcmp(which, "all") != 0) {
+    // diagnostics: one kernel per process so a sticky error names its culprit
+    Dim d = {200, 100, 200};
+    const size_t n = (size_t)d.X * d.Y * d.Z * 4;
+    float* g;
+    CK(cudaMalloc(&g, n * 4)); CK(cudaMemset(g, 0, n * 4));
+    CUtensorMap tm = make_map(g, d);
+    if (!strcmp(which, "red")) k_red<<<sms * 4, 256>>>(g, d, N, 0, 1);
+    else if (!strcmp(which, "tma")) k_tma<NS><<<sms, 256, smem>>>(tm, g, d, N, 0, 1, 0);
+    else if (!strcmp(which, "tma_elect")) k_tma_elect<NS><<<sms, 256, smem>>>(tm, d, N, 0, 0);
+    else if (!strcmp(which, "tma_elect_in")) k_tma_elect<NS><<<sms, 256, smem>>>(tm, d, N, 0, 1);
+    else if (!strcmp(which, "bulk")) k_bulk<NS><<<sms, 256, smem>>>(g, d, N, 0);
+    else if (!strncmp(which, "oob", 3)) {
+      // one op with a hand-picked coordinate: oob_x-  oob_x+  oob_y-  oob_y+  oob_z-  oob_z+
+      int c[3] = {5, 5, 5};
+      const int ax = which[4] - 'x';
+      const int ext[3] = {d.X, d.Y, d.Z};
+      c[ax] = which[5] == '-' ? -1 : ext[ax] - 1;
+      k_one<<<1, 32, 128>>>(tm, c[0], c[1], c[2]);
+    }
+    report(which, cudaDeviceSynchronize());
+    return 0;
+  }
   printf("{\"sms\": %d, \"N\": %d, \"results\": [\n", sms, N);
   Dim dims[2] = {{200, 100, 200}, {40, 20, 40}};
   bool first = true;
@@ -167,15 +258,11 @@ int main(int argc, char** argv) {
     float *g0, *g1;
     CK(cudaMalloc(&g0, n * 4)); CK(cudaMalloc(&g1, n * 4));
     CUtensorMap tm = make_map(g1, d);
-    constexpr int NS = 2;
-    const size_t smem = 256 * NS * 128;
-    CK(cudaFuncSetAttribute(k_tma<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_bulk<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int mode = 0; mode < 2; ++mode) {
       // correctness: one pass each, compare
       CK(cudaMemset(g0, 0, n * 4)); CK(cudaMemset(g1, 0, n * 4));
-      k_red<<<sms * 4, 256>>>(g0, d, N, mode, 1);
-      k_tma<NS><<<sms * 3, 256, smem>>>(tm, g1, d, N, mode, 1, 0);
+      k_red<<<sms * 4, 256>>>(g0, d, N, mode, 1, 1);
+      k_tma_elect<NS><<<sms * 3, 256, smem>>>(tm, d, N, mode, 1);
       CK(cudaDeviceSynchronize());
       std::vector<float> h0(n), h1(n);
       CK(cudaMemcpy(h0.data(), g0, n * 4, cudaMemcpyDeviceToHost));
@@ -184,17 +271,14 @@ int main(int argc, char** argv) {
       for (size_t i = 0; i < n; ++i) { maxd = fmax(maxd, fabs((double)h0[i] - h1[i])); sum += fabs(h0[i]); }
       for (int blocks_per_sm = 1; blocks_per_sm <= 3; blocks_per_sm += 2) {
         const int nb = sms * blocks_per_sm;
-        float t_red1 = time_ms([&] { k_red<<<sms * 4, 256>>>(g0, d, N, mode, 1); }, 20);
-        float t_red2 = time_ms([&] { k_red<<<sms * 4, 256>>>(g0, d, N, mode, 2); }, 20);
-        float t_tma1 = time_ms([&] { k_tma<NS><<<nb, 256, smem>>>(tm, g1, d, N, mode, 1, 0); }, 20);
-        float t_tma2 = time_ms([&] { k_tma<NS><<<nb, 256, smem>>>(tm, g1, d, N, mode, 2, 0); }, 20);
-        float t_mix = time_ms([&] { k_tma<NS><<<nb, 256, smem>>>(tm, g1, d, N, mode, 1, 1); }, 20);
+        float t_red1 = time_ms([&] { k_red<<<sms * 4, 256>>>(g0, d, N, mode, 1, 1); }, 20);
+        float t_red2 = time_ms([&] { k_red<<<sms * 4, 256>>>(g0, d, N, mode, 2, 1); }, 20);
+        float t_tma1 = time_ms([&] { k_tma_elect<NS><<<nb, 256, smem>>>(tm, d, N, mode, 1); }, 20);
+        float t_mix = time_ms([&] { k_tma_elect<NS><<<nb, 256, smem>>>(tm, d, N, mode, 1, g0); }, 20);
         float t_bulk = time_ms([&] { k_bulk<NS><<<nb, 256, smem>>>(g1, d, N, mode); }, 20);
         printf("%s{\"grid\": [%d,%d,%d], \"mode\": \"%s\", \"ctas_per_sm\": %d, \"max_abs_diff\": %.3g, \"sum_abs\": %.6g, "
-               "\"ms_red_1level\": %.4f, \"ms_red_2level\": %.4f, \"ms_tma_1level\": %.4f, \"ms_tma_2level\": %.4f, "
-               "\"ms_mixed_1tma_1red\": %.4f, \"ms_bulk32x4_1level\": %.4f}",
-               first ? "" : ",\n", d.X, d.Y, d.Z, mode == 0 ? "uniform" : "rays", blocks_per_sm, maxd, sum, t_red1, t_red2, t_tma1,
-               t_tma2, t_mix, t_bulk);
+               "\"ms_red_1level\": %.4f, \"ms_red_2level\": %.4f, \"ms_tma_elect_1level\": %.4f, \"ms_mixed_1tma_1red\": %.4f, \"ms_bulk32x4_1level\": %.4f}",
+               first ? "" : ",\n", d.X, d.Y, d.Z, mode == 0 ? "uniform" : "rays", blocks_per_sm, maxd, sum, t_red1, t_red2, t_tma1, t_mix, t_bulk);
         first = false;
       }
     }

@@ -190,17 +190,28 @@ __device__ __forceinline__ FieldGeom field_geom(const miso_field_t& fl) {
   return g;
 }
 
+// A sample whose keyframe id has no pose (outside [0, num_frames), or a table row the host marked with a NaN
+// translation because no 'KF<id>' key was registered) must not train silently with somebody else's pose -- the
+// reference asserts "Key KF.. not found" (grid_net.py:243).  Such a sample gets NaN coordinates (it then interpolates
+// zeros, scatters to no voxel) and, in the mapping step, raises the poison word that turns the step's loss into NaN.
+__device__ __forceinline__ void flag_bad_frame(float* poison) {
+  if (poison) *poison = __int_as_float(0x7fc00000);
+}
+
 __device__ __forceinline__ void load_point(const float* __restrict__ x, const miso_frames_t& fr, int64_t n,
-                                           float (&p)[3]) {
+                                           float (&p)[3], float* poison = nullptr) {
   float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
   if (fr.ids) {
     // transform_points_to (utils_geometry.py:214-225): x R^T + t^T, pose picked per sample (loss.py:764-774)
     int64_t id = fr.ids[n];
-    if (id < 0 || id >= fr.num_frames) id = 0;
+    const bool bad = id < 0 || id >= fr.num_frames;
+    if (bad) id = 0;
     const float* R = fr.R + id * 9;
     const float* t = fr.t + id * 3;
 #pragma unroll
     for (int j = 0; j < 3; ++j) p[j] = fmaf(c, R[3 * j + 2], fmaf(b, R[3 * j + 1], a * R[3 * j])) + t[j];
+    if (bad) p[0] = p[1] = p[2] = __int_as_float(0x7fc00000);
+    if (p[0] != p[0]) flag_bad_frame(poison);
   } else {
     p[0] = a, p[1] = b, p[2] = c;
   }
@@ -690,6 +701,7 @@ struct MapArgs {
   miso_mapping_cfg_t cfg;
   const int32_t* eik_count;
   float* partials;
+  float* poison;   // one float past the per-block partials: set to NaN by a sample without a pose, consumed by finalize
   float* sdf_out;
   float* jac;      // forward modes of the two-thread kernel: (N,F) Jacobian, (N,3) grad_x sdf, (N,3) world coordinates
   float* gradx;
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, MISO_MAP_MIN_BLOCKS)
   float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < m.N; n += (int64_t)gridDim.x * blockDim.x) {
     float p[3], xn[3];
-    load_point(m.x, fr, n, p);
+    load_point(m.x, fr, n, p, m.poison);
 #pragma unroll
     for (int d = 0; d < 3; ++d) xn[d] = normalize_coord(p[d], g.bmin[d], g.bmax[d]);
     float f[F], dfx[F], dfy[F], dfz[F];
@@ -825,20 +837,23 @@ constexpr int kTcMaxSmemPoses = 256;                // keyframe pose table kept 
 
 // load_point with the pose table in shared memory (same arithmetic as load_point)
 __device__ __forceinline__ void load_point_smem(const float* __restrict__ x, const miso_frames_t& fr, int64_t n,
-                                                const float* __restrict__ spose, float (&p)[3]) {
+                                                const float* __restrict__ spose, float (&p)[3], float* poison = nullptr) {
   if (!fr.ids || !spose) {
-    load_point(x, fr, n, p);
+    load_point(x, fr, n, p, poison);
     return;
   }
   const float a = x[3 * n], b = x[3 * n + 1], c = x[3 * n + 2];
   int64_t id = fr.ids[n];
-  if (id < 0 || id >= fr.num_frames) id = 0;
+  const bool bad = id < 0 || id >= fr.num_frames;
+  if (bad) id = 0;
   const float4* P = reinterpret_cast<const float4*>(spose + id * 12);
   const float4 q0 = P[0], q1 = P[1], q2 = P[2];
   const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
   const float tt[3] = {q2.y, q2.z, q2.w};
 #pragma unroll
   for (int j = 0; j < 3; ++j) p[j] = fmaf(c, R[3 * j + 2], fmaf(b, R[3 * j + 1], a * R[3 * j])) + tt[j];
+  if (bad) p[0] = p[1] = p[2] = __int_as_float(0x7fc00000);
+  if (p[0] != p[0]) flag_bad_frame(poison);
 }
 
 template <int F>
@@ -1115,7 +1130,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float gt = 0.f, wgt = 1.f, sgn = 0.f;
     unsigned char vld = 0;
     if (active) {
-      load_point_smem(m.x, fr, n, poses_in_smem ? t.s->poses : nullptr, p);
+      load_point_smem(m.x, fr, n, poses_in_smem ? t.s->poses : nullptr, p, m.poison);
       // asm volatile: keeps these loads up here (the compiler would otherwise sink them to their first use
       // after the decoder, exposing a full memory latency in the loss epilogue)
       gt = ldg_early_f32(m.gt_sdf + n);
@@ -1273,7 +1288,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 namespace miso {
 
 __global__ void mapping_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
-                                        miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out) {
+                                        miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out,
+                                        float* __restrict__ poison) {
   // fixed-order reduction => deterministic loss values
   __shared__ double red[32];
   double s[3] = {0, 0, 0};
@@ -1293,6 +1309,10 @@ __global__ void mapping_finalize_kernel(const float* __restrict__ partials, int 
     out[1] = l_fs;
     out[2] = l_eik;
     out[3] = cfg.weight_sdf * l_sdf + cfg.weight_fs * l_fs + (eik_on ? cfg.weight_eik * l_eik : 0.f);
+    if (*poison != *poison) {   // some sample had no keyframe pose: the step is invalid, say so loudly
+      out[0] = out[1] = out[2] = out[3] = *poison;
+      *poison = 0.f;
+    }
   }
 }
 
@@ -1627,7 +1647,8 @@ extern "C" int miso_get_tuning(const char* key) {
   return -1;
 }
 
-extern "C" int64_t miso_mapping_workspace_floats(void) { return (int64_t)sm_count() * 8 * 4; }
+static int64_t partial_floats() { return (int64_t)sm_count() * 8 * 4; }
+extern "C" int64_t miso_mapping_workspace_floats(void) { return partial_floats() + 4; }   // + the poison word
 
 extern "C" int miso_mapping_count(const float* gt_sdf, int64_t N, float eik_trunc_dist, int32_t* eik_count,
                                   miso_stream_t stream) {
@@ -1657,6 +1678,7 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   MapArgs m;
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
+  m.poison = partials + partial_floats();
   m.jac = nullptr, m.gradx = nullptr, m.xw = nullptr;
   fill_scales(field, m);
   m.dbg = tuning().dbg;
@@ -1681,11 +1703,11 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
       constexpr size_t smem = sizeof(DecoderSmem<L * C>);
       auto k = mapping_step_kernel<L, C>;
       nblocks = blocks_for(k, smem, N);
-      if ((int64_t)nblocks * 4 > miso_mapping_workspace_floats()) nblocks = (int)(miso_mapping_workspace_floats() / 4);
+      if ((int64_t)nblocks * 4 > partial_floats()) nblocks = (int)(partial_floats() / 4);
       k<<<nblocks, kThreads, smem, s>>>(*field, *dec, fr, m);
     });
   }
   if (int e = check_launch("mapping_step")) return e;
-  mapping_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nblocks, N, *cfg, eik_count, loss_out);
+  mapping_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nblocks, N, *cfg, eik_count, loss_out, m.poison);
   return check_launch("mapping_finalize");
 }

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(G * 256, 1)
     const int n2 = t2 * 128 + pt;
     float p[3] = {0.f, 0.f, 0.f};
     if (n2 < N32) {
-      load_point_smem(m.x, fr, n2, poses_in_smem ? s->poses : nullptr, p);
+      load_point_smem(m.x, fr, n2, poses_in_smem ? s->poses : nullptr, p, kMode == 0 ? m.poison : nullptr);
       if constexpr (kMode != 0) {
         if (m.xw) m.xw[3 * (int64_t)n2] = p[0], m.xw[3 * (int64_t)n2 + 1] = p[1], m.xw[3 * (int64_t)n2 + 2] = p[2];
       }

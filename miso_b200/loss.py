@@ -27,47 +27,46 @@ from .diff import gradient3d
 
 
 def miso_loss_regression(pred, targ, valid_mask=None, sample_weights=None, loss_type="L1"):
-    """loss.py:594-635."""
-    assert pred.shape == targ.shape
-    num_samples = pred.shape[0]
-    if valid_mask is None:
-        valid_mask = torch.ones((num_samples, 1)).to(pred)
-    if sample_weights is None:
-        sample_weights = torch.ones((num_samples, 1)).to(pred)
-    assert valid_mask.shape == (num_samples, 1)
-    assert sample_weights.shape == (num_samples, 1)
-    if loss_type == "L2":
-        loss_vec = torch.sum((pred - targ) ** 2, dim=1, keepdim=True)
-    elif loss_type == "L1":
-        loss_vec = torch.sum(torch.abs(pred - targ), dim=1, keepdim=True)
+    """mean_i( w_i * [valid_i == 1] * rho(pred_i, targ_i) ), rho = squared / absolute error summed over the feature
+    dim, or 1 - cosine similarity; the mean runs over ALL samples (loss.py:594-635)."""
+    if pred.shape != targ.shape:
+        raise AssertionError(f"pred {tuple(pred.shape)} vs targ {tuple(targ.shape)}")
+    n = pred.shape[0]
+    diff = pred - targ
+    if loss_type == "L1":
+        per_sample = diff.abs().sum(dim=1, keepdim=True)
+    elif loss_type == "L2":
+        per_sample = (diff ** 2).sum(dim=1, keepdim=True)
     elif loss_type == "Cosine":
-        loss_vec = 1.0 - F.cosine_similarity(pred, targ, dim=1, eps=1e-8).unsqueeze(1)
+        per_sample = (1.0 - F.cosine_similarity(pred, targ, dim=1, eps=1e-8)).unsqueeze(1)
     else:
         raise ValueError(f"Invalid loss type: {loss_type}")
-    loss_vec = torch.where(valid_mask == 1, loss_vec, torch.zeros_like(loss_vec))
-    return torch.mean(sample_weights * loss_vec)
+    if valid_mask is not None:
+        assert valid_mask.shape == (n, 1)
+        per_sample = torch.where(valid_mask == 1, per_sample, torch.zeros_like(per_sample))
+    if sample_weights is not None:
+        assert sample_weights.shape == (n, 1)
+        per_sample = sample_weights * per_sample
+    return per_sample.mean()
 
 
 def miso_loss_eikonal(model, coords_world, gt_sdf, eik_trunc_dist, grad_method, finite_diff_eps):
-    """loss.py:638-665."""
-    if eik_trunc_dist is not None:
-        valid_mask = torch.abs(gt_sdf) < eik_trunc_dist
-        valid_indices = torch.nonzero(valid_mask, as_tuple=False)[:, 0]
-        x_eik = coords_world[valid_indices, :].clone()
-    else:
-        x_eik = coords_world.clone()
-    x_eik.requires_grad_(True)
-    gradient = gradient3d(x_eik, model, method=grad_method, finite_diff_eps=finite_diff_eps, create_graph=True)
-    grad_constraint = gradient.norm(dim=-1) - 1
-    return torch.mean(grad_constraint ** 2)
+    """mean (|grad_x f| - 1)^2 over the samples with |gt| < eik_trunc_dist (all samples when None), loss.py:638-665."""
+    pts = coords_world if eik_trunc_dist is None else coords_world[(gt_sdf.abs() < eik_trunc_dist)[:, 0]]
+    pts = pts.clone().requires_grad_(True)
+    g = gradient3d(pts, model, method=grad_method, finite_diff_eps=finite_diff_eps, create_graph=True)
+    return ((g.norm(dim=-1) - 1) ** 2).mean()
 
 
 def miso_loss_free_space(pred_sdf, gt_sdf, gt_sdf_sign, trunc_dist):
-    """loss.py:668-700."""
+    """On samples in front of the surface (sign == 1): max(relu(pred - gt), relu(trunc - pred)); mean over all
+    samples (loss.py:668-700)."""
     assert trunc_dist is not None
-    fs_upper = torch.where(gt_sdf_sign == 1, F.relu(pred_sdf - gt_sdf), torch.zeros_like(pred_sdf))
-    fs_lower = torch.where(gt_sdf_sign == 1, F.relu(trunc_dist - pred_sdf), torch.zeros_like(pred_sdf))
-    return torch.mean(torch.maximum(fs_upper, fs_lower))
+    front = gt_sdf_sign == 1
+    zero = torch.zeros_like(pred_sdf)
+    over = torch.where(front, F.relu(pred_sdf - gt_sdf), zero)
+    under = torch.where(front, F.relu(trunc_dist - pred_sdf), zero)
+    return torch.maximum(over, under).mean()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,6 +201,12 @@ class MisoLossMappingBase:
         if use_stability or weight_clip > 0:
             raise NotImplementedError("stability / CLIP terms are outside the hot path (SURVEY.md section 8)")
         self.last_terms = None
+        # `compute` checks (one host sync) that every sample's keyframe has a pose, as the reference's per-keyframe
+        # loop does by construction; the trainer's sync-free `step_into_grads` relies on the kernel's NaN poison
+        self.check_frame_ids = True
+
+    def validate_frame_ids(self, model, sample_frame_ids):
+        pass
 
     # -- pose table -------------------------------------------------------------------------------
     def frame_table(self, model):
@@ -228,6 +233,8 @@ class MisoLossMappingBase:
         gt_sdf_sign = gt["sdf_signs"][0]
         assert coords_frame.ndim == 2 and gt_sdf.ndim == 2
         assert sample_weights.shape == gt_sdf.shape
+        if self.check_frame_ids:
+            self.validate_frame_ids(model, sample_frame_ids)
         if self._fused_ok(model):
             return self._compute_fused(model, coords_frame, sample_frame_ids, sample_weights, gt_sdf, gt_sdf_valid,
                                        gt_sdf_sign)
@@ -309,8 +316,11 @@ class MisoLossMapping(MisoLossMappingBase):
     f'KF{k}' (grid_net.py:232-235)."""
 
     def frame_table(self, model):
-        """Tables indexed by GLOBAL keyframe id (so the kernel consumes `sample_frame_ids` directly).  While
-        poses are locked the table is cached and only rebuilt when a pose tensor's version counter moves."""
+        """Pose tables indexed by GLOBAL keyframe id (so the kernel consumes `sample_frame_ids` directly).  An id
+        with no registered 'KF<id>' key gets a NaN row: the kernels turn a sample that hits one (or an id outside the
+        table) into a NaN step loss instead of training it with some other keyframe's pose, and `compute` raises the
+        reference's assertion for it (grid_net.py:243).  While poses are locked the table is cached and only
+        rebuilt when a pose tensor's version counter moves."""
         keys = model._pose_key_to_id
         params = (model.rotation_corrections, model.translation_corrections, model.Rwk, model.twk)
         locked = not (model.rotation_corrections.requires_grad or model.translation_corrections.requires_grad)
@@ -319,12 +329,27 @@ class MisoLossMapping(MisoLossMappingBase):
         if locked and cache is not None and cache[0] == stamp:
             return cache[1], cache[2], None
         R, t = model.all_kf_poses()
-        n = 1 + max([int(k[2:]) for k in keys], default=-1)
-        lut = torch.zeros(max(n, 1), dtype=torch.int64)
+        n = max(1 + max([int(k[2:]) for k in keys], default=-1), 1)
+        row = torch.full((n,), -1, dtype=torch.int64)
         for k, v in keys.items():
-            lut[int(k[2:])] = v
-        lut = lut.to(R.device)
-        Rg, tg = R[lut], t[lut]
+            row[int(k[2:])] = v
+        known = (row >= 0).to(R.device)
+        row = row.clamp(min=0).to(R.device)
+        Rg = R[row]
+        tg = torch.where(known[:, None, None], t[row], torch.full_like(t[row], float("nan")))
+        model._miso_frame_known = known
         if locked:
             model._miso_frame_cache = (stamp, Rg.detach(), tg.detach())
         return Rg, tg, None
+
+    def validate_frame_ids(self, model, sample_frame_ids):
+        """Host-side check (one device sync) that every sample's keyframe id has a registered pose; raises the
+        reference's message (grid_net.py:243) for the first one that has not."""
+        self.frame_table(model)
+        known = model._miso_frame_known
+        ids = sample_frame_ids.reshape(-1)
+        inside = (ids >= 0) & (ids < known.numel())
+        ok = inside & known[ids.clamp(0, known.numel() - 1)]
+        if not bool(ok.all()):
+            bad = int(ids[~ok][0])
+            raise AssertionError(f"Key KF{bad} not found in pose key to ID mapping!")

@@ -1,22 +1,22 @@
-"""Host-side mirror of the reference's model interface for the hot path: same class names,
-constructor arguments, attribute names and state-dict keys as
+"""Parameter holders of the hot path: dense feature levels, the ReLU decoder, keyframe / submap pose tables.
 
-    grid_opt/models/grid_modules.py  (FeatureGrid            :41-123)
-    grid_opt/models/modules.py       (MLPNet                 :11-40)
-    grid_opt/models/grid_net.py      (GridNet                :17-352)
-    grid_opt/models/grid_atlas.py    (GridAtlas              :18-587, the parts alignment uses)
-    grid_opt/utils/utils.py          (normalize_coordinates :22-51, grid_interp_regular :143-164,
-                                      grid_decode :194-208, all_grid_positions :294-307)
+The classes answer to the reference's names and keep its constructor arguments, method names and state-dict keys
+(`features.<l>.feature`, `feature_stability.<l>.feature`, `decoder.network.<i>.{weight,bias}`,
+`rotation_corrections`, `translation_corrections`, `Rwk`, `twk`) so that checkpoints and call sites of
 
-so a user of the reference finds the same objects; the compute underneath is the CUDA path.
-What changes on purpose: grid parameters are stored channels_last_3d (logical shape `(1,C,Z,Y,X)`
-unchanged), `grid_sample_func` is always `miso_b200.cuda_gridsample.grid_sample_3d`, and
-`GridNet.forward` takes the fused kernel when the decoder is fixed (cfg decoder.fix: True).
+    grid_opt/models/grid_modules.py  FeatureGrid   :41-123
+    grid_opt/models/modules.py       MLPNet        :11-40
+    grid_opt/models/grid_net.py      GridNet       :17-352
+    grid_opt/models/grid_atlas.py    GridAtlas     :18-587 (construction, poses, alignment samples, queries)
+
+carry over; the bodies are written for this package: levels live channels_last_3d, every query goes to the CUDA
+library (fused kernels when the decoder is frozen, the per-level plugin otherwise), pose tables are evaluated in
+batch with a per-keyframe trainable mask instead of a Python loop, and the keyframe <-> submap maps are integer
+tables.  To use the kernels from the reference's own classes instead, see `miso_b200.adapter` / INTEGRATION.md.
 """
-import math
+import copy
 import os
-from copy import deepcopy
-from typing import Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -24,179 +24,166 @@ from torch import nn
 
 from . import cuda_gridsample as cu
 from . import field as _field
-from . import geometry as utils_geometry
+from . import geometry as geo
+
+FUSED_LEVEL_CHANNEL_SHAPES = {(1, 4), (2, 4), (3, 4), (4, 4), (1, 8), (2, 8), (1, 16)}
 
 
 # ------------------------------------------------------------------------------------------------
-# utils.py mirrors
+# coordinate helpers (grid_opt/utils/utils.py:22-80, :294-307)
 # ------------------------------------------------------------------------------------------------
-def normalize_coordinates(queries: torch.Tensor, bounds: torch.Tensor):
-    """utils.py:22-51 (same operation order: 2*(x-bmin)/(bmax-bmin) - 1)."""
-    d = bounds.shape[0]
-    assert queries.shape[-1] == d
-    if queries.dim() == 2:
-        bounds_min = bounds[:, 0].view(1, -1)
-        bounds_max = bounds[:, 1].view(1, -1)
-    elif queries.dim() == 3:
-        bounds_min = bounds[:, 0].view(1, 1, -1)
-        bounds_max = bounds[:, 1].view(1, 1, -1)
-    else:
-        raise ValueError("queries tensor must be either 2D or 3D")
-    return 2 * (queries - bounds_min) / (bounds_max - bounds_min) - 1
+def _lo_hi(bounds: torch.Tensor, like: torch.Tensor):
+    """bounds (d,2) -> broadcastable (lo, hi) rows for a (..., d) coordinate tensor."""
+    if like.dim() not in (2, 3):
+        raise ValueError("coordinates must be (N,d) or (B,N,d)")
+    shape = (1,) * (like.dim() - 1) + (-1,)
+    return bounds[:, 0].reshape(shape), bounds[:, 1].reshape(shape)
 
 
-def denormalize_coordinates(normalized_queries: torch.Tensor, bounds: torch.Tensor):
-    """utils.py:53-80."""
-    if normalized_queries.dim() == 2:
-        bounds_min = bounds[:, 0].view(1, -1)
-        bounds_max = bounds[:, 1].view(1, -1)
-    elif normalized_queries.dim() == 3:
-        bounds_min = bounds[:, 0].view(1, 1, -1)
-        bounds_max = bounds[:, 1].view(1, 1, -1)
-    else:
-        raise ValueError("normalized_queries tensor must be either 2D or 3D")
-    return (normalized_queries + 1) / 2 * (bounds_max - bounds_min) + bounds_min
+def normalize_coordinates(queries: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """World -> [-1,1]^d.  The operation order `2 (x - lo) / (hi - lo) - 1` is the reference's (utils.py:49) and the
+    kernels' (`normalize_coord`, csrc/common.cuh): floor() decisions depend on it."""
+    lo, hi = _lo_hi(bounds, queries)
+    return 2 * (queries - lo) / (hi - lo) - 1
 
 
-def all_grid_positions(features):
-    """utils.py:294-307: voxel-centre coordinates, shape (1,Z,Y,X,3), last dim (x,y,z)."""
-    B, Cc, D, H, W = features.shape
-    half_dx = 0.5 * 1 / D
-    half_dy = 0.5 * 1 / H
-    half_dz = 0.5 * 1 / W
-    xs = 2 * torch.linspace(half_dx, 1 - half_dx, D) - 1.
-    ys = 2 * torch.linspace(half_dy, 1 - half_dy, H) - 1.
-    zs = 2 * torch.linspace(half_dz, 1 - half_dz, W) - 1.
-    xv, yv, zv = torch.meshgrid([xs, ys, zs], indexing="ij")
-    grid = torch.stack((zv, yv, xv), axis=-1)
-    return grid.unsqueeze(0)
+def denormalize_coordinates(unit: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """[-1,1]^d -> world, `(u + 1) / 2 (hi - lo) + lo` (utils.py:53-80)."""
+    lo, hi = _lo_hi(bounds, unit)
+    return (unit + 1) / 2 * (hi - lo) + lo
 
 
-def grid_interp_regular(reg_grids, x, ignore_level=None):
-    """utils.py:143-164."""
-    num_levels = len(reg_grids)
-    if ignore_level is None:
-        ignore_level = np.zeros(num_levels).astype(bool)
-    level_feats = []
-    for level in range(num_levels):
-        feats = reg_grids[level].interpolate(x)
-        if not ignore_level[level]:
-            level_feats.append(feats)
-        else:
-            level_feats.append(torch.zeros_like(feats))
-    return torch.cat(level_feats, dim=1)
+def _axis_centres(n: int) -> torch.Tensor:
+    """Normalised centres of n voxels along one axis, with the rounding sequence of utils.py:294-307
+    (linspace over [1/2n, 1 - 1/2n], then 2u - 1) so alignment samples are bit-identical to the reference's."""
+    half = 0.5 / n
+    return 2 * torch.linspace(half, 1 - half, n) - 1.0
 
 
-def grid_decode(feats, x, decoder=None, pos_invariant=True):
-    """utils.py:194-208."""
-    assert feats.ndim == 2
-    if decoder is not None:
-        inputs = feats if pos_invariant else torch.cat((feats, x), dim=1)
-        preds = decoder(inputs)
-    else:
-        preds = feats
-    return preds
+def all_grid_positions(features: torch.Tensor) -> torch.Tensor:
+    """(1,Z,Y,X,3) normalised voxel centres of a (1,C,Z,Y,X) level, last dim (x,y,z)."""
+    Z, Y, X = features.shape[2:]
+    out = torch.empty((1, Z, Y, X, 3))
+    out[..., 0] = _axis_centres(X).reshape(1, 1, 1, X)
+    out[..., 1] = _axis_centres(Y).reshape(1, 1, Y, 1)
+    out[..., 2] = _axis_centres(Z).reshape(1, Z, 1, 1)
+    return out
+
+
+def level_dims(bound, cell_size: float) -> Tuple[int, int, int]:
+    """Voxels per axis (X,Y,Z) = ceil(extent / cell) in float32, as the reference sizes a level (grid_modules.py:47-53)."""
+    b = np.asarray(bound.detach().cpu() if isinstance(bound, torch.Tensor) else bound, dtype=np.float32)
+    n = np.ceil((b[:, 1] - b[:, 0]) / cell_size).astype(int)
+    return int(n[0]), int(n[1]), int(n[2])
+
+
+def grid_interp_regular(levels: Sequence["FeatureGrid"], x: torch.Tensor, ignore_level=None) -> torch.Tensor:
+    """Per-level interpolation + concat; an ignored level keeps its slot filled with zeros (utils.py:143-164)."""
+    cols = []
+    for l, lvl in enumerate(levels):
+        f = lvl.interpolate(x)
+        cols.append(f * 0 if (ignore_level is not None and ignore_level[l]) else f)
+    return torch.cat(cols, dim=1)
+
+
+def grid_decode(feats: torch.Tensor, x: Optional[torch.Tensor], decoder=None, pos_invariant=True) -> torch.Tensor:
+    """utils.py:194-208: features (optionally with the position appended) through the decoder, or unchanged."""
+    if feats.ndim != 2:
+        raise AssertionError(f"features must be (N,F), got {tuple(feats.shape)}")
+    if decoder is None:
+        return feats
+    return decoder(feats if pos_invariant else torch.cat((feats, x), dim=1))
+
+
+def _set_trainable(module: nn.Module, flag: bool):
+    for p in module.parameters():
+        p.requires_grad_(flag)
 
 
 # ------------------------------------------------------------------------------------------------
-# grid_modules.py / modules.py mirrors
+# one dense level
 # ------------------------------------------------------------------------------------------------
 class FeatureGrid(nn.Module):
-    """Dense 3D feature grid `(1,C,Z,Y,X)` (grid_modules.py:41-123)."""
+    """Dense feature level, logical shape (1,C,Z,Y,X), stored channels_last_3d (one voxel = C contiguous floats)."""
 
     def __init__(self, d, fdim, bound, cell_size, name="grid", dtype=torch.float32, initial_feature=None,
                  init_stddev=0.0, second_order_grid_sample=False):
         super().__init__()
         if d != 3:
-            raise NotImplementedError("miso_b200 implements spatial_dim 3 only (shipped MISO configs)")
-        self.d = d
-        self.fdim = fdim
-        self.bound = bound
-        self.cell_size = cell_size
-        self.dtype = dtype
-        self.name = name
-        assert self.bound.shape == (d, 2)
-        grid_len = (self.bound[:, 1] - self.bound[:, 0]).cpu().numpy()
-        grid_size = np.ceil(grid_len / cell_size).astype(int)
-        feature_shape = (1, self.fdim, int(grid_size[2]), int(grid_size[1]), int(grid_size[0]))
+            raise NotImplementedError("miso_b200 implements spatial_dim 3 only (every shipped MISO config)")
+        self.d, self.fdim, self.cell_size, self.dtype, self.name = d, fdim, cell_size, dtype, name
+        self.bound = bound if isinstance(bound, torch.Tensor) else torch.as_tensor(np.asarray(bound), dtype=dtype)
+        if tuple(self.bound.shape) != (3, 2):
+            raise AssertionError(f"bound must be (3,2), got {tuple(self.bound.shape)}")
+        X, Y, Z = level_dims(self.bound, cell_size)
+        shape = (1, fdim, Z, Y, X)
         if initial_feature is None:
-            initial_feature = torch.randn(feature_shape, dtype=self.dtype) * init_stddev
-        assert initial_feature.shape == feature_shape
-        self.feature = torch.nn.Parameter(initial_feature.contiguous(memory_format=torch.channels_last_3d))
-        # the reference picks F.grid_sample or the CUDA double-backward plugin here (:63-69);
-        # the B200 op covers both, so the flag only records the request
+            initial_feature = torch.randn(shape, dtype=dtype) * init_stddev
+        elif tuple(initial_feature.shape) != shape:
+            raise AssertionError(f"initial feature {tuple(initial_feature.shape)} does not fit level shape {shape}")
+        self.feature = nn.Parameter(initial_feature.contiguous(memory_format=torch.channels_last_3d))
+        # the reference switches between F.grid_sample and its double-backward plugin here (grid_modules.py:63-69);
+        # the CUDA op below is both, the flag is only remembered
         self.second_order_grid_sample = second_order_grid_sample
         self.grid_sample_func = cu.grid_sample_3d
-        self._bound_host = _field.bound_to_list(bound)
+        self._bound_host = _field.bound_to_list(self.bound)
 
-    def _apply(self, fn, *a, **k):
-        super()._apply(fn, *a, **k)
-        # .to(device) / .cuda() re-allocate: keep the channels-last layout and follow with `bound`
-        _field.to_channels_last_3d_(self.feature)
-        if isinstance(self.bound, torch.Tensor):
-            self.bound = fn(self.bound)
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        _field.to_channels_last_3d_(self.feature)    # .to()/.cuda() re-allocate: restore the layout
+        self.bound = fn(self.bound)
         return self
 
-    def interpolate(self, x):
-        """grid_modules.py:72-95."""
-        x = normalize_coordinates(x, self.bound)
-        N = x.shape[0]
-        sample_coords = x.reshape(1, N, 1, 1, 3)
-        feats = self.grid_sample_func(self.feature, sample_coords, align_corners=False,
-                                      padding_mode="zeros")[0, :, :, 0, 0].transpose(0, 1)
-        return feats
+    def interpolate(self, x: torch.Tensor) -> torch.Tensor:
+        """(N,3) world points -> (N,C) trilinear features, zeros outside, align_corners=False (grid_modules.py:72-95)."""
+        unit = normalize_coordinates(x, self.bound).reshape(1, -1, 1, 1, 3)
+        sampled = self.grid_sample_func(self.feature, unit, padding_mode="zeros", align_corners=False)
+        return sampled[0, :, :, 0, 0].t()
 
     def norm(self):
         return self.feature.norm()
 
-    def num_params(self):
+    def num_params(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
     def lock(self):
-        for param in self.parameters():
-            param.requires_grad = False
+        _set_trainable(self, False)
 
     def unlock(self):
-        for param in self.parameters():
-            param.requires_grad = True
+        _set_trainable(self, True)
 
+    @torch.no_grad()
     def zero_features(self):
-        with torch.no_grad():
-            self.feature.zero_()
+        self.feature.zero_()
 
-    def randn_features(self, std):
-        with torch.no_grad():
-            new_feat = torch.randn(self.feature.shape, dtype=self.dtype) * std
-            self.feature.copy_(new_feat.to(self.feature))
+    @torch.no_grad()
+    def randn_features(self, std: float):
+        self.feature.copy_((torch.randn(self.feature.shape, dtype=self.dtype) * std).to(self.feature.device))
 
     def vertex_positions(self, denormalize=True) -> torch.Tensor:
-        """grid_modules.py:111-123 (computed on the host exactly like the reference, then moved)."""
-        pos_nrm = all_grid_positions(self.feature)
-        pos_nrm = torch.flatten(pos_nrm.squeeze(0), start_dim=0, end_dim=-2)
-        if denormalize:
-            return denormalize_coordinates(pos_nrm, self.bound.to(pos_nrm))
-        return pos_nrm
+        """(Z*Y*X, 3) voxel centres, x fastest (grid_modules.py:111-123); evaluated on the host like the reference."""
+        unit = all_grid_positions(self.feature).reshape(-1, 3)
+        return denormalize_coordinates(unit, self.bound.to(unit)) if denormalize else unit
 
 
 class MLPNet(nn.Module):
-    """modules.py:11-40."""
+    """Linear -> act -> (Linear -> act) x hidden_layers -> Linear, exposed as `.network` (modules.py:11-40)."""
 
     def __init__(self, input_dim, output_dim, hidden_dim=64, hidden_layers=1, bias=False, acti_func=nn.ReLU,
                  pretrained_path=None, no_optimize=False):
         super().__init__()
-        self.input_dim = input_dim
-        self.output_dim = output_dim
-        self.layers = [nn.Linear(input_dim, hidden_dim, bias=bias), acti_func()]
-        for _ in range(hidden_layers):
-            self.layers.append(nn.Linear(hidden_dim, hidden_dim, bias=bias))
-            self.layers.append(acti_func())
-        self.layers.append(nn.Linear(hidden_dim, output_dim, bias=bias))
-        self.network = nn.Sequential(*self.layers)
+        self.input_dim, self.output_dim = input_dim, output_dim
+        widths = [input_dim] + [hidden_dim] * (hidden_layers + 1)
+        stack: List[nn.Module] = []
+        for w_in, w_out in zip(widths[:-1], widths[1:]):
+            stack += [nn.Linear(w_in, w_out, bias=bias), acti_func()]
+        stack.append(nn.Linear(hidden_dim, output_dim, bias=bias))
+        self.layers = stack
+        self.network = nn.Sequential(*stack)
         if pretrained_path is not None:
             self.load(pretrained_path)
         if no_optimize:
-            for param in self.parameters():
-                param.requires_grad = False
+            _set_trainable(self, False)
 
     def forward(self, x):
         return self.network(x)
@@ -209,170 +196,166 @@ class MLPNet(nn.Module):
 
 
 class BaseNet(nn.Module):
-    """models/base_net.py:11-40."""
+    """cfg + spatial bound shared by GridNet / GridAtlas (models/base_net.py:11-40)."""
 
     def __init__(self, cfg: dict, device="cpu", dtype=torch.float32):
         super().__init__()
-        self.cfg = cfg
-        self.d = self.cfg["spatial_dim"]
-        self.device = device
-        self.dtype = dtype
-        assert self.d == 2 or self.d == 3
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        self.d = cfg["spatial_dim"]
         self.bound = torch.tensor(np.asarray(cfg["grid"]["bound"]), device=device, dtype=dtype)
-        assert self.bound.shape == (self.d, 2)
+        if self.d != 3 or tuple(self.bound.shape) != (3, 2):
+            raise AssertionError("miso_b200 models are 3-D with a (3,2) bound")
 
 
+# ------------------------------------------------------------------------------------------------
+# one submap
+# ------------------------------------------------------------------------------------------------
 class GridNet(BaseNet):
-    """One submap: L FeatureGrid levels + MLP decoder + per-keyframe pose corrections
-    (grid_net.py:17-352).  `forward` / `query_feature` / `params_at_level` keep their signatures."""
+    """One submap: L levels (+ their 1-channel stability levels), the decoder, K keyframe poses with corrections."""
 
     def __init__(self, cfg: dict, device="cuda:0", dtype=torch.float32, initial_features=dict()):
         super().__init__(cfg, device, dtype)
         self.initial_features = initial_features
-        self.init_grid(cfg)
-        self.init_decoder(cfg)
-        self.init_poses(cfg)
+        self._build_levels(cfg["grid"])
+        self._build_decoder(cfg["decoder"])
+        self._build_pose_table(cfg["pose"])
         self.to(device)
         self._bound_host = _field.bound_to_list(cfg["grid"]["bound"])
-        self._spec_cache = None
+        self._decoder_spec = None
 
-    def _apply(self, fn, *a, **k):
-        super()._apply(fn, *a, **k)
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
         self.bound = fn(self.bound)
-        self._spec_cache = None
+        self._decoder_spec = None
         return self
+
+    # ---- construction -----------------------------------------------------------------------------
+    def _build_levels(self, g: dict):
+        if g["type"] != "regular":
+            raise NotImplementedError("grid.type 'regular' only (the shipped configs); VM grids are out of scope")
+        self.grid_type = g["type"]
+        self.num_levels, self.fdim = g["n_levels"], g["feature_dim"]
+        self.second_order_grid_sample = bool(g.get("second_order_grid_sample", False))
+        self.cell_sizes = [g["base_cell_size"] / g["per_level_scale"] ** l for l in range(self.num_levels)]
+        host_bound = self.bound.detach().cpu()
+
+        def level(l, channels, tag, init, std):
+            return FeatureGrid(d=3, fdim=channels, bound=host_bound, cell_size=self.cell_sizes[l], name=f"{tag}-{l}",
+                               dtype=self.dtype, initial_feature=init, init_stddev=std,
+                               second_order_grid_sample=self.second_order_grid_sample)
+
+        self.features = nn.ModuleList(level(l, self.fdim, "feat", self.initial_features.get(l), g["init_stddev"])
+                                      for l in range(self.num_levels))
+        self.feature_stability = nn.ModuleList(level(l, 1, "stab", None, 0.0) for l in range(self.num_levels))
+        self.ignore_level_ = np.zeros(self.num_levels, dtype=bool)
+
+    def _build_decoder(self, d: dict):
+        self.decoder_hidden_dim, self.decoder_hidden_layers = d["hidden_dim"], d["hidden_layers"]
+        self.decoder_out_dim, self.pos_invariant = d["out_dim"], d["pos_invariant"]
+        self.decoder_fixed, self.decoder_type = d["fix"], d["type"]
+        if self.decoder_type == "none":
+            self.decoder = None
+        elif self.decoder_type == "mlp":
+            width_in = self.num_levels * self.fdim + (0 if self.pos_invariant else 3)
+            self.decoder = MLPNet(width_in, self.decoder_out_dim, hidden_dim=self.decoder_hidden_dim,
+                                  hidden_layers=self.decoder_hidden_layers, bias=True,
+                                  pretrained_path=d["pretrained_model"], no_optimize=self.decoder_fixed)
+        else:
+            raise ValueError(f"Unknown decoder type: {self.decoder_type}")
+
+    def _build_pose_table(self, p: dict):
+        K = self.num_poses = p["num_poses"]
+        self.optimize_pose = p["optimize"]
+        self.rotation_corrections = nn.Parameter(torch.zeros(K, 3), requires_grad=self.optimize_pose)
+        self.translation_corrections = nn.Parameter(torch.zeros(K, 3, 1), requires_grad=self.optimize_pose)
+        self.register_buffer("Rwk", geo.identity_rotations(K))
+        self.register_buffer("twk", torch.zeros(K, 3, 1))
+        self.pose_estimates_known = [False] * K
+        self.locked_pose_indices = set()
+        self._pose_key_to_id: Dict[str, int] = {}
 
     def save(self, ckpt_dir, ckpt_prefix):
         self.decoder.save(os.path.join(ckpt_dir, f"{ckpt_prefix}_decoder.pt"))
 
-    def init_grid(self, cfg):
-        self.num_levels = cfg["grid"]["n_levels"]
-        self.second_order_grid_sample = bool(cfg["grid"].get("second_order_grid_sample", False))
-        base_cell_size = cfg["grid"]["base_cell_size"]
-        scale_factor = cfg["grid"]["per_level_scale"]
-        self.fdim = cfg["grid"]["feature_dim"]
-        self.features = nn.ModuleList()
-        self.feature_stability = nn.ModuleList()
-        self.grid_type = cfg["grid"]["type"]
-        if self.grid_type != "regular":
-            raise NotImplementedError("miso_b200 implements grid.type 'regular' (the shipped configs); "
-                                      "the VM variants are out of scope (SURVEY.md section 2, row 1)")
-        self.cell_sizes = []
-        bound_cpu = self.bound.detach().cpu()
-        for level in range(self.num_levels):
-            cell_size = base_cell_size / (scale_factor ** level)
-            self.cell_sizes.append(cell_size)
-            init_feature = self.initial_features.get(level, None)
-            self.features.append(FeatureGrid(d=self.d, fdim=self.fdim, bound=bound_cpu, cell_size=cell_size,
-                                             name=f"feat-{level}", dtype=self.dtype, initial_feature=init_feature,
-                                             init_stddev=cfg["grid"]["init_stddev"],
-                                             second_order_grid_sample=self.second_order_grid_sample))
-            self.feature_stability.append(FeatureGrid(d=self.d, fdim=1, bound=bound_cpu, cell_size=cell_size,
-                                                      name=f"stab-{level}", dtype=self.dtype, initial_feature=None,
-                                                      init_stddev=0.0,
-                                                      second_order_grid_sample=self.second_order_grid_sample))
-        self.ignore_level_ = np.zeros(self.num_levels).astype(bool)
-
-    def init_decoder(self, cfg):
-        self.decoder_hidden_dim = cfg["decoder"]["hidden_dim"]
-        self.decoder_hidden_layers = cfg["decoder"]["hidden_layers"]
-        self.decoder_out_dim = cfg["decoder"]["out_dim"]
-        self.pos_invariant = cfg["decoder"]["pos_invariant"]
-        self.decoder_fixed = cfg["decoder"]["fix"]
-        self.decoder_type = cfg["decoder"]["type"]
-        input_dim = self.num_levels * self.fdim
-        if not self.pos_invariant:
-            input_dim += self.d
-        if self.decoder_type == "mlp":
-            self.decoder = MLPNet(input_dim=input_dim, output_dim=self.decoder_out_dim,
-                                  hidden_dim=self.decoder_hidden_dim, hidden_layers=self.decoder_hidden_layers,
-                                  bias=True, pretrained_path=cfg["decoder"]["pretrained_model"],
-                                  no_optimize=self.decoder_fixed)
-        elif self.decoder_type == "none":
-            self.decoder = None
-        else:
-            raise ValueError(f"Unknown decoder type: {self.decoder_type}")
-
-    def init_poses(self, cfg):
-        self.num_poses = cfg["pose"]["num_poses"]
-        self.optimize_pose = cfg["pose"]["optimize"]
-        self.rotation_corrections = torch.nn.Parameter(torch.zeros(self.num_poses, 3).float(),
-                                                       requires_grad=self.optimize_pose)
-        self.translation_corrections = torch.nn.Parameter(torch.zeros(self.num_poses, 3, 1).float(),
-                                                          requires_grad=self.optimize_pose)
-        self.pose_estimates_known = [False] * self.num_poses
-        self.register_buffer("Rwk", utils_geometry.identity_rotations(self.num_poses))
-        self.register_buffer("twk", torch.zeros(size=(self.num_poses, 3, 1)))
-        self.locked_pose_indices = set()
-        self._pose_key_to_id = dict()
-
-    # ---- level / pose bookkeeping (grid_net.py:159-262) ------------------------------------------
+    # ---- levels -------------------------------------------------------------------------------------
     def ignore_level(self, l):
-        self.ignore_level_[l] = True
-        self._spec_cache = None
+        self.ignore_level_[int(l)] = True     # the level keeps its slot in the feature vector, filled with zeros
 
     def include_level(self, l):
-        self.ignore_level_[l] = False
-        self._spec_cache = None
+        self.ignore_level_[int(l)] = False
+
+    def _ignore_mask(self) -> int:
+        return sum(1 << l for l in range(self.num_levels) if self.ignore_level_[l])
+
+    def _level_trainable(self, levels, flag: bool):
+        for l in levels:
+            _set_trainable(self.features[l], flag)
+            _set_trainable(self.feature_stability[l], flag)
 
     def lock_level(self, l):
-        self.features[l].lock()
-        self.feature_stability[l].lock()
+        self._level_trainable((l,), False)
 
     def unlock_level(self, l):
-        self.features[l].unlock()
-        self.feature_stability[l].unlock()
+        self._level_trainable((l,), True)
 
     def lock_feature(self):
-        for level in range(self.num_levels):
-            self.lock_level(level)
+        self._level_trainable(range(self.num_levels), False)
 
     def unlock_feature(self):
-        for level in range(self.num_levels):
-            self.unlock_level(level)
+        self._level_trainable(range(self.num_levels), True)
+
+    def zero_features(self):
+        for lvl in self.features:
+            lvl.zero_features()
+
+    def randn_features(self, std):
+        for lvl in self.features:
+            lvl.randn_features(std)
+
+    def level_tensors(self) -> List[torch.Tensor]:
+        return [lvl.feature for lvl in self.features]
+
+    # ---- keyframe poses (grid_net.py:159-262) ---------------------------------------------------------
+    def _poses_trainable(self, flag: bool):
+        for p in self.params_for_poses():
+            p.requires_grad_(flag)
+        self.locked_pose_indices = set() if flag else set(range(self.num_poses))
 
     def lock_pose(self):
-        self.rotation_corrections.requires_grad_(False)
-        self.translation_corrections.requires_grad_(False)
-        self.lock_all_pose_indices()
+        self._poses_trainable(False)
 
     def unlock_pose(self):
-        self.rotation_corrections.requires_grad_(True)
-        self.translation_corrections.requires_grad_(True)
-        self.unlock_all_pose_indices()
+        self._poses_trainable(True)
 
     def lock_pose_index(self, pose_index: int):
-        self.locked_pose_indices.add(pose_index)
+        self.locked_pose_indices |= {int(pose_index)}
+
+    def unlock_pose_index(self, pose_index: int):
+        self.locked_pose_indices.remove(int(pose_index))    # KeyError when it was not locked, like the reference
 
     def lock_all_pose_indices(self):
         self.locked_pose_indices = set(range(self.num_poses))
 
-    def unlock_pose_index(self, pose_index: int):
-        self.locked_pose_indices.remove(pose_index)
-
     def unlock_all_pose_indices(self):
-        self.locked_pose_indices.clear()
+        self.locked_pose_indices = set()
 
     def pose_correction(self, kf_id: int):
-        r = self.rotation_corrections[[kf_id], :]
-        t = self.translation_corrections[kf_id, :, :]
-        if kf_id in self.locked_pose_indices:
-            r = r.clone().detach()
-            t = t.clone().detach()
-        return r, t
+        """(1,3) rotation and (3,1) translation correction of one keyframe; a locked keyframe's are detached."""
+        dr, dt = self.rotation_corrections[kf_id:kf_id + 1], self.translation_corrections[kf_id]
+        return (dr.detach().clone(), dt.detach().clone()) if kf_id in self.locked_pose_indices else (dr, dt)
 
     def set_initial_kf_pose(self, kf_id: int, Rwk: torch.Tensor, twk: torch.Tensor, kf_key=None):
-        assert Rwk.shape == (3, 3)
-        assert twk.shape == (3, 1)
+        if tuple(Rwk.shape) != (3, 3) or tuple(twk.shape) != (3, 1):
+            raise AssertionError("keyframe pose must be R (3,3), t (3,1)")
         assert kf_id < self.num_poses, f"KF ID {kf_id} exceeds the number of poses {self.num_poses}!"
-        self.pose_estimates_known[kf_id] = True
-        self.Rwk[kf_id, :, :] = Rwk.to(self.Rwk)
-        self.twk[kf_id, :, :] = twk.to(self.twk)
         with torch.no_grad():
-            self.rotation_corrections[kf_id, :].zero_()
-            self.translation_corrections[kf_id, :, :].zero_()
+            self.Rwk[kf_id] = Rwk.to(self.Rwk)
+            self.twk[kf_id] = twk.to(self.twk)
+            self.rotation_corrections[kf_id].zero_()
+            self.translation_corrections[kf_id].zero_()
+        self.pose_estimates_known[kf_id] = True
         if kf_key is not None:
-            self._pose_key_to_id[kf_key] = kf_id
+            self._pose_key_to_id[str(kf_key)] = int(kf_id)
 
     def pose_key_to_id(self, kf_key):
         assert kf_key in self._pose_key_to_id, f"Key {kf_key} not found in pose key to ID mapping!"
@@ -380,363 +363,313 @@ class GridNet(BaseNet):
 
     def initial_kf_pose(self, kf_id: int):
         assert self.pose_estimates_known[kf_id], f"Initial pose estimate for KF {kf_id} is not available!"
-        return self.Rwk[kf_id, :, :], self.twk[kf_id, :, :]
+        return self.Rwk[kf_id], self.twk[kf_id]
 
-    def initial_kf_pose_in_world(self, kf_id: int):
-        return self.initial_kf_pose(kf_id)
+    initial_kf_pose_in_world = initial_kf_pose
 
     def updated_kf_pose(self, kf_id: int):
-        Rwk, twk = self.initial_kf_pose_in_world(kf_id)
-        Dr, Dt = self.pose_correction(kf_id)
-        return utils_geometry.apply_pose_correction(Rwk, twk, Dr, Dt)
+        R0, t0 = self.initial_kf_pose(kf_id)
+        return geo.apply_pose_correction(R0, t0, *self.pose_correction(kf_id))
 
-    def updated_kf_pose_in_world(self, kf_id: int):
-        return self.updated_kf_pose(kf_id)
+    updated_kf_pose_in_world = updated_kf_pose
 
     def updated_kf_pose_from_key(self, kf_key):
         return self.updated_kf_pose(self.pose_key_to_id(kf_key))
 
     def all_kf_poses(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Batched `updated_kf_pose` for every keyframe: (K,3,3), (K,3,1) -- one so3_exp_map instead of a
-        per-keyframe Python loop (loss.py:764-774)."""
-        R = torch.matmul(self.Rwk, utils_geometry.so3_exp_map(self.rotation_corrections))
-        t = self.twk + self.translation_corrections
-        return R, t
+        """`updated_kf_pose` of every keyframe at once: (K,3,3), (K,3,1).  Rows listed in `locked_pose_indices` use
+        detached corrections, exactly like `pose_correction` -- so a batch that mixes samples of locked and unlocked
+        keyframes (the reference's track_window: unlock_pose, lock_all_pose_indices, unlock_pose_index) sends no
+        gradient into the locked ones."""
+        dr, dt = self.rotation_corrections, self.translation_corrections
+        if self.locked_pose_indices and (dr.requires_grad or dt.requires_grad):
+            frozen = torch.zeros(self.num_poses, dtype=torch.bool, device=dr.device)
+            frozen[sorted(self.locked_pose_indices)] = True
+            dr = torch.where(frozen[:, None], dr.detach(), dr)
+            dt = torch.where(frozen[:, None, None], dt.detach(), dt)
+        return torch.matmul(self.Rwk, geo.so3_exp_map(dr)), self.twk + dt
 
-    def zero_features(self):
-        for grid in self.features:
-            grid.zero_features()
-
-    def randn_features(self, std):
-        for grid in self.features:
-            grid.randn_features(std)
-
-    # ---- the hot path -----------------------------------------------------------------------------
-    def fused_spec(self):
-        """FieldSpec when the fused kernels apply (decoder fixed, 64-wide single hidden layer,
-        uniform channel count in {4,8,16}); None -> generic path."""
-        if self._spec_cache is not None:
-            return self._spec_cache if self._spec_cache != "no" else None
-        ok = (self.decoder is not None and self.decoder_type == "mlp" and self.pos_invariant
-              and self.decoder_hidden_dim == 64 and self.decoder_hidden_layers == 1 and self.decoder_out_dim == 1
-              and not any(p.requires_grad for p in self.decoder.parameters())
-              and (self.num_levels, self.fdim) in {(1, 4), (2, 4), (3, 4), (4, 4), (1, 8), (2, 8), (1, 16)}
-              and self.features[0].feature.is_cuda)
-        if not ok:
-            self._spec_cache = "no"
+    # ---- queries: the hot path ------------------------------------------------------------------------
+    def fused_spec(self) -> Optional[_field.FieldSpec]:
+        """Descriptor for the fused kernels, or None when they do not apply (trainable / non-64-wide / positional
+        decoder, unsupported (levels, channels), not on CUDA).  The cheap predicate is re-evaluated on every call
+        -- un-freezing the decoder or swapping it takes effect immediately -- and only the packed decoder weights
+        are cached, keyed on the identity and storage of the weight tensors."""
+        dec = self.decoder
+        if (dec is None or self.decoder_type != "mlp" or not self.pos_invariant or self.decoder_hidden_dim != 64
+                or self.decoder_hidden_layers != 1 or self.decoder_out_dim != 1
+                or (self.num_levels, self.fdim) not in FUSED_LEVEL_CHANNEL_SHAPES
+                or not self.features[0].feature.is_cuda or any(p.requires_grad for p in dec.parameters())):
             return None
-        mask = 0
-        for l in range(self.num_levels):
-            if self.ignore_level_[l]:
-                mask |= 1 << l
-        self._spec_cache = _field.FieldSpec(self._bound_host, _field.DecoderSpec.from_mlp(self.decoder), mask)
-        return self._spec_cache
+        key = tuple((id(p), p.data_ptr(), p._version) for p in dec.parameters())
+        if self._decoder_spec is None or self._decoder_spec[0] != key:
+            self._decoder_spec = (key, _field.DecoderSpec.from_mlp(dec))
+        return _field.FieldSpec(self._bound_host, self._decoder_spec[1], self._ignore_mask())
 
-    def level_tensors(self):
-        return [g.feature for g in self.features]
+    def _wants_graph(self, x: torch.Tensor) -> bool:
+        return torch.is_grad_enabled() and (x.requires_grad or any(f.requires_grad for f in self.level_tensors()))
 
-    def query_feature(self, x: torch.Tensor):
-        """grid_net.py:288-297."""
-        assert x.ndim == 2, f"Invalid input coords shape {x.shape}!"
-        assert x.shape[-1] == self.d
-        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(f.requires_grad for f in self.level_tensors()))
-        if (not needs_graph and self.fdim % 4 == 0 and self.fdim <= 16 and x.is_cuda):
-            mask = sum((1 << l) for l in range(self.num_levels) if self.ignore_level_[l])
-            return _field.field_features_raw(self.level_tensors(), self._bound_host, x, mask)
+    def _check_points(self, x: torch.Tensor):
+        assert x.ndim == 2 and x.shape[-1] == 3, f"Invalid input coords shape {tuple(x.shape)}!"
+
+    def query_feature(self, x: torch.Tensor) -> torch.Tensor:
+        """(N,3) -> (N, L*C) concatenated level features (grid_net.py:288-297): one fused launch when no autograd
+        graph is needed, the twice-differentiable per-level op otherwise."""
+        self._check_points(x)
+        if x.is_cuda and self.fdim in (4, 8, 12, 16) and not self._wants_graph(x):
+            return _field.field_features_raw(self.level_tensors(), self._bound_host, x, self._ignore_mask())
         return grid_interp_regular(self.features, x, self.ignore_level_)
 
-    def query_stability(self, x: torch.Tensor):
-        assert x.ndim == 2, f"Invalid input coords shape {x.shape}!"
-        assert x.shape[-1] == self.d
-        return grid_interp_regular(self.feature_stability, x, None)
+    def query_stability(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_points(x)
+        return grid_interp_regular(self.feature_stability, x)
 
-    def forward(self, x: torch.Tensor, noise_std=0):
-        """grid_net.py:306-325."""
-        spec = self.fused_spec()
-        if spec is not None:
-            needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(f.requires_grad for f in self.level_tensors()))
-            if needs_graph:
-                pred, _ = _field.fused_sdf(x, self.level_tensors(), spec)
-            else:
-                # inference / dense queries (utils_sdf.extract_fields): forward only, no Jacobian pass
-                sdf, _, _, _ = _field.sdf_forward_raw(self.level_tensors(), spec, x, want_jac=False, want_gradx=False)
-                pred = sdf.unsqueeze(1)
-        else:
-            feats = grid_interp_regular(self.features, x, self.ignore_level_)
-            pred = grid_decode(feats, x, self.decoder, self.pos_invariant)
-        if noise_std > 0:
-            pred = pred + torch.randn(pred.shape, device=x.device) * noise_std
-        return pred
-
-    def forward_with_gradient(self, x: torch.Tensor):
-        """(sdf (N,1), grad_x sdf (N,3)) from ONE fused launch; both outputs are differentiable wrt the
-        grids (the gradient output carries the eikonal double-backward)."""
+    def forward(self, x: torch.Tensor, noise_std=0) -> torch.Tensor:
+        """(N,3) -> (N,out) decoded prediction (grid_net.py:306-325)."""
         spec = self.fused_spec()
         if spec is None:
-            x = x if x.requires_grad else x.clone().requires_grad_(True)
-            y = self.forward(x)
-            g = torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), create_graph=True)[0]
-            return y, g
-        return _field.fused_sdf(x, self.level_tensors(), spec)
+            out = grid_decode(grid_interp_regular(self.features, x, self.ignore_level_), x, self.decoder,
+                              self.pos_invariant)
+        elif self._wants_graph(x):
+            out, _ = _field.fused_sdf(x, self.level_tensors(), spec)
+        else:   # inference / dense queries: values only, no Jacobian pass
+            out = _field.sdf_forward_raw(self.level_tensors(), spec, x, want_jac=False, want_gradx=False)[0].unsqueeze(1)
+        return out + torch.randn_like(out) * noise_std if noise_std > 0 else out
 
+    def forward_with_gradient(self, x: torch.Tensor):
+        """(sdf (N,1), grad_x sdf (N,3)) from ONE fused launch; both are differentiable w.r.t. the levels (the
+        gradient output carries the eikonal double-backward).  Falls back to autograd.grad over `forward`."""
+        spec = self.fused_spec()
+        if spec is not None:
+            return _field.fused_sdf(x, self.level_tensors(), spec)
+        xr = x if x.requires_grad else x.clone().requires_grad_(True)
+        y = self.forward(xr)
+        return y, torch.autograd.grad(y, xr, grad_outputs=torch.ones_like(y), create_graph=True)[0]
+
+    # ---- parameter groups (grid_net.py:327-351) ---------------------------------------------------------
     def params_for_poses(self):
         return [self.rotation_corrections, self.translation_corrections]
 
     def params_for_features(self, stop_level=None):
-        if stop_level is None:
-            stop_level = self.num_levels
-        assert stop_level <= self.num_levels
-        params = []
-        for level in range(stop_level):
-            params += list(self.features[level].parameters())
-        return params
+        stop = self.num_levels if stop_level is None else stop_level
+        assert stop <= self.num_levels
+        return [p for l in range(stop) for p in self.features[l].parameters()]
 
     def params_at_level(self, level):
-        """grid_net.py:339-351."""
-        params = []
-        target_levels = [level] if level < self.num_levels else range(self.num_levels)
-        for l in target_levels:
-            params += list(self.features[l].parameters())
-            params += list(self.feature_stability[l].parameters())
+        """Level `level`'s feature + stability tensors (every level when level == num_levels: the joint stage), plus
+        the decoder when trainable and the pose corrections when optimised."""
+        chosen = range(self.num_levels) if level >= self.num_levels else (level,)
+        out = [p for l in chosen for grid in (self.features[l], self.feature_stability[l]) for p in grid.parameters()]
         if not self.decoder_fixed:
-            params += list(self.decoder.parameters())
+            out += list(self.decoder.parameters())
         if self.optimize_pose:
-            params += self.params_for_poses()
-        return params
+            out += self.params_for_poses()
+        return out
 
 
+# ------------------------------------------------------------------------------------------------
+# many submaps
+# ------------------------------------------------------------------------------------------------
 class GridAtlas(BaseNet):
-    """N submaps + per-submap world pose (grid_atlas.py:18-587): the parts the alignment path uses.
-    Keyframe <-> submap maps are plain integer tables (bit-exact by construction)."""
+    """Submaps with a world pose each (+ se(3) correction parameters) and the integer keyframe <-> submap tables."""
 
     def __init__(self, cfg: dict, device="cuda:0", dtype=torch.float32):
         super().__init__(cfg, device, dtype)
-        self.cfg = cfg
-        self.submaps = torch.nn.ModuleList()
-        self.rotation_corrections = torch.nn.ParameterList()
-        self.translation_corrections = torch.nn.ParameterList()
-        self.R_world_submap_list = []
-        self.t_world_submap_list = []
-        self._submap_anchor_kf = []
-        self._kf_id_to_submap_id = []
-        self._submap_id_to_kf_ids = dict()
-        self.curr_submap_id = -1
-        self.curr_kf_id = -1
+        self.submaps = nn.ModuleList()
+        self.rotation_corrections = nn.ParameterList()
+        self.translation_corrections = nn.ParameterList()
+        self.R_world_submap_list: List[torch.Tensor] = []
+        self.t_world_submap_list: List[torch.Tensor] = []
+        self._submap_anchor_kf: List[int] = []
+        self._kf_id_to_submap_id: List[int] = []
+        self._submap_id_to_kf_ids: Dict[int, set] = {}
+        self.curr_submap_id = self.curr_kf_id = -1
         self.num_levels = cfg["grid"]["n_levels"]
-        self._coords_for_alignment = dict()
+        self.active_submaps = range(0)
+        self._coords_for_alignment: Dict[str, torch.Tensor] = {}
 
-    # ---- construction (grid_atlas.py:96-169) ------------------------------------------------------
-    def anchor_kf_for_submap(self, submap_id: int):
-        return self._submap_anchor_kf[submap_id]
-
-    def add_kf(self, Rsk: torch.Tensor, tsk: torch.Tensor):
-        assert Rsk.shape == (3, 3)
-        assert tsk.shape == (3, 1)
-        assert self.curr_submap_id >= 0, "No submap is created yet. Create a submap first."
-        submap_id = self.curr_submap_id
-        kf_id_global = self.curr_kf_id + 1
-        kf_id_submap = kf_id_global - self.anchor_kf_for_submap(self.curr_submap_id)
-        self._kf_id_to_submap_id.append(submap_id)
-        self.get_submap(submap_id).set_initial_kf_pose(kf_id_submap, Rsk, tsk, kf_key=f"KF{kf_id_global}")
-        self._submap_id_to_kf_ids[submap_id].add(kf_id_global)
-        self.curr_kf_id = kf_id_global
-        return kf_id_global
-
-    def add_submap(self, local_bound: torch.Tensor, Rws: torch.Tensor, tws: torch.Tensor, num_poses=1,
-                   optimize_poses=True):
-        assert Rws.shape == (3, 3)
-        assert tws.shape == (3, 1)
-        submap_id = len(self.submaps)
-        cfg_model = deepcopy(self.cfg)
-        cfg_model["grid"]["bound"] = local_bound.numpy()
-        cfg_model["pose"]["num_poses"] = num_poses
-        cfg_model["pose"]["optimize"] = optimize_poses
-        self.submaps.append(GridNet(cfg=cfg_model, device=self.device, dtype=self.dtype))
-        self.R_world_submap_list.append(Rws.to(self.device))
-        self.t_world_submap_list.append(tws.to(self.device))
-        anchor_kf = self.curr_kf_id + 1
-        self._submap_anchor_kf.append(anchor_kf)
-        self.rotation_corrections.append(torch.nn.Parameter(torch.zeros(1, 3).float().to(self.device),
-                                                            requires_grad=True))
-        self.translation_corrections.append(torch.nn.Parameter(torch.zeros(3, 1).float().to(self.device),
-                                                               requires_grad=True))
-        self.active_submaps = range(self.num_submaps)
-        self.curr_submap_id = submap_id
-        self._submap_id_to_kf_ids[submap_id] = set()
-        self._submap_id_to_kf_ids[submap_id].add(anchor_kf)
-
-    def add_existing_submap(self, submap: GridNet, Rws: torch.Tensor, tws: torch.Tensor):
-        """Attach an already-built GridNet (multi-GPU build_submaps gathers submaps to rank 0 in id order,
-        grid_atlas.py:145-150)."""
-        self.submaps.append(submap)
-        self.R_world_submap_list.append(Rws.to(self.device))
-        self.t_world_submap_list.append(tws.to(self.device))
-        self._submap_anchor_kf.append(self.curr_kf_id + 1)
-        self.rotation_corrections.append(torch.nn.Parameter(torch.zeros(1, 3).float().to(self.device)))
-        self.translation_corrections.append(torch.nn.Parameter(torch.zeros(3, 1).float().to(self.device)))
-        self.active_submaps = range(self.num_submaps)
-        self.curr_submap_id = len(self.submaps) - 1
-        self._submap_id_to_kf_ids[self.curr_submap_id] = set()
-
-    def set_submap_pose(self, submap_id: int, Rws: torch.Tensor, tws: torch.Tensor):
-        """grid_atlas.py:171-187 (also resets the corrections to zero)."""
-        assert Rws.shape == (3, 3)
-        assert tws.shape == (3, 1)
-        with torch.no_grad():
-            self.R_world_submap_list[submap_id].copy_(Rws.to(self.device))
-            self.t_world_submap_list[submap_id].copy_(tws.to(self.device))
-            self.rotation_corrections[submap_id].zero_()
-            self.translation_corrections[submap_id].zero_()
-
-    def set_submap_pose_correction(self, submap_id: int, R_delta: torch.Tensor, t_delta: torch.Tensor):
-        assert R_delta.shape == (1, 3)
-        assert t_delta.shape == (3, 1)
-        with torch.no_grad():
-            self.rotation_corrections[submap_id].copy_(R_delta)
-            self.translation_corrections[submap_id].copy_(t_delta)
-
+    # ---- bookkeeping ------------------------------------------------------------------------------------
     @property
-    def num_submaps(self):
+    def num_submaps(self) -> int:
         return len(self.submaps)
 
     @property
-    def num_keyframes(self):
+    def num_keyframes(self) -> int:
         return self.curr_kf_id + 1
 
-    def submap_id_for_kf(self, kf_id: int):
+    def get_submap(self, submap_id: int) -> GridNet:
+        assert 0 <= submap_id < self.num_submaps
+        return self.submaps[submap_id]
+
+    def anchor_kf_for_submap(self, submap_id: int) -> int:
+        return self._submap_anchor_kf[submap_id]
+
+    def submap_id_for_kf(self, kf_id: int) -> int:
         return self._kf_id_to_submap_id[kf_id]
 
     def submap_id_for_kf_batch(self, kf_ids: torch.Tensor) -> torch.Tensor:
-        """grid_atlas.py:226-236: integer gather."""
-        table = torch.tensor(self._kf_id_to_submap_id, device=kf_ids.device)
-        return table[kf_ids]
+        """Integer gather through the keyframe -> submap table (grid_atlas.py:226-236)."""
+        return torch.as_tensor(self._kf_id_to_submap_id, device=kf_ids.device)[kf_ids]
 
-    def updated_kf_pose_in_submap(self, kf_id: int, submap_id: int):
-        """grid_atlas.py:286-300."""
-        expect_submap_id = self.submap_id_for_kf(kf_id)
-        assert expect_submap_id == submap_id, f"Wrong submap for KF {kf_id}! Expect {expect_submap_id}, got {submap_id}."
-        kf_id_submap = kf_id - self.anchor_kf_for_submap(submap_id)
-        return self.get_submap(submap_id).updated_kf_pose(kf_id_submap)
+    def _register_submap(self, net: GridNet, Rws, tws):
+        if tuple(Rws.shape) != (3, 3) or tuple(tws.shape) != (3, 1):
+            raise AssertionError("submap pose must be R (3,3), t (3,1)")
+        sid = self.num_submaps
+        self.submaps.append(net)
+        dev = self.device
+        self.R_world_submap_list += [Rws.to(dev)]
+        self.t_world_submap_list += [tws.to(dev)]
+        self.rotation_corrections.append(nn.Parameter(torch.zeros(1, 3, device=dev)))
+        self.translation_corrections.append(nn.Parameter(torch.zeros(3, 1, device=dev)))
+        first_kf = self.curr_kf_id + 1
+        self._submap_anchor_kf.append(first_kf)
+        self._submap_id_to_kf_ids[sid] = set()
+        self.active_submaps = range(self.num_submaps)
+        self.curr_submap_id = sid
+        return sid, first_kf
+
+    def add_submap(self, local_bound: torch.Tensor, Rws: torch.Tensor, tws: torch.Tensor, num_poses=1,
+                   optimize_poses=True):
+        """New empty submap over `local_bound` posed at (Rws, tws) (grid_atlas.py:120-169)."""
+        sub_cfg = copy.deepcopy(self.cfg)
+        sub_cfg["grid"]["bound"] = np.asarray(local_bound)
+        sub_cfg["pose"].update(num_poses=num_poses, optimize=optimize_poses)
+        sid, first_kf = self._register_submap(GridNet(cfg=sub_cfg, device=self.device, dtype=self.dtype), Rws, tws)
+        self._submap_id_to_kf_ids[sid].add(first_kf)
+
+    def add_existing_submap(self, submap: GridNet, Rws: torch.Tensor, tws: torch.Tensor):
+        """Attach a GridNet built elsewhere (multi-GPU build_submaps gathers them to rank 0 in id order)."""
+        self._register_submap(submap, Rws, tws)
+
+    def add_kf(self, Rsk: torch.Tensor, tsk: torch.Tensor) -> int:
+        """Next global keyframe, posed (Rsk, tsk) inside the CURRENT submap (grid_atlas.py:96-118)."""
+        assert self.curr_submap_id >= 0, "No submap is created yet. Create a submap first."
+        sid, kf = self.curr_submap_id, self.curr_kf_id + 1
+        self.get_submap(sid).set_initial_kf_pose(kf - self._submap_anchor_kf[sid], Rsk, tsk, kf_key=f"KF{kf}")
+        self._kf_id_to_submap_id.append(sid)
+        self._submap_id_to_kf_ids[sid].add(kf)
+        self.curr_kf_id = kf
+        return kf
+
+    # ---- submap poses -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def set_submap_pose(self, submap_id: int, Rws: torch.Tensor, tws: torch.Tensor):
+        """Overwrite the initial pose and reset the correction to zero (grid_atlas.py:171-187)."""
+        if tuple(Rws.shape) != (3, 3) or tuple(tws.shape) != (3, 1):
+            raise AssertionError("submap pose must be R (3,3), t (3,1)")
+        R0, t0 = self.initial_submap_pose(submap_id)
+        R0.copy_(Rws.to(R0))
+        t0.copy_(tws.to(t0))
+        for corr in self.params_for_submap_pose(submap_id):
+            corr.zero_()
+
+    @torch.no_grad()
+    def set_submap_pose_correction(self, submap_id: int, R_delta: torch.Tensor, t_delta: torch.Tensor):
+        if tuple(R_delta.shape) != (1, 3) or tuple(t_delta.shape) != (3, 1):
+            raise AssertionError("correction must be w (1,3), tau (3,1)")
+        w, tau = self.params_for_submap_pose(submap_id)
+        w.copy_(R_delta)
+        tau.copy_(t_delta)
 
     def initial_submap_pose(self, submap_id: int):
         return self.R_world_submap_list[submap_id], self.t_world_submap_list[submap_id]
 
     def updated_submap_pose(self, submap_id: int, device=None):
-        """grid_atlas.py:250-268."""
-        R, t = self.initial_submap_pose(submap_id)
-        R, t = utils_geometry.apply_pose_correction(R=R, t=t, R_delta=self.rotation_corrections[submap_id],
-                                                    t_delta=self.translation_corrections[submap_id])
-        if device is not None:
-            R, t = R.to(device), t.to(device)
-        return R, t
+        """(R0 Exp(w), t0 + tau) of one submap (grid_atlas.py:250-268); stays in the autograd graph."""
+        R, t = geo.apply_pose_correction(*self.initial_submap_pose(submap_id), self.rotation_corrections[submap_id],
+                                         self.translation_corrections[submap_id])
+        return (R, t) if device is None else (R.to(device), t.to(device))
 
     def params_for_submap_pose(self, submap_id: int):
         return [self.rotation_corrections[submap_id], self.translation_corrections[submap_id]]
 
-    def get_submap(self, submap_id: int) -> GridNet:
-        assert submap_id >= 0 and submap_id < self.num_submaps
-        return self.submaps[submap_id]
+    def updated_kf_pose_in_submap(self, kf_id: int, submap_id: int):
+        owner = self.submap_id_for_kf(kf_id)
+        assert owner == submap_id, f"Wrong submap for KF {kf_id}! Expect {owner}, got {submap_id}."
+        return self.get_submap(submap_id).updated_kf_pose(kf_id - self._submap_anchor_kf[submap_id])
 
-    def _fused_query_ok(self, x_world):
+    # ---- queries ------------------------------------------------------------------------------------------
+    def _world_to_submap_rows(self) -> torch.Tensor:
+        """(S,12) rows [R^T row-major | -R^T t]: the world -> submap transform of every submap."""
+        rows = []
+        for sid in range(self.num_submaps):
+            R, t = self.updated_submap_pose(sid)
+            rows.append(torch.cat([R.T.reshape(9), (-R.T @ t).reshape(3)]))
+        return torch.stack(rows).float().contiguous()
+
+    def _one_launch_query_ok(self, x_world: torch.Tensor) -> bool:
+        subs = list(self.submaps)
         if not x_world.is_cuda or len(self.active_submaps) == 0:
             return False
         if torch.is_grad_enabled() and (x_world.requires_grad or any(
-                f.requires_grad for i in self.active_submaps for f in self.get_submap(i).level_tensors())):
+                f.requires_grad for sid in self.active_submaps for f in subs[sid].level_tensors())):
             return False
-        subs = [self.get_submap(i) for i in range(self.num_submaps)]
-        return all(sm.fdim == 4 and sm.num_levels == subs[0].num_levels and sm.num_levels <= 4 and
-                   sm.features[0].feature.is_cuda for sm in subs)
+        L = subs[0].num_levels
+        return L <= 4 and all(s.fdim == 4 and s.num_levels == L and s.features[0].feature.is_cuda for s in subs)
 
-    def query_feature(self, x_world: torch.Tensor):
-        """grid_atlas.py:374-391: in-bound-masked mean of the submaps' features at world points.  Without autograd
-        (fusion / meshing queries) every submap is visited inside ONE launch (miso_atlas_features)."""
-        if self._fused_query_ok(x_world):
-            import ctypes as C
+    def query_feature(self, x_world: torch.Tensor) -> torch.Tensor:
+        """Mean over the active submaps whose bound contains the point of that submap's features
+        (grid_atlas.py:374-391).  Without autograd all submaps are visited inside one launch."""
+        if self._one_launch_query_ok(x_world):
             from . import _lib
-            lib = _lib.load()
-            dev = x_world.device
-            key = tuple((f.data_ptr(), tuple(f.stride())) for i in range(self.num_submaps)
-                        for f in self.get_submap(i).level_tensors()) + tuple(
-                tuple(self.get_submap(i).ignore_level_) for i in range(self.num_submaps))
-            cache = getattr(self, "_atlas_fields_cache", None)
-            if cache is None or cache[0] != key:
-                fields = []
-                for i in range(self.num_submaps):
-                    sm = self.get_submap(i)
-                    mask = sum((1 << l) for l in range(sm.num_levels) if sm.ignore_level_[l])
-                    fields.append(_field.make_field(sm.level_tensors(), sm._bound_host, None, mask))
-                cache = (key, _field.structs_to_device(fields, dev))
-                self._atlas_fields_cache = cache
+            lib, dev, subs = _lib.load(), x_world.device, list(self.submaps)
+            key = tuple((f.data_ptr(), f.stride()) for s in subs for f in s.level_tensors()) + tuple(
+                s._ignore_mask() for s in subs)
+            cached = getattr(self, "_atlas_fields_cache", None)
+            if cached is None or cached[0] != key:
+                descr = [_field.make_field(s.level_tensors(), s._bound_host, None, s._ignore_mask()) for s in subs]
+                cached = self._atlas_fields_cache = (key, _field.structs_to_device(descr, dev))
             with torch.no_grad():
-                poses = []
-                for i in range(self.num_submaps):
-                    R, t = self.updated_submap_pose(i)
-                    Rt_ = R.T                                        # transfrom_points_from (utils_geometry.py:227-240)
-                    poses.append(torch.cat([Rt_.reshape(9), (-Rt_ @ t).reshape(3)]))
-                poses = torch.stack(poses, 0).contiguous().float()
+                rows = self._world_to_submap_rows()
             active = torch.tensor(list(self.active_submaps), dtype=torch.int32, device=dev)
             x = _field._prep_x(x_world)
-            L = self.get_submap(0).num_levels
+            L = subs[0].num_levels
             out = torch.empty((x.shape[0], 4 * L), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(lib.miso_atlas_features(cache[1].data_ptr(), self.num_submaps, active.data_ptr(),
-                                                   int(active.numel()), poses.data_ptr(), x.data_ptr(), x.shape[0], L,
-                                                   out.data_ptr(), _lib.stream_ptr(dev)), "atlas_features")
+                _lib.check(lib.miso_atlas_features(cached[1].data_ptr(), len(subs), active.data_ptr(), active.numel(),
+                                                   rows.data_ptr(), x.data_ptr(), x.shape[0], L, out.data_ptr(),
+                                                   _lib.stream_ptr(dev)), "atlas_features")
             return out
-        sum_feats = 0
-        sum_weights = 0
-        for submap_id in self.active_submaps:
-            submap = self.get_submap(submap_id)
-            R_world_submap, t_world_submap = self.updated_submap_pose(submap_id)
-            x_submap = utils_geometry.transfrom_points_from(x_world, R_world_submap, t_world_submap)
-            mask_bnd = utils_geometry.coords_in_bound(x_submap, submap.bound)
-            submap_feats = submap.query_feature(x_submap)
-            sum_feats = sum_feats + mask_bnd * submap_feats
-            sum_weights = sum_weights + mask_bnd
-        sum_weights = torch.where(sum_weights == 0, torch.ones_like(sum_weights), sum_weights).float()
-        return sum_feats / sum_weights
+        total, hits = 0, 0
+        for sid in self.active_submaps:
+            sub = self.get_submap(sid)
+            x_local = geo.transfrom_points_from(x_world, *self.updated_submap_pose(sid))
+            inside = geo.coords_in_bound(x_local, sub.bound)
+            total = total + inside * sub.query_feature(x_local)
+            hits = hits + inside
+        return total / torch.where(hits == 0, torch.ones_like(hits), hits).float()
 
-    def forward(self, x_world: torch.Tensor, noise_std=0):
-        """grid_atlas.py:393-399: decode the mean feature with submap 0's decoder."""
-        mean_feats = self.query_feature(x_world)
-        pred = grid_decode(mean_feats, None, self.submaps[0].decoder, True)
-        if noise_std > 0:
-            pred = pred + torch.randn(pred.shape, device=x_world.device) * noise_std
-        return pred
+    def forward(self, x_world: torch.Tensor, noise_std=0) -> torch.Tensor:
+        """Decode the mean feature with submap 0's decoder (grid_atlas.py:393-399)."""
+        out = grid_decode(self.query_feature(x_world), None, self.submaps[0].decoder, True)
+        return out + torch.randn_like(out) * noise_std if noise_std > 0 else out
 
+    # ---- alignment support ------------------------------------------------------------------------------------
     def check_submap_intersection(self, src_id: int, dst_id: int, overlap_thresh=1e-2):
-        """grid_atlas.py:405-420 (torch ops; the batched kernel version lives in miso_b200.align)."""
-        submap_src = self.get_submap(src_id)
-        submap_dst = self.get_submap(dst_id)
-        corners_src = submap_src.features[-1].vertex_positions().to(self.device)
-        R_world_src, t_world_src = self.updated_submap_pose(src_id)
-        R_world_dst, t_world_dst = self.updated_submap_pose(dst_id)
-        corners_world = utils_geometry.transform_points_to(corners_src, R_world_src, t_world_src)
-        corners_dst = utils_geometry.transfrom_points_from(corners_world, R_world_dst, t_world_dst)
-        mask_bnd = utils_geometry.coords_in_bound(corners_dst, submap_dst.bound)
-        num_valid = torch.count_nonzero(mask_bnd)
-        return num_valid / corners_src.shape[0] > overlap_thresh
+        """Share of src's finest-level voxel centres that land inside dst's bound > thresh (grid_atlas.py:405-420).
+        Torch ops; `miso_b200.align` runs the batched kernel version inside the alignment loop."""
+        centres = self.get_submap(src_id).features[-1].vertex_positions().to(self.device)
+        in_world = geo.transform_points_to(centres, *self.updated_submap_pose(src_id))
+        in_dst = geo.transfrom_points_from(in_world, *self.updated_submap_pose(dst_id))
+        inside = geo.coords_in_bound(in_dst, self.get_submap(dst_id).bound)
+        return torch.count_nonzero(inside) / centres.shape[0] > overlap_thresh
 
     def precompute_coordinates_for_alignment(self, norm_thresh=1e-5):
-        """grid_atlas.py:565-579: voxel centres of every level whose feature norm exceeds the threshold,
-        in the reference's flatten order (Z,Y,X with X fastest)."""
-        self._coords_for_alignment = dict()
+        """Per (submap, level): the voxel centres of that level whose full feature vector has norm > thresh, in
+        (Z,Y,X) order with X fastest (grid_atlas.py:565-579)."""
+        self._coords_for_alignment = {}
         for level in range(self.num_levels):
-            for submap_id in range(self.num_submaps):
-                submap = self.get_submap(submap_id)
-                coords = submap.features[level].vertex_positions().to(self.device)
+            for sid, sub in enumerate(self.submaps):
+                centres = sub.features[level].vertex_positions().to(self.device)
                 with torch.no_grad():
-                    feature = submap.query_feature(coords)
-                featnorm_from = torch.linalg.norm(feature, dim=1, keepdim=True).detach()
-                mask_feat = featnorm_from > norm_thresh
-                valid_indices = torch.nonzero(mask_feat, as_tuple=False)[:, 0]
-                self._coords_for_alignment[f"submap{submap_id}_level{level}"] = coords[valid_indices, :].detach()
+                    strength = torch.linalg.norm(sub.query_feature(centres), dim=1)
+                keep = torch.nonzero(strength > norm_thresh)[:, 0]
+                self._coords_for_alignment[f"submap{sid}_level{level}"] = centres[keep].detach()
 
-    def coordinates_for_alignment(self, submap_id: int, level: int):
-        assert submap_id >= 0 and submap_id < self.num_submaps
-        assert level >= 0 and level < self.num_levels
-        key = f"submap{submap_id}_level{level}"
-        if key not in self._coords_for_alignment:
+    def coordinates_for_alignment(self, submap_id: int, level: int) -> torch.Tensor:
+        assert 0 <= submap_id < self.num_submaps and 0 <= level < self.num_levels
+        try:
+            return self._coords_for_alignment[f"submap{submap_id}_level{level}"]
+        except KeyError:
             raise ValueError(f"Coordinates for alignment not found for submap {submap_id} and level {level}. "
-                             "Did you call precompute_coordinates_for_alignment()?")
-        return self._coords_for_alignment[key]
+                             "Did you call precompute_coordinates_for_alignment()?") from None

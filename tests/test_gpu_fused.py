@@ -385,3 +385,61 @@ def test_mapping_step_other_level_channel_shapes(n_levels, fdim, scale):
         assert rel_err(ld[k], lo[k]) < TOL_G, k
     for l in range(n_levels):
         assert rel_err(net.features[l].feature.grad, o2.features[l].grad) < TOL_G, l
+
+
+def test_unregistered_keyframe_id_is_loud():
+    """a sample whose keyframe id has no 'KF<id>' key (or lies outside the table) must not train with
+    some other keyframe's pose.  `compute` raises the reference's assertion (grid_net.py:243); the trainer's sync-free
+    step returns a NaN loss (kernel poison word) -- and recovers on the next clean batch."""
+    from miso_b200.loss import MisoLossMapping
+    net, _, _ = make_pair(num_poses=6)
+    mi, gt, (R, t) = _batch(3000)
+    for k in (0, 1, 3):                                  # keyframe 2 is never registered
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=None)
+    assert (mi["sample_frame_ids"] == 2).any()
+    with pytest.raises(AssertionError, match="Key KF2 not found"):
+        L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    terms = L.step_into_grads(net, _to_cuda(mi), _to_cuda(gt))
+    assert torch.isnan(terms).all()
+    bad = {k: v.clone() for k, v in mi.items()}
+    bad["sample_frame_ids"][bad["sample_frame_ids"] == 2] = 77      # outside the table
+    with pytest.raises(AssertionError, match="Key KF77 not found"):
+        L.compute(net, _to_cuda(bad), _to_cuda(gt))
+    assert torch.isnan(L.step_into_grads(net, _to_cuda(bad), _to_cuda(gt))).all()
+    ok = {k: v.clone() for k, v in mi.items()}
+    ok["sample_frame_ids"][ok["sample_frame_ids"] == 2] = 3
+    assert torch.isfinite(L.step_into_grads(net, _to_cuda(ok), _to_cuda(gt))).all()
+
+
+def test_locked_keyframes_get_no_pose_gradient_in_mixed_batches():
+    """ADVICE r01 / grid_net.py:209-215: unlock_pose(); lock_all_pose_indices(); unlock_pose_index(k) -- the
+    reference's track_window pattern -- must send pose gradients to keyframe k only, although the batch holds
+    samples of every keyframe; values against the oracle's per-keyframe restatement."""
+    from miso_b200.loss import MisoLossMapping
+    net, o1, _ = make_pair(num_poses=4)
+    mi, gt, (R, t) = _batch(3000)
+    for k in range(4):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.lock_feature()
+    net.unlock_pose()
+    net.lock_all_pose_indices()
+    net.unlock_pose_index(2)
+    L = MisoLossMapping(loss_type="L2", weight_sdf=1.0, weight_eik=0.0, weight_fs=0.5, trunc_dist=0.15)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    sum(ld.values()).backward()
+    gr, gtr = net.rotation_corrections.grad, net.translation_corrections.grad
+    for k in (0, 1, 3):
+        assert torch.count_nonzero(gr[k]) == 0 and torch.count_nonzero(gtr[k]) == 0
+    assert torch.count_nonzero(gr[2]) > 0 and torch.count_nonzero(gtr[2]) > 0
+    # oracle: keyframe 2's pose through (w, tau) with autograd, the others constant
+    w = torch.zeros(1, 3, requires_grad=True)
+    tau = torch.zeros(3, 1, requires_grad=True)
+    poses = {k: (R[k], t[k]) for k in range(4)}
+    poses[2] = O.apply_pose_correction(R[2], t[2], w, tau)
+    lo = O.mapping_loss(o1, mi, gt, poses, "L2", 1.0, 0.0, 0.5, 0.15)
+    sum(lo.values()).backward()
+    assert rel_err(gr[2], w.grad[0]) < TOL_G and rel_err(gtr[2], tau.grad) < TOL_G
