@@ -48,7 +48,18 @@ elif os.environ.get("MISO_TC", "") == "1":
 else:
     KERNEL_NAME = "mapping_step_tc2_kernel<2,4,%s,%s> (two threads per point) (+finalize)" % (
         os.environ.get("MISO_TC2_GROUPS", "4"), "unpaired" if os.environ.get("MISO_PAIR", "1") == "0" else "paired")
-NCU_DRAM_BYTES_PER_LAUNCH = 120334336 + 12498688     # profiles/r01_ncu_mapping_step_tc2.csv (2^20 points)
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json is written by tools/ncu_summary.py from
+    the .ncu-rep; a profiler cannot run inside the timed region).  None when no capture of that workload exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as fh:
+        d = json.load(fh).get(key)
+    return (d["dram_bytes_per_launch"], d["source"]) if d else (None, None)
 
 
 def measured_hbm_peak():
@@ -117,16 +128,29 @@ def workload_config(world):
                          "(~360 MB/step touched) exceed the 126 MB L2"}
 
 
-def make_host_batches(seed0):
+def host_batch(seed0, b, poses=None):
+    """Batch `b` of rank `seed0` (CPU tensors, reference dict layout) -- the GPU arm and the CPU arm draw from here, so
+    rank 0's batch 0 is the same tensor set on both."""
     from miso_b200 import synth
-    batches = []
-    poses = synth.keyframe_poses(NUM_KF, synth.SCANNET_SUBMAP_BOUND, seed=55 + seed0)
+    poses = poses if poses is not None else synth.keyframe_poses(NUM_KF, synth.SCANNET_SUBMAP_BOUND, seed=55 + seed0)
+    mi, gt, _ = synth.rgbd_batch(N_POINTS, num_kf=NUM_KF, seed=1000 * seed0 + b, poses=poses)
+    return mi, gt, poses
+
+
+def make_host_batches(seed0):
+    batches, poses = [], None
     for b in range(NUM_HOST_BATCHES):
-        mi, gt, _ = synth.rgbd_batch(N_POINTS, num_kf=NUM_KF, seed=1000 * seed0 + b, poses=poses)
+        mi, gt, poses = host_batch(seed0, b, poses)
         mi = {k: v.pin_memory() for k, v in mi.items()}
         gt = {k: v.pin_memory() for k, v in gt.items()}
         batches.append((mi, gt))
     return batches, poses
+
+
+def initial_features(shapes, seed):
+    """Seeded N(0, 1e-2) level tensors: the same values for the product model and the CPU arm's model."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(tuple(s), generator=g) * 1e-2 for s in shapes]
 
 
 def build_model(device, poses, seed):
@@ -134,10 +158,9 @@ def build_model(device, poses, seed):
     from miso_b200.models import GridNet
     cfg = synth.model_cfg(synth.SCANNET_SUBMAP_BOUND, num_poses=NUM_KF)
     net = GridNet(cfg, device=device)
-    g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
-        for lvl in net.features:
-            lvl.feature.copy_((torch.randn(lvl.feature.shape, generator=g) * 1e-2).to(device))
+        for lvl, f in zip(net.features, initial_features([l.feature.shape for l in net.features], seed)):
+            lvl.feature.copy_(f.to(device))
     net.decoder.load_state_dict(synth.decoder_weights(8, seed=0))
     R, t = poses
     for k in range(R.shape[0]):
@@ -197,8 +220,11 @@ def run_ours(args):
         return float(t.item())
 
     # ---------------- device-resident value ----------------
+    first_terms = None
     for i in range(args.warmup):
-        trainer.train_step(*dev_batches[i % NUM_HOST_BATCHES])
+        terms = trainer.train_step(*dev_batches[i % NUM_HOST_BATCHES])
+        if i == 0:
+            first_terms = [float(v) for v in terms.tolist()]   # loss of batch 0 at the initial parameters
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -265,10 +291,13 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None   # sampled across all timed regions (value + e2e + e2e_compact)
     assert torch.isfinite(loss_host[args.warmup:]).all(), "non-finite loss in the compact e2e run"
 
-    align = None
+    align, ncd, torch_gpu = None, None, None
     if not args.no_extras:
         del dev_batches
         torch.cuda.empty_cache()
+        if world == 1:
+            ncd = bench_ncd(device, steps=max(100, min(args.steps, 200)))
+            torch_gpu = torch_gpu_arm(device)
         align = bench_align(device, iters=10, warmup=2, world=world, rank=rank)
         if world > 1:
             # pair-sharded: an iteration ends when the slowest rank is done
@@ -303,10 +332,11 @@ def run_ours(args):
         "host_numa_node_rank0": numa_node,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("scannet_2p20")[0],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                       "kernel at this size (profiles/r01_ncu_mapping_step_tc2.csv); below the algorithmic "
-                                       "bytes because the 64 MB grid and its gradient stay L2-resident",
+                                       "kernel at this size (%s); below the algorithmic bytes because the 64 MB grid and "
+                                       "its gradient stay L2-resident" % ncu_traffic("scannet_2p20")[1],
                      "bytes_per_point": BYTES_PER_POINT, "survey_bytes_per_point": SURVEY_BYTES_PER_POINT,
                      "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
                      "fp32_equiv_tflops_achieved": FLOPS_PER_POINT * N_POINTS / (kms * 1e-3) / 1e12,
@@ -314,12 +344,22 @@ def run_ours(args):
                      "floors_ms": {"red_v4_scatter_only": 0.121, "gather_only": 0.041,
                                    "source": "profiles/r01_scatter_probe.json (benchmarks/scatter_probe.py, same batch)"}},
         "final_loss_terms": final_loss,
-        "extra": {"align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
+        "extra": {"ncd": ncd, "torch_gpu_baseline": torch_gpu, "align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
                   "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "
                   "<= 32 k samples/pair, level 1: <= 4 M samples/pair"},
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_arm(steps=2, warmup=1)
+        cb = cpu_reference_arm(steps=2, warmup=1)
+        # same batch, same initial parameters on both arms: the CPU arm's first step doubles as a full-size
+        # (2^20-point) value check of the kernel's loss terms (the CPU arm is the checker here, never the product)
+        want = cb.pop("first_step_terms")
+        got = {"sdf_L1": first_terms[0], "free_space": first_terms[1], "eik": first_terms[2], "total": first_terms[3]}
+        rel = {k: abs(got[k] - want[k]) / max(abs(want[k]), 1e-12) for k in want}
+        line["parity_check"] = {"what": "loss terms of rank 0's batch 0 (2^20 points) at the initial parameters: fused CUDA "
+                                        "step vs the CPU arm's first step on the same tensors", "cuda": got, "cpu": want,
+                                "rel_err": rel, "tolerance": 1e-5, "ok": max(rel.values()) <= 1e-5}
+        assert line["parity_check"]["ok"], line["parity_check"]
+        line["cpu_baseline"] = cb
         if not args.no_extras:
             line["extra"]["align_cpu_baseline"] = cpu_align_arm(iters=1)
     print(json.dumps(line), flush=True)
@@ -327,39 +367,46 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_reference_arm(steps, warmup, sample_points=1 << 18):
-    """The reference's CPU path for the SAME step (oracle port: identical torch ops to
-    grid_opt/loss.py:754-813 + torch.optim.Adam; the second-order eikonal goes through the gather
-    restatement because F.grid_sample has no double backward on CPU), on a bounded
-    sample of the workload: full-size grids, `sample_points` of the 2^20 points per step."""
+def cpu_reference_arm(steps, warmup, sample_points=N_POINTS):
+    """The reference's CPU path for the SAME step on the SAME inputs (oracle port: identical torch ops to
+    grid_opt/loss.py:754-813 + torch.optim.Adam; the second-order eikonal goes through the gather restatement
+    because F.grid_sample has no double backward on CPU): rank 0's batch 0, all 2^20
+    points, the full-size grids, the product arm's initial parameters.  Bounded by the step count, not by
+    shrinking the workload."""
     from miso_b200 import synth
     from oracle import oracle as O
     torch.set_num_threads(os.cpu_count())
     shapes = O.level_shapes(synth.SCANNET_SUBMAP_BOUND, 0.5, 5, 2, 4)
-    g = torch.Generator().manual_seed(0)
-    feats = [torch.randn(s, generator=g) * 1e-2 for s in shapes]
+    feats = initial_features(shapes, 0)
     dec = O.make_decoder(8)
     dec.load_state_dict({k.replace("network.", ""): v for k, v in synth.decoder_weights(8).items()})
     model = O.OracleGridNet(synth.SCANNET_SUBMAP_BOUND, feats, dec, second_order=True)
-    mi, gt, (R, t) = synth.rgbd_batch(sample_points, num_kf=NUM_KF, seed=0)
+    mi, gt, (R, t) = host_batch(0, 0)
+    if sample_points < N_POINTS:
+        mi = {k: v[:, :sample_points] for k, v in mi.items()}
+        gt = {k: v[:, :sample_points] for k, v in gt.items()}
     poses = {k: (R[k], t[k]) for k in range(R.shape[0])}
     opt = torch.optim.Adam(list(model.features.parameters()), lr=1e-3)
-    times = []
+    times, first = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
         ld = O.mapping_loss(model, mi, gt, poses, LOSS_CFG["loss_type"], LOSS_CFG["weight_sdf"], LOSS_CFG["weight_eik"],
                             LOSS_CFG["weight_fs"], LOSS_CFG["trunc_dist"], grad_method="autograd", eik_trunc_dist=None)
-        sum(ld.values()).backward()
+        total = sum(ld.values())
+        total.backward()
         opt.step()
+        if i == 0:   # unweighted terms + weighted total, the layout of the kernel's loss_out
+            first = {"sdf_L1": float(ld["sdf_L1"]) / LOSS_CFG["weight_sdf"], "free_space": float(ld["free_space"]) / LOSS_CFG["weight_fs"],
+                     "eik": float(ld["eik"]) / LOSS_CFG["weight_eik"], "total": float(total)}
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
     return {"value": sample_points / sec, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{sample_points} of the 2^20 points/step on the full-size grids, {steps} timed steps "
-                      f"(+{warmup} warm-up), loss+backward+Adam; Adam sweeps the full dense grids as in the reference",
-            "sec_per_step": sec}
-
+            "sample": f"all {sample_points} points/step of rank 0's batch 0 on the full-size grids (same config as the "
+                      f"product arm), {steps} timed steps (+{warmup} warm-up), loss+backward+Adam; Adam sweeps the full "
+                      "dense grids as in the reference",
+            "sec_per_step": sec, "first_step_terms": first}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -484,6 +531,133 @@ def cpu_align_arm(iters=1):
             "sample": "level 0 only (M0 = 32000 samples/pair, 120 pairs, intersection test skipped), 1 iteration"}
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: Newer-College-quad grid, 2^22 LiDAR points per step (the size the 0.6 target is quoted on)
+# ------------------------------------------------------------------------------------------------
+NCD_POINTS = 1 << 22
+NCD_KF = 8
+NCD_LOSS = dict(loss_type="L2", weight_sdf=1.0, weight_eik=0.0, weight_fs=0.5, trunc_dist=0.5)   # ncd_quad.yaml:42-46
+
+
+def build_ncd_model(device, poses):
+    from miso_b200 import synth
+    from miso_b200.models import GridNet
+    cfg = synth.model_cfg(synth.NCD_QUAD_BOUND, base_cell_size=1.0, per_level_scale=5, num_poses=NCD_KF)
+    net = GridNet(cfg, device=device)
+    with torch.no_grad():
+        for lvl, f in zip(net.features, initial_features([l.feature.shape for l in net.features], 0)):
+            lvl.feature.copy_(f.to(device))
+    net.decoder.load_state_dict(synth.decoder_weights(8, seed=0))
+    R, t = poses
+    for k in range(NCD_KF):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    return net
+
+
+def bench_ncd(device, steps=100, warmup=5):
+    """One GPU: fused step + Adam on the NCD quad grid (levels 20x90x90 + 100x450x450 x C4: the 324 MB fine level, its
+    gradient and the Adam moments are NOT L2-resident, so dram traffic is meaningful here), 2^22 LiDAR-sampled points."""
+    from miso_b200 import loss as mloss, synth
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    mi, gt, poses = synth.lidar_batch(NCD_POINTS, num_kf=NCD_KF, seed=3)
+    net = build_ncd_model(device, poses)
+    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net, MisoLossMapping(**NCD_LOSS), None,
+                     device=device)
+    dmi = {k: v.to(device) for k, v in mi.items()}
+    dgt = {k: v.to(device) for k, v in gt.items()}
+    for _ in range(warmup):
+        tr.train_step(dmi, dgt)
+    torch.cuda.synchronize()
+    mloss.PROFILE_EVENTS = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        terms = tr.train_step(dmi, dgt)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = float(np.mean([a.elapsed_time(b) for a, b in mloss.PROFILE_EVENTS]))
+    mloss.PROFILE_EVENTS = None
+    ms = e0.elapsed_time(e1) / steps
+    peak, peak_src = measured_hbm_peak()
+    achieved = BYTES_PER_POINT * NCD_POINTS / (kms * 1e-3) / 1e9
+    traffic, tsrc = ncu_traffic("ncd_2p22")
+    out = {"workload": "Newer-College-quad single grid (20x90x90 + 100x450x450 x C4, decoder 8-64-64-1 fixed), 2^22 "
+                       "LiDAR-sampled pts/step, L2 sdf + 0.5 free-space (trunc 0.5), Adam joint; one GPU",
+           "steps": steps, "ms_per_step": ms, "points_per_s": NCD_POINTS / (ms * 1e-3),
+           "loss_terms": [float(v) for v in terms.tolist()],
+           "roofline": {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+                        "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kms, "kernel_share_of_step": kms / ms}}
+    del tr, net, dmi, dgt
+    torch.cuda.empty_cache()
+    return out
+
+
+def torch_gpu_arm(device, steps=5, warmup=2):
+    """The reference's GPU op sequence for the same headline step on this B200, as the kernel-for-kernel bar (SURVEY.md
+    section 2a / 8d): ATen grid_sampler_3d (+ its backward) per level, the reference's own double-backward extension
+    (oracle/_ref/gridsample_grad2.so, built unmodified by oracle/build_ref.py) for the eikonal term, cuBLAS Linear
+    layers, torch.optim.Adam -- the oracle's restatement of loss.py:754-813 moved to cuda.  When the extension was not
+    built the second-order term falls back to the pure-torch gather sampler (slower; flagged in `second_order`)."""
+    from miso_b200 import synth
+    from oracle import oracle as O
+    from oracle import ref_gpu
+    shapes = O.level_shapes(synth.SCANNET_SUBMAP_BOUND, 0.5, 5, 2, 4)
+    dec = O.make_decoder(8)
+    dec.load_state_dict({k.replace("network.", ""): v for k, v in synth.decoder_weights(8).items()})
+    mode = "plugin" if ref_gpu.available() else True
+    model = O.OracleGridNet(synth.SCANNET_SUBMAP_BOUND, initial_features(shapes, 0), dec, second_order=mode).to(device)
+    mi, gt, (R, t) = host_batch(0, 0)
+    mi = {k: v.to(device) for k, v in mi.items()}
+    gt = {k: v.to(device) for k, v in gt.items()}
+    poses = {k: (R[k].to(device), t[k].to(device)) for k in range(R.shape[0])}
+    opt = torch.optim.Adam(list(model.features.parameters()), lr=1e-3)
+    first = None
+
+    def step():
+        opt.zero_grad()
+        ld = O.mapping_loss(model, mi, gt, poses, LOSS_CFG["loss_type"], LOSS_CFG["weight_sdf"], LOSS_CFG["weight_eik"],
+                            LOSS_CFG["weight_fs"], LOSS_CFG["trunc_dist"], grad_method="autograd", eik_trunc_dist=None)
+        total = sum(ld.values())
+        total.backward()
+        opt.step()
+        return total
+
+    for i in range(warmup):
+        tot = step()
+        if i == 0:
+            first = float(tot)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": N_POINTS / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "steps": steps,
+            "second_order": "reference extension gridsample_grad2 (oracle/_ref)" if mode == "plugin" else "torch gather sampler",
+            "first_step_total": first,
+            "what": "reference op sequence on cuda: F.grid_sample + aten backward + grad2 plugin + cuBLAS MLP + torch Adam, "
+                    "same batch / parameters as the product arm"}
+
+
+def run_torch_gpu(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(0)
+    r = torch_gpu_arm(torch.device("cuda", 0), steps=max(1, min(args.steps, 20)), warmup=max(2, min(args.warmup, 3)))
+    line = {"impl": "torch-gpu", "metric": "SDF train pts/s (grid+MLP fwd/bwd/eikonal)", "value": r["value"], "unit": "points/s",
+            "n_gpus": 1, "steps": r["steps"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(1), "detail": r}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -491,6 +665,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 3))
     warm = max(1, min(args.warmup, 1))
     cb = cpu_reference_arm(steps=steps, warmup=warm)
+    cb.pop("first_step_terms", None)
     line = {"impl": "reference", "metric": "SDF train pts/s (grid+MLP fwd/bwd/eikonal)", "value": cb["value"],
             "unit": "points/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
             "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -508,13 +683,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the alignment half of the metric")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

@@ -2,8 +2,10 @@
 """BASELINE.json configs[4]: grid interpolation forward / backward / double-backward throughput sweep
 (2^16..2^24 points x 2-4 levels x 4-16 channels) on one B200, as points/s and as a fraction of the measured
 HBM roofline (algorithmic bytes of SURVEY.md section 8d).  ATen's F.grid_sample (NCDHW, the reference's
-first-order path) is timed beside it as the kernel-for-kernel bar; the reference's double-backward
-extension needs /root/reference + a JIT build and is not available on the GPU box.
+first-order path) is timed beside it as the kernel-for-kernel bar, and -- when oracle/_ref/gridsample_grad2.so was
+built (oracle/build_ref.py: the reference's own extension, unmodified, for sm_100a) -- the reference's double-backward
+kernel `grid_sampler_3d_grad2_kernel` (third_party/cuda_gridsample_grad2/gridsample_cuda.cu:212-533), both through
+its autograd plugin and launch-for-launch against miso_grid_sample3d_bwd_bwd.
 
     python benchmarks/interp_sweep.py > profiles/rNN_interp_sweep.csv
 """
@@ -17,8 +19,12 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+from miso_b200 import _lib  # noqa: E402
 from miso_b200 import cuda_gridsample as cu  # noqa: E402
 from miso_b200 import field, synth  # noqa: E402
+from oracle import build_ref, ref_gpu  # noqa: E402  (benchmark baseline only)
+
+REF_EXT = build_ref.load_module()
 
 PEAK = 6535.7
 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
@@ -54,8 +60,9 @@ def levels_for(L, C, dev):
 
 def main():
     dev = torch.device("cuda")
-    print("kind,levels,channels,points,distribution,ms,points_per_s,algorithmic_GBps,frac_of_hbm_peak,aten_ms,speedup_vs_aten")
-    for (L, C) in [(2, 4), (3, 4), (4, 4), (2, 8), (2, 16)]:
+    print("kind,levels,channels,points,distribution,ms,points_per_s,algorithmic_GBps,frac_of_hbm_peak,baseline_ms,speedup_vs_baseline")
+    print("# baseline = ATen F.grid_sample for fwd/bwd rows, the reference's grad2 extension for double_bwd rows", flush=True)
+    for (L, C) in [(2, 4), (3, 4), (2, 8), (2, 16)]:
         feats, bound = levels_for(L, C, dev)
         bl = field.bound_to_list(bound)
         b = torch.tensor(bound, device=dev)
@@ -125,8 +132,50 @@ def main():
                     torch.autograd.grad(out, xg, gov, create_graph=False)
 
                 t3 = timeit(plug_dbl) - timeit(plug_first)
-                row("double_bwd_level(+zerofill+glue)", 1, C, N, dist, max(t3, 1e-9), 24 + 2 * C * 4 + 2 * 8 * C * 4 + 12, float("nan"))
-                del fl, pl
+                dbl_bytes = 24 + 2 * C * 4 + 2 * 8 * C * 4 + 12
+                t3_ref = float("nan")
+                if REF_EXT is not None:
+                    def ref_dbl():
+                        pl.grad = None
+                        out = ref_gpu.grid_sample_3d(pl, xg, padding_mode="zeros", align_corners=False)
+                        (gx,) = torch.autograd.grad(out, xg, gov, create_graph=True)
+                        (gx * g2).sum().backward()
+
+                    def ref_first():
+                        out = ref_gpu.grid_sample_3d(pl, xg, padding_mode="zeros", align_corners=False)
+                        torch.autograd.grad(out, xg, gov, create_graph=False)
+
+                    t3_ref = timeit(ref_dbl) - timeit(ref_first)
+                row("double_bwd_level(+zerofill+glue)", 1, C, N, dist, max(t3, 1e-9), dbl_bytes, t3_ref)
+
+                # launch for launch: gg_grid given, outputs gg_output + g_input (accumulated) -- the eikonal pattern
+                lib = _lib.load()
+                gg_out = torch.empty(1, N, C, device=dev)
+                g_in = torch.zeros_like(fl.detach())
+                xnc, g2c = xn.reshape(1, N, 3).contiguous(), g2.reshape(1, N, 3).contiguous()
+                fd = fl.detach()
+                args = (_lib.F32, None, None, g2c.data_ptr(), gov.data_ptr(), _lib.i64(gov.reshape(1, C, N).stride()),
+                        fd.data_ptr(), _lib.i64(fd.shape), _lib.i64(fd.stride()), xnc.data_ptr(), N, gg_out.data_ptr(),
+                        _lib.i64([gg_out.stride(0), gg_out.stride(2), gg_out.stride(1)]), g_in.data_ptr(),
+                        _lib.i64(g_in.stride()), None, 0, 0, _lib.stream_ptr(dev))
+
+                def ours_kernel():
+                    _lib.check(lib.miso_grid_sample3d_bwd_bwd(*args), "grid_sample3d_bwd_bwd")
+
+                t4 = timeit(ours_kernel)
+                t4_ref = float("nan")
+                if REF_EXT is not None:
+                    zeros_in = torch.zeros_like(pl.detach())
+                    govc = gov.contiguous()
+                    pld = pl.detach()
+
+                    def ref_kernel():   # allocates + zero-fills its three outputs inside, as the reference does
+                        REF_EXT.grad2_3d(zeros_in, g2, govc, pld, xn, False, False)
+
+                    t4_ref = timeit(ref_kernel)
+                    del zeros_in
+                row("double_bwd_kernel_only", 1, C, N, dist, t4, dbl_bytes, t4_ref)
+                del fl, pl, g_in, gg_out
         del feats, planar
         torch.cuda.empty_cache()
 

@@ -184,3 +184,34 @@ def test_far_out_of_bounds_is_zero():
     assert torch.count_nonzero(out) == 0
     gi, gg = grad(out.sum(), [image, g])
     assert torch.count_nonzero(gi) == 0 and torch.count_nonzero(gg) == 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("padding_mode,align_corners", [("zeros", False), ("zeros", True), ("border", False)])
+def test_double_backward_matches_reference_extension(dtype, tol, padding_mode, align_corners):
+    """Value parity against the reference's OWN double-backward kernel (grid_sampler_3d_grad2_kernel,
+    gridsample_cuda.cu:212-533), compiled unmodified into oracle/_ref/gridsample_grad2.so by oracle/build_ref.py and
+    driven through the reference's plugin structure (oracle/ref_gpu.py): first-order grads, the double-backward's three
+    outputs (gg_output via a second cotangent, g_input, g_grid) on the same inputs."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/gridsample_grad2.so not built (python oracle/build_ref.py in the build container)")
+    from miso_b200 import cuda_gridsample as cu
+    g = torch.Generator().manual_seed(3)
+    inp0 = torch.randn(2, 4, 5, 6, 7, generator=g, dtype=dtype)
+    grid0 = (torch.rand(2, 300, 1, 1, 3, generator=g, dtype=dtype) * 2.4 - 1.2)
+    go = torch.randn(2, 4, 300, 1, 1, generator=g, dtype=dtype).cuda()
+    g2 = torch.randn(2, 300, 1, 1, 3, generator=g, dtype=dtype).cuda()
+    g2i = torch.randn(2, 4, 5, 6, 7, generator=g, dtype=dtype).cuda()
+    res = []
+    for fn in (cu.grid_sample_3d, ref_gpu.grid_sample_3d):
+        inp = inp0.clone().cuda().requires_grad_(True)
+        grid = grid0.clone().cuda().requires_grad_(True)
+        gor = go.clone().requires_grad_(True)
+        out = fn(inp, grid, padding_mode=padding_mode, align_corners=align_corners)
+        gi, gg = torch.autograd.grad(out, (inp, grid), gor, create_graph=True)
+        ((gg * g2).sum() + (gi * g2i).sum()).backward()
+        res.append((out.detach(), gi.detach(), gg.detach(), inp.grad, grid.grad, gor.grad))
+    names = ["out", "grad_input", "grad_grid", "dbl.g_input", "dbl.g_grid", "dbl.gg_output"]
+    for n, a, b in zip(names, res[0], res[1]):
+        assert rel_err(a, b) < tol, (n, rel_err(a, b))

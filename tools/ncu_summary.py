@@ -26,3 +26,18 @@ for i, n in enumerate(h):
 st = [(float(v[i]), n) for i, n in enumerate(h) if n.startswith('smsp__average_warps_issue_stalled_') and n.endswith('_per_issue_active.ratio')]
 for val, n in sorted(st, reverse=True)[:8]:
     print(f"{n},ratio,{val:.3f}")
+
+# --traffic-key KEY: record dram bytes per launch of this capture in profiles/ncu_traffic.json (read by bench.py)
+if "--traffic-key" in sys.argv:
+    import json, os
+    key = sys.argv[sys.argv.index("--traffic-key") + 1]
+    rd = float(v[h.index('dram__bytes_read.sum')]); wr = float(v[h.index('dram__bytes_write.sum')])
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd *= scale.get(u[h.index('dram__bytes_read.sum')], 1); wr *= scale.get(u[h.index('dram__bytes_write.sum')], 1)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = {"dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
+              "kernel": v[h.index('Kernel Name')] if 'Kernel Name' in h else None,
+              "duration_us_under_ncu": float(v[h.index('gpu__time_duration.sum')]) if 'gpu__time_duration.sum' in h else None,
+              "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", ".csv") + " (ncu --set full, one launch)"}
+    json.dump(d, open(path, "w"), indent=1)
