@@ -206,9 +206,17 @@ typedef struct miso_align_pair {
 } miso_align_pair_t;
 
 /* fields, pairs, poses ((num_pairs,24) floats: A1 row-major, b1, A2 row-major, b2) and out are
- * DEVICE pointers; out is overwritten. */
+ * DEVICE pointers; out is overwritten.  flags: bit 0 = accumulate the Gauss-Newton block; bits 4-5 = align_loss
+ * (miso.py:200-205): 0 'L2' = sum r^2, 1 'L1' = sum_i |r_i|_2, 2 'cos' = sum_i (1 - cosine_similarity(f_s, f_d)).
+ * out[0] holds the sum of the per-point loss values and gamma its derivative w.r.t. q, so the caller normalises
+ * with weight/(count*K) for L2 and weight/count for L1 / cos.  Feature-grid scatter and the Gauss-Newton block
+ * exist for L2 only. */
+#define MISO_ALIGN_WANT_GN 1
+#define MISO_ALIGN_LOSS_L2 (0 << 4)
+#define MISO_ALIGN_LOSS_L1 (1 << 4)
+#define MISO_ALIGN_LOSS_COS (2 << 4)
 int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
-                     int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t want_gn,
+                     int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t flags,
                      miso_stream_t stream);
 
 /* check_submap_intersection (grid_atlas.py:405-420) for all pairs in one launch.  Here pairs[i].p / M are

@@ -38,9 +38,19 @@ class AlignBatch:
     """Device-side description of one alignment problem: all submaps' fields + a list of
     (src, dst) pairs at one level.  Built once per level; reused by every iteration."""
 
+    LOSS_KINDS = {"L2": 0, "L1": 1, "cos": 2}
+
     def __init__(self, grid_atlas: GridAtlas, pairs: Sequence[Tuple[int, int]], level: int, fdim: int = 4,
                  subsample_points: Optional[int] = None, cache_src_features: bool = True, want_masks: bool = False,
-                 check_intersection: bool = True, lattice_rows: bool = True):
+                 check_intersection: bool = True, lattice_rows: bool = True, align_loss: str = "L2",
+                 trunc_factor: Optional[float] = None):
+        if align_loss not in self.LOSS_KINDS:
+            if align_loss == "InfoNCE":
+                raise NotImplementedError("align_loss='InfoNCE' (miso.py:206-208) couples every pair of samples of a "
+                                          "batch; the fused per-sample kernel implements L2, L1 and cos")
+            raise ValueError(f"Invalid align loss: {align_loss}!")
+        self.align_loss = align_loss
+        self.loss_flags = self.LOSS_KINDS[align_loss] << 4
         self.atlas = grid_atlas
         self.pairs = list(pairs)
         self.level = level
@@ -76,6 +86,13 @@ class AlignBatch:
                     n = min(subsample_points, p.shape[0])
                     idx = np.random.choice(p.shape[0], n, replace=False)  # miso.py:146-149
                     p = p[torch.from_numpy(idx).to(p.device), :]
+                if trunc_factor is not None:
+                    # truncation pruning (miso.py:176-183): keep the samples whose SOURCE sdf is within trunc_factor
+                    # cells of the surface -- a function of the source submap alone, so it is applied once here
+                    sm = grid_atlas.get_submap(src)
+                    with torch.no_grad():
+                        near = torch.abs(sm(p)) < trunc_factor * sm.cell_sizes[level]
+                    p = p[near[:, 0]]
                 p = p.detach().contiguous().float()
                 self._coords[src] = p
                 if cache_src_features and p.shape[0] > 0:
@@ -131,6 +148,7 @@ class AlignBatch:
         self.src_idx = torch.tensor([s for s, _ in self.pairs], dtype=torch.long, device=self.device)
         self.dst_idx = torch.tensor([d for _, d in self.pairs], dtype=torch.long, device=self.device)
         self.K = K
+        self.norm_channels = K if align_loss == "L2" else 1
 
     # ---- poses ------------------------------------------------------------------------------------
     def submap_poses(self):
@@ -175,11 +193,11 @@ class AlignBatch:
         with torch.cuda.device(self.device):
             _lib.check(lib.miso_align_batch(
                 self.fields_dev.data_ptr(), self.num_fields, self.pairs_dev.data_ptr(), P, self.max_M, p.data_ptr(),
-                out.data_ptr(), int(want_gn), _lib.stream_ptr(self.device)), "align_batch")
+                out.data_ptr(), int(want_gn) | self.loss_flags, _lib.stream_ptr(self.device)), "align_batch")
         return out
 
     def losses(self, align_weight: float = 3000.0, poses24: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """(P,) L2 alignment losses, differentiable w.r.t. the submap pose corrections."""
+        """(P,) alignment losses (self.align_loss), differentiable w.r.t. the submap pose corrections."""
         if poses24 is None:
             poses24 = self.pair_poses()
         return _AlignBatchFn.apply(poses24, self, float(align_weight))
@@ -190,8 +208,9 @@ class _AlignBatchFn(torch.autograd.Function):
     def forward(ctx, poses24, batch: AlignBatch, align_weight: float):
         out = batch.launch(poses24)
         S, cnt = out[:, 0], out[:, 1]
-        denom = cnt * batch.K
-        # mean((f_s - f_d)^2) * weight over M_valid x K elements; 0 when nothing is valid (miso.py:180-182,200-201)
+        # L2: mean over M_valid x K elements of r^2; L1 / cos: mean over the M_valid samples of |r|_2 / (1 - cos)
+        denom = cnt * batch.norm_channels
+        # times weight; 0 when nothing is valid (miso.py:180-182,200-205)
         scale = torch.where(cnt > 0, align_weight / denom.clamp(min=1.0), torch.zeros_like(denom))
         loss = (S * scale).to(torch.float32)
         ctx.save_for_backward(poses24, out, scale)
@@ -272,12 +291,12 @@ class FusedPoseAligner:
         with torch.cuda.device(b.device):
             if self.P:
                 _lib.check(lib.miso_align_batch(b.fields_dev.data_ptr(), b.num_fields, b.pairs_dev.data_ptr(), self.P,
-                                                b.max_M, self.poses24.data_ptr(), self.out.data_ptr(), 0, stream),
-                           "align_batch")
+                                                b.max_M, self.poses24.data_ptr(), self.out.data_ptr(), b.loss_flags,
+                                                stream), "align_batch")
             _lib.check(lib.miso_align_pose_grads(
                 self.R0.data_ptr(), self.t0.data_ptr(), self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S,
                 self.src.data_ptr(), self.dst.data_ptr(), self.P, self.out.data_ptr(), self.poses24.data_ptr(),
-                self.Rt.data_ptr(), b.K, self.align_weight, self.grads.data_ptr(), self.loss_hist.data_ptr(),
+                self.Rt.data_ptr(), b.norm_channels, self.align_weight, self.grads.data_ptr(), self.loss_hist.data_ptr(),
                 self.iter_counter.data_ptr(), self.pair_loss.data_ptr(), stream), "align_pose_grads")
             if self.allreduce is not None:
                 self.allreduce([self.grads])
@@ -325,18 +344,21 @@ class FusedPoseAligner:
 def pairwise_loss_latent(grid_atlas: GridAtlas, data_loader, src_id: int, dst_id: int, level: int, fdim=4,
                          align_weight=3000, align_loss="L2", use_bound=True, stability_thresh=0,
                          covariance_thresh=None, subsample_points=None, trunc_factor=None, device="cuda:0"):
-    """miso.py:116-211 for one pair.  L2 / use_bound=True (the shipped configuration,
-    configs/rgbd/scannet.yaml:56-63) runs the fused kernel; other variants are rejected loudly."""
+    """miso.py:116-211 for one pair on the fused kernel: align_loss 'L2' (the shipped configuration,
+    configs/rgbd/scannet.yaml:56-63), 'L1' or 'cos'; truncation pruning (`trunc_factor`) is applied to the source
+    samples.  Variants that need data outside the path are rejected loudly: use_bound=False, stability pruning
+    (stability grids), covariance pruning (NotImplementedError in the reference too), InfoNCE."""
     loss_key = f"align_latent_level{level}_{src_id}_{dst_id}"
     assert src_id < grid_atlas.num_submaps
     assert dst_id < grid_atlas.num_submaps
     if covariance_thresh is not None:
         raise NotImplementedError
-    if align_loss != "L2" or not use_bound or stability_thresh > 0 or trunc_factor is not None:
-        raise NotImplementedError("miso_b200.pairwise_loss_latent implements align_loss='L2', use_bound=True, "
-                                  "no stability / truncation pruning (the shipped configs)")
+    if not use_bound or stability_thresh > 0:
+        raise NotImplementedError("miso_b200.pairwise_loss_latent needs use_bound=True and stability_thresh=0 (the "
+                                  "stability grids are outside the hot path, SURVEY.md section 8)")
     batch = AlignBatch(grid_atlas, [(src_id, dst_id)], level, fdim=fdim, subsample_points=subsample_points,
-                       cache_src_features=False, check_intersection=False)
+                       cache_src_features=False, check_intersection=False, align_loss=align_loss,
+                       trunc_factor=trunc_factor)
     return {loss_key: batch.losses(align_weight)[0]}
 
 
@@ -440,11 +462,11 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
                                    pose_reg_weight=0, pose_thresh_rad=1.0, pose_thresh_m=1.0, verbose=True,
                                    save_iterations=False, *, level: int = 0, align_weight=3000.0,
                                    subsample_points=None, pair_filter=None, allreduce=None, use_cuda_graph=False,
-                                   fused_pose_glue=True):
+                                   fused_pose_glue=True, align_loss="L2", trunc_factor=None):
     """base.py:89-163 with the pair loop replaced by one batched launch per iteration.
 
-    `pairwise_loss_tuple` is accepted for signature compatibility; the loss is the latent L2 loss at
-    `level`.  `pair_filter` / `allreduce` are the multi-GPU hooks (miso_b200.dist): a rank evaluates
+    `pairwise_loss_tuple` is accepted for signature compatibility; the loss is the latent `align_loss` ('L2' | 'L1' |
+    'cos', miso.py:200-205) at `level`, optionally with truncation pruning of the source samples.  `pair_filter` / `allreduce` are the multi-GPU hooks (miso_b200.dist): a rank evaluates
     only its share of the pairs and the per-submap pose gradients are summed across ranks before Adam.
     Runs `num_iters + 1` iterations like the reference (`while iter <= num_iters`, base.py:127).
     `use_cuda_graph=True` captures one whole iteration (pose composition, intersection test, alignment
@@ -468,7 +490,7 @@ def generic_align_multiple_submaps(grid_atlas: GridAtlas, dataset=None, pairwise
         submap_pairs = [(s, d) for s in range(grid_atlas.num_submaps) for d in range(s + 1, grid_atlas.num_submaps)]
     my_pairs = list(submap_pairs) if pair_filter is None else [p for i, p in enumerate(submap_pairs) if pair_filter(i, p)]
     batch = AlignBatch(grid_atlas, my_pairs, level, subsample_points=subsample_points,
-                       check_intersection=check_intersection)
+                       check_intersection=check_intersection, align_loss=align_loss, trunc_factor=trunc_factor)
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -632,8 +654,8 @@ def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, lev
                                         allreduce=None):
     """miso.py:217-322: latent-space levels (one batched launch per iteration), then -- unless `skip_finetune`
     (True in the shipped configs, scannet.yaml:63) -- the SDF-space fine-tune with pairwise_loss_sdf on `dataset`."""
-    if align_loss != "L2" or not use_bound or stability_thresh > 0:
-        raise NotImplementedError("fused alignment implements align_loss='L2', use_bound=True, stability_thresh=0")
+    if not use_bound or stability_thresh > 0:
+        raise NotImplementedError("fused alignment needs use_bound=True and stability_thresh=0")
     if not skip_finetune and dataset is None:
         raise ValueError("the SDF-space fine-tune needs a dataset of (model_input, gt) batches")
     grid_atlas.precompute_coordinates_for_alignment()
@@ -648,7 +670,7 @@ def align_multiple_submaps_hierarchical(grid_atlas: GridAtlas, dataset=None, lev
             submap_pairs=submap_pairs, pose_reg_weight=pose_reg_weight, pose_thresh_m=pose_thresh_m,
             pose_thresh_rad=pose_thresh_rad, verbose=verbose, save_iterations=save_iterations, level=curr_level,
             align_weight=align_weight, subsample_points=subsample_points, pair_filter=pair_filter,
-            allreduce=allreduce)
+            allreduce=allreduce, align_loss=align_loss)
         cpu_total += level_dict["cpu_time_sec"]
         gpu_total += level_dict["gpu_time_sec"]
         info[loss_name] = level_dict

@@ -109,7 +109,11 @@ __device__ __forceinline__ void scatter4(const miso_level_t& lv, const Cell& c, 
   }
 }
 
-template <int C, bool kGN>
+// kLoss: 0 = L2 (mean r^2 over points x channels, miso.py:200-201), 1 = "L1" (mean over points of |r|_2, :202-203),
+// 2 = cos (mean over points of 1 - cosine_similarity(f_s, f_d), :204-205; ATen clamps each norm at eps = 1e-8).
+// acc[0] always holds the sum of the per-point loss values and gamma = d(that sum)/dq, so the host-side
+// normalisation is weight / (count * K) for L2 and weight / count for the other two.
+template <int C, bool kGN, int kLoss>
 __global__ void __launch_bounds__(kThreads)
     align_batch_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
                        const float* __restrict__ poses, double* __restrict__ out) {
@@ -154,6 +158,72 @@ __global__ void __launch_bounds__(kThreads)
     }
     float gam[3] = {0.f, 0.f, 0.f};
     float rr = 0.f;
+    if constexpr (kLoss != 0) {
+      // the per-point factor of these losses needs the whole feature vector first: keep f_s, f_d and grad_q f_d
+      float fsv[MISO_MAX_LEVELS * C], fdv[MISO_MAX_LEVELS * C], gq[MISO_MAX_LEVELS * C][3];
+#pragma unroll
+      for (int l = 0; l < MISO_MAX_LEVELS; ++l) {
+        if (l >= LU) continue;
+        float fs[C], fd[C], dx[C], dy[C], dz[C];
+        const miso_level_t& sl = src.level[l];
+        const miso_level_t& dl = dst.level[l];
+        if (pr.fsrc) {
+#pragma unroll
+          for (int ch = 0; ch < C; ch += 4) {
+            float4 t = *reinterpret_cast<const float4*>(pr.fsrc + n * K + l * C + ch);
+            fs[ch] = t.x, fs[ch + 1] = t.y, fs[ch + 2] = t.z, fs[ch + 3] = t.w;
+          }
+        } else if ((src.ignore_mask >> l) & 1u) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) fs[ch] = 0.f;
+        } else {
+          Cell cs = make_cell(unnormalize_nc(pn[0], sl.X), unnormalize_nc(pn[1], sl.Y), unnormalize_nc(pn[2], sl.Z), sl);
+          gather4<C>(sl, cs, fs, nullptr, nullptr, nullptr, false);
+        }
+        if ((dst.ignore_mask >> l) & 1u) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) fd[ch] = dx[ch] = dy[ch] = dz[ch] = 0.f;
+        } else {
+          Cell cd = make_cell(unnormalize_nc(qn[0], dl.X), unnormalize_nc(qn[1], dl.Y), unnormalize_nc(qn[2], dl.Z), dl);
+          gather4<C>(dl, cd, fd, dx, dy, dz, true);
+        }
+        const float kx = (float)dl.X / (dbmax[0] - dbmin[0]), ky = (float)dl.Y / (dbmax[1] - dbmin[1]),
+                    kz = (float)dl.Z / (dbmax[2] - dbmin[2]);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          fsv[l * C + ch] = fs[ch], fdv[l * C + ch] = fd[ch];
+          gq[l * C + ch][0] = dx[ch] * kx, gq[l * C + ch][1] = dy[ch] * ky, gq[l * C + ch][2] = dz[ch] * kz;
+        }
+      }
+      float ss = 0.f, dd = 0.f, sd = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < MISO_MAX_LEVELS * C; ++k) {
+        if (k >= K) continue;
+        const float r = fsv[k] - fdv[k];
+        r2 = fmaf(r, r, r2), ss = fmaf(fsv[k], fsv[k], ss), dd = fmaf(fdv[k], fdv[k], dd), sd = fmaf(fsv[k], fdv[k], sd);
+      }
+      float a_s = 0.f, a_d = 0.f;   // d(loss_i)/d(f_d) = a_s * f_s + a_d * f_d
+      if constexpr (kLoss == 1) {
+        const float nr = sqrtf(r2);
+        rr = nr;                                   // loss_i = |r|_2 ; d/df_d = -(f_s - f_d)/|r| (0 at r = 0, as autograd)
+        if (nr > 0.f) a_s = -1.f / nr, a_d = 1.f / nr;
+      } else {
+        const float eps = 1e-8f;
+        const float ns = sqrtf(ss), nd = sqrtf(dd);
+        const float cs_ = fmaxf(ns, eps), cd_ = fmaxf(nd, eps);
+        rr = 1.f - sd / (cs_ * cd_);
+        // cos = (f_s/cs).(f_d/cd), cd = max(|f_d|, eps):  d cos/d f_d = f_s/(cs cd) - [|f_d| > eps] (f_s.f_d) f_d/(cs cd^2 |f_d|)
+        a_s = -1.f / (cs_ * cd_);
+        a_d = nd > eps ? sd / (cs_ * cd_ * cd_ * nd) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < MISO_MAX_LEVELS * C; ++k) {
+        if (k >= K) continue;
+        const float c = fmaf(a_s, fsv[k], a_d * fdv[k]);
+        gam[0] = fmaf(c, gq[k][0], gam[0]), gam[1] = fmaf(c, gq[k][1], gam[1]), gam[2] = fmaf(c, gq[k][2], gam[2]);
+      }
+      acc[23] += sqrtf(r2);
+    } else {
     for (int l = 0; l < LU; ++l) {
       float fs[C], fd[C], dx[C], dy[C], dz[C];
       const miso_level_t& sl = src.level[l];
@@ -218,9 +288,10 @@ __global__ void __launch_bounds__(kThreads)
       if (sl.grad && !src_ignored && pr.src_grad_scale != 0.f) scatter4<C>(sl, cs, 2.f * pr.src_grad_scale, r);
       if (dl.grad && !dst_ignored && pr.dst_grad_scale != 0.f) scatter4<C>(dl, cd, -2.f * pr.dst_grad_scale, r);
     }
+    acc[23] += sqrtf(rr);
+    }
     acc[0] += rr;
     acc[1] += 1.f;
-    acc[23] += sqrtf(rr);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       acc[2 + i] += gam[i];
@@ -538,8 +609,11 @@ __global__ void __launch_bounds__(kThreads)
 using namespace miso;
 
 extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
-                                int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t want_gn,
+                                int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t flags,
                                 miso_stream_t stream) {
+  const int want_gn = flags & 1, loss_kind = (flags >> 4) & 3;
+  MISO_REQUIRE(loss_kind <= 2, "align_batch: loss kind must be 0 (L2), 1 (L1) or 2 (cos)");
+  MISO_REQUIRE(!(want_gn && loss_kind != 0), "align_batch: Gauss-Newton accumulators exist for the L2 loss only");
   MISO_REQUIRE(fields && pairs && poses && out, "align_batch: null argument");
   MISO_REQUIRE(num_fields > 0 && num_pairs >= 0, "align_batch: bad counts");
   if (num_pairs == 0) return MISO_OK;
@@ -552,9 +626,13 @@ extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, 
   int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_pairs, sm_count() * 8))));
   dim3 grid(bx, num_pairs);
   if (want_gn)
-    align_batch_kernel<4, true><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+    align_batch_kernel<4, true, 0><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+  else if (loss_kind == 1)
+    align_batch_kernel<4, false, 1><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+  else if (loss_kind == 2)
+    align_batch_kernel<4, false, 2><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
   else
-    align_batch_kernel<4, false><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
+    align_batch_kernel<4, false, 0><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
   return check_launch("align_batch");
 }
 

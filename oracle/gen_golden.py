@@ -140,6 +140,58 @@ def gen_align():
     np.savez_compressed(os.path.join(OUT, "align.npz"), **out)
 
 
+def gen_align_variants():
+    """pairwise_loss_latent (miso.py:116-211) variants on the atlas of gen_align: align_loss 'L1' and 'cos' at both
+    levels, and truncation pruning (trunc_factor, :176-183, needs the source decoder) with the L2 loss."""
+    from grid_opt.models.grid_atlas import GridAtlas
+    import grid_opt.align.miso as amiso
+    from oracle import oracle as O
+    cfg = ref_loader.reference_model_cfg(ABOUND, base_cell_size=1.0, per_level_scale=2, num_poses=1)
+    Rt, tt = synth.submap_layout(2, spacing=(4.0, 3.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=4.0, trans_m=0.3)
+    atlas = GridAtlas(cfg, device="cpu")
+    shapes = O.level_shapes(ABOUND, 1.0, 2, 2, 4)
+    out = {"bound": np.asarray(ABOUND, np.float32)}
+    dec_sd = synth.decoder_weights(8, seed=3)
+    for i in range(2):
+        atlas.add_submap(torch.tensor(ABOUND), Rp[i], tp[i])
+        feats = synth.fill_submap_from_field(shapes, ABOUND, Rt[i], tt[i])
+        feats[0][:, :, :, :, :1] = 0
+        feats[1][:, :, :, :, :2] = 0
+        sm = atlas.get_submap(i)
+        sm.decoder.load_state_dict(dec_sd)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(feats[l])
+                out[f"sm{i}.feat{l}"] = _np(feats[l])
+        out[f"sm{i}.R"], out[f"sm{i}.t"] = _np(Rp[i]), _np(tp[i])
+    for k, v in dec_sd.items():
+        out[f"dec.{k}"] = _np(v)
+    atlas.precompute_coordinates_for_alignment()
+
+    def run(tag, **kw):
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        (key, val), = amiso.pairwise_loss_latent(atlas, None, 0, 1, device="cpu", **kw).items()
+        val.backward()
+        out[f"{tag}.loss"] = _np(val)
+        for i in range(2):
+            out[f"{tag}.grad_rot{i}"] = _np(atlas.rotation_corrections[i].grad)
+            out[f"{tag}.grad_tra{i}"] = _np(atlas.translation_corrections[i].grad)
+
+    for level in range(2):
+        for loss in ("L1", "cos"):
+            run(f"{loss}.L{level}", level=level, align_loss=loss)
+    sm0 = atlas.get_submap(0)
+    with torch.no_grad():
+        sd = torch.abs(sm0(atlas.coordinates_for_alignment(0, 1)))
+    tf = float(torch.median(sd) / sm0.cell_sizes[1])      # keeps about half of the samples
+    out["trunc.factor"] = np.asarray(tf, np.float32)
+    out["trunc.kept"] = np.asarray(int((sd < tf * sm0.cell_sizes[1]).sum()))
+    run("trunc.L1level", level=1, align_loss="L2", trunc_factor=tf)
+    np.savez_compressed(os.path.join(OUT, "align_variants.npz"), **out)
+
+
 def gen_align_sdf():
     """pairwise_loss_sdf (miso.py:14-113) on a 2-submap atlas with two keyframes per submap; L2 / L1 / GM."""
     from grid_opt.models.grid_atlas import GridAtlas
@@ -344,13 +396,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     np.random.seed(0)
-    gen_gridnet()
-    gen_mapping()
-    gen_align()
-    gen_align_sdf()
-    gen_variants()
-    gen_tracker()
-    gen_align_loop()
+    gens = {"gridnet": gen_gridnet, "mapping": gen_mapping, "align": gen_align, "align_variants": gen_align_variants,
+            "align_sdf": gen_align_sdf, "variants": gen_variants, "tracker": gen_tracker, "align_loop": gen_align_loop}
+    for name in (sys.argv[1:] or list(gens)):     # `python oracle/gen_golden.py align_variants` regenerates one fixture
+        gens[name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

@@ -275,3 +275,68 @@ def test_alignment_loop_against_reference_outputs(fused_glue):
     for i in range(3):
         assert rel_err(atlas.rotation_corrections[i], T(z[f"final.rot{i}"])) < 1e-3, i
         assert rel_err(atlas.translation_corrections[i], T(z[f"final.tra{i}"])) < 1e-3, i
+
+
+def _variants_atlas(z):
+    from miso_b200.models import GridAtlas
+    bound = z["bound"].tolist()
+    atlas = GridAtlas(synth.model_cfg(bound, base_cell_size=1.0, per_level_scale=2, num_poses=1), device="cuda")
+    dec = {k[len("dec."):]: T(z[k]) for k in z.files if k.startswith("dec.")}
+    for i in range(2):
+        atlas.add_submap(torch.tensor(bound), T(z[f"sm{i}.R"]), T(z[f"sm{i}.t"]))
+        sm = atlas.get_submap(i)
+        sm.decoder.load_state_dict(dec)
+        with torch.no_grad():
+            for l in range(2):
+                sm.features[l].feature.copy_(T(z[f"sm{i}.feat{l}"]).cuda())
+    atlas.precompute_coordinates_for_alignment()
+    return atlas
+
+
+def _check_pair(atlas, z, tag, **kw):
+    from miso_b200.align import pairwise_loss_latent
+    for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+        p.grad = None
+    (key, val), = pairwise_loss_latent(atlas, None, 0, 1, device="cuda", **kw).items()
+    val.backward()
+    assert rel_err(val, T(z[f"{tag}.loss"])) < 1e-5, tag
+    for i in range(2):
+        assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"{tag}.grad_rot{i}"])) < 1e-4, (tag, "rot", i)
+        assert rel_err(atlas.translation_corrections[i].grad, T(z[f"{tag}.grad_tra{i}"])) < 1e-4, (tag, "tra", i)
+
+
+@pytest.mark.parametrize("loss", ["L1", "cos"])
+def test_alignment_loss_variants_against_reference_outputs(loss):
+    """align_loss 'L1' (mean |r|_2) and 'cos' of pairwise_loss_latent (miso.py:202-205) in the fused kernel: loss and
+    pose gradients at both levels against the reference's own outputs."""
+    z = load("align_variants.npz")
+    atlas = _variants_atlas(z)
+    for level in range(2):
+        _check_pair(atlas, z, f"{loss}.L{level}", level=level, align_loss=loss)
+
+
+def test_alignment_truncation_pruning_against_reference_outputs():
+    """trunc_factor (miso.py:176-183): samples whose source sdf is beyond trunc_factor cells are dropped."""
+    from miso_b200.align import AlignBatch
+    z = load("align_variants.npz")
+    atlas = _variants_atlas(z)
+    tf = float(z["trunc.factor"])
+    batch = AlignBatch(atlas, [(0, 1)], level=1, check_intersection=False, trunc_factor=tf)
+    kept = batch._coords[0].shape[0]
+    # |sdf| < threshold is decided on the fused decoder's value (1e-6 relative to the CPU's): a sample sitting exactly
+    # at the threshold may fall on the other side -- the fixture's threshold IS a sample value (the median)
+    assert abs(kept - int(z["trunc.kept"])) <= 1
+    if kept == int(z["trunc.kept"]):
+        _check_pair(atlas, z, "trunc.L1level", level=1, align_loss="L2", trunc_factor=tf)
+
+
+def test_alignment_variant_rejections():
+    from miso_b200.align import pairwise_loss_latent
+    z = load("align_variants.npz")
+    atlas = _variants_atlas(z)
+    with pytest.raises(NotImplementedError):
+        pairwise_loss_latent(atlas, None, 0, 1, level=0, align_loss="InfoNCE")
+    with pytest.raises(ValueError):
+        pairwise_loss_latent(atlas, None, 0, 1, level=0, align_loss="huber")
+    with pytest.raises(NotImplementedError):
+        pairwise_loss_latent(atlas, None, 0, 1, level=0, stability_thresh=0.5)
