@@ -165,6 +165,20 @@ int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, cons
                       const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
                       miso_stream_t stream);
 
+/* The same step with the FINITE-DIFFERENCE eikonal term the shipped configs select (grad_method: finitediff,
+ * configs/rgbd/scannet.yaml:48-49; grid_opt/diff.py:18-26 + loss.py:638-665):
+ *   g_d = (f(x + eps e_d) - f(x - eps e_d)) / (2 eps), eik = mean (|g| - 1)^2, all six evaluations differentiated.
+ * Four launches instead of the reference's 14 interpolation + 14 decoder passes and their autograd glue: the step on
+ * the N samples (sdf + free-space terms), ONE forward launch over the 6 N displaced points, the eikonal epilogue
+ * (term + the six cotangents), ONE backward launch that scatters them.  cfg->eik_mode is ignored (the term is on
+ * when weight_eik != 0).  fd_workspace: device float[12 * N].  Returns MISO_ERR_UNSUPPORTED when the
+ * two-threads-per-point kernel does not cover the field (levels*channels % 8 != 0, >= 2^31-element grids). */
+int miso_mapping_step_fd(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                         const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                         const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                         const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                         float finite_diff_eps, float* fd_workspace, miso_stream_t stream);
+
 /* Gauss-Newton / LM normal equations of one keyframe in ONE launch (Tracker.lm_step, grid_opt/slam/tracker.py:148-212):
  * x_w = R x + t, r = sdf(x_w) - gt, g = grad_x sdf(x_w), J = [((R x) x g)^T R, g^T], w = 1 (loss_type 0, L2) or
  * gm_scale/(gm_scale + r^2)^2 (loss_type 1, Geman-McClure :139-146); samples with |gt| >= trunc_dist are skipped when

@@ -72,6 +72,9 @@ _SIGNATURES = {
     "miso_mapping_step": (C.c_int, [C.POINTER(Field), C.POINTER(Decoder), C.POINTER(Frames), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MappingCfg),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "miso_mapping_step_fd": (C.c_int, [C.POINTER(Field), C.POINTER(Decoder), C.POINTER(Frames), C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MappingCfg),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "miso_align_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p]),
     "miso_align_intersections": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -128,7 +131,7 @@ def load():
 
 # kernels launched by each entry point (for bench.py's `gpu_launches` claim)
 KERNELS_PER_CALL = {"grid_sample3d_fwd": 1, "grid_sample3d_bwd": 1, "grid_sample3d_bwd_bwd": 1, "field_features": 1,
-                    "sdf_forward": 1, "sdf_backward": 1, "mapping_count": 1, "mapping_step": 2, "align_batch": 1,
+                    "sdf_forward": 1, "sdf_backward": 1, "mapping_count": 1, "mapping_step": 2, "mapping_step_fd": 6, "align_batch": 1,
                     "align_intersections": 2, "morton_keys": 1, "transform_points": 1, "adam_step": 1}
 LAUNCHES = {"total": 0}
 

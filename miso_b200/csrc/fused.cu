@@ -706,6 +706,9 @@ struct MapArgs {
   float* jac;      // forward modes of the two-thread kernel: (N,F) Jacobian, (N,3) grad_x sdf, (N,3) world coordinates
   float* gradx;
   float* xw;
+  const float* a_ext;   // two-thread kernel, step mode: per-point d total / d sdf given by the caller (no loss terms)
+  int fd_n;             // > 0: the launch runs over 6 * fd_n virtual points displaced by +-fd_eps (finite differences)
+  float fd_eps;
   float inv_len[3];                       // 1/(bmax-bmin), computed on the host with the device's fp32 ops
   float lvl_scale[MISO_MAX_LEVELS][3];    // (float)dim * inv_len: index-space -> world-space derivative scale
   int dbg;   // MISO_DBG ablation bits (profiling only): 1 = no reductions, 2 = no corner loads, 4 = no g1 TMEM loads
@@ -1469,7 +1472,8 @@ template <int L, int C, int G>
 static int launch_tc2(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t& fr, const MapArgs& m,
                       cudaStream_t s) {
   constexpr size_t smem = sizeof(Tc2Smem<L * C, G>) + 128;
-  auto k = tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true, 0> : mapping_step_tc2_kernel<L, C, G, false, 0>;
+  auto k = m.a_ext ? mapping_step_tc2_kernel<L, C, G, true, 3>
+                   : (tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true, 0> : mapping_step_tc2_kernel<L, C, G, false, 0>);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nblocks = grid_for((m.N + G * 128 - 1) / (G * 128), 1, sm_count());
   k<<<nblocks, G * 256, smem, s>>>(*field, *dec, fr, m);
@@ -1659,16 +1663,136 @@ extern "C" int miso_mapping_count(const float* gt_sdf, int64_t N, float eik_trun
   return check_launch("mapping_count");
 }
 
+// finite-difference eikonal (diff.py:18-26 + loss.py:638-665) from the six displaced values f[k N + i]:
+//   g_d = (f[2d] - f[2d+1]) / (2 eps),  term = (|g| - 1)^2 over the samples that pass the |gt| < trunc filter,
+//   a_ext[(2d) N + i] = +c g_d / (2 eps), a_ext[(2d+1) N + i] = -c g_d / (2 eps),  c = w_eik * scale * 2 (|g|-1) / (n_eik |g|)
+// i.e. d(w_eik * eik)/d f at each displaced evaluation -- the cotangents of the six first-order backward passes.
+__global__ void __launch_bounds__(kThreads)
+    fd_eikonal_kernel(const float* __restrict__ f, const float* __restrict__ gt_sdf, int64_t N, float eps,
+                      miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ a_ext,
+                      float* __restrict__ partials) {
+  __shared__ float red[32];
+  const bool filter = cfg.eik_trunc_dist >= 0.f;
+  const float n_den = (float)(cfg.n_total > 0 ? cfg.n_total : N);
+  const float n_eik = filter ? (float)(*eik_count) : n_den;
+  const float scale = cfg.weight_eik * cfg.grad_scale * 2.f * (1.0f / n_eik);
+  const float inv2e = 1.0f / (eps * 2.0f);
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float g[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) g[d] = (f[(2 * d) * N + i] - f[(2 * d + 1) * N + i]) / (eps * 2.0f);
+    const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    const float e = nrm - 1.f;
+    const bool use = !filter || fabsf(gt_sdf[i]) < cfg.eik_trunc_dist;
+    acc += use ? e * e : 0.f;
+    const float c = (use && nrm > 0.f) ? scale * e / nrm : 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float a = c * g[d] * inv2e;
+      a_ext[(2 * d) * N + i] = a;
+      a_ext[(2 * d + 1) * N + i] = -a;
+    }
+  }
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void fd_eikonal_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t N,
+                                           miso_mapping_cfg_t cfg, const int32_t* eik_count, float* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += (double)partials[b];
+  const double t = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const double nden = (double)(cfg.n_total > 0 ? cfg.n_total : N);
+    const double neik = cfg.eik_trunc_dist >= 0.f ? (double)(*eik_count) : nden;
+    const float l_eik = (float)(t / neik);
+    out[2] = l_eik;                         // NaN-poisoned steps stay NaN: NaN + x = NaN
+    out[3] = out[3] + cfg.weight_eik * l_eik;
+  }
+}
+
+static int mapping_step_impl(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                             const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                             const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                             const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                             miso_stream_t stream, const float* a_ext, int fd_n, float fd_eps);
+
 extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
                                  const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
                                  const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
                                  const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
                                  miso_stream_t stream) {
+  return mapping_step_impl(field, dec, frames, x, N, gt_sdf, gt_valid, gt_sign, weights, cfg, eik_count, partials,
+                           loss_out, sdf_out, stream, nullptr, 0, 0.f);
+}
+
+extern "C" int miso_mapping_step_fd(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                                    const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                                    const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                                    const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                                    float finite_diff_eps, float* fd_workspace, miso_stream_t stream) {
+  if (int e = validate_field(field, true)) return e;
+  if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
+  MISO_REQUIRE(cfg && fd_workspace && finite_diff_eps > 0.f, "mapping_step_fd: null cfg/workspace or eps <= 0");
+  MISO_REQUIRE(cfg->weight_eik != 0.f, "mapping_step_fd: weight_eik == 0, call miso_mapping_step");
+  MISO_REQUIRE(!(cfg->eik_trunc_dist >= 0.f) || eik_count, "mapping_step_fd: eik filter needs eik_count");
+  const int F_ = field->num_levels * field->level[0].C;
+  const bool tc2_ok = use_tensor_cores() && fits_int32(field) && tc2_groups() != 0 && F_ % 8 == 0 &&
+                      6 * N < ((int64_t)1 << 31) - ((int64_t)1 << 26);
+  if (!tc2_ok) {
+    set_error("mapping_step_fd: needs the two-threads-per-point tensor-core kernel (levels*channels %% 8 == 0, "
+              "32-bit addressable grids, 6 N < 2^31)");
+    return MISO_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* f6 = fd_workspace;            // (6, N) displaced values
+  float* a6 = fd_workspace + 6 * N;    // (6, N) their cotangents
+  // (1) sdf + free-space terms and their scatter on the N samples, eikonal off
+  miso_mapping_cfg_t base = *cfg;
+  base.eik_mode = 0;
+  if (int e = mapping_step_impl(field, dec, frames, x, N, gt_sdf, gt_valid, gt_sign, weights, &base, eik_count, partials,
+                                loss_out, sdf_out, stream, nullptr, 0, 0.f))
+    return e;
+  // (2) six displaced forward evaluations in one launch (values only)
+  const miso_frames_t fr = frames_or_none(frames);
+  {
+    MapArgs m;
+    memset(&m, 0, sizeof(m));
+    m.x = x, m.N = 6 * N, m.sdf_out = f6, m.fd_n = (int)N, m.fd_eps = finite_diff_eps;
+    fill_scales(field, m);
+    int nb = 0;
+    MISO_DISPATCH_LC_TC2(field->num_levels, field->level[0].C, { nb = launch_tc2_forward<L, C, 2>(field, dec, fr, m, s); });
+    MISO_REQUIRE(nb > 0, "mapping_step_fd: unsupported (levels=%d, channels=%d)", field->num_levels, field->level[0].C);
+    if (int e = check_launch("mapping_step_fd(forward)")) return e;
+  }
+  // (3) eikonal term + cotangents of the six evaluations
+  const int nbk = grid_for(N, kThreads, (int)(partial_floats() / 4));
+  fd_eikonal_kernel<<<nbk, kThreads, 0, s>>>(f6, gt_sdf, N, finite_diff_eps, *cfg, eik_count, a6, partials);
+  fd_eikonal_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nbk, N, *cfg, eik_count, loss_out);
+  if (int e = check_launch("mapping_step_fd(eikonal)")) return e;
+  // (4) six first-order backward passes in one launch: scatter a_ext * w_c * J at the displaced points
+  {
+    float scratch_loss_unused = 0.f;
+    (void)scratch_loss_unused;
+    if (int e = mapping_step_impl(field, dec, frames, x, 6 * N, nullptr, nullptr, nullptr, nullptr, &base, eik_count,
+                                  partials, nullptr, nullptr, stream, a6, (int)N, finite_diff_eps))
+      return e;
+  }
+  return MISO_OK;
+}
+
+static int mapping_step_impl(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                             const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                             const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                             const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
+                             miso_stream_t stream, const float* a_ext, int fd_n, float fd_eps) {
   if (int e = validate_field(field, true)) return e;
   if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
   if (int e = validate_frames(frames)) return e;
-  MISO_REQUIRE(cfg && partials && loss_out, "mapping_step: null cfg/partials/loss_out");
-  MISO_REQUIRE(N > 0 && x && gt_sdf && gt_valid && gt_sign, "mapping_step: null inputs or N == 0");
+  MISO_REQUIRE(cfg && partials && (loss_out || a_ext), "mapping_step: null cfg/partials/loss_out");
+  MISO_REQUIRE(N > 0 && x && (a_ext || (gt_sdf && gt_valid && gt_sign)), "mapping_step: null inputs or N == 0");
   MISO_REQUIRE(cfg->loss_type == 0 || cfg->loss_type == 1, "mapping_step: loss_type must be 0 (L1) or 1 (L2)");
   MISO_REQUIRE(cfg->eik_mode == 0 || cfg->eik_mode == 1, "mapping_step: eik_mode must be 0 or 1");
   const bool eik_on = cfg->eik_mode != 0 && cfg->weight_eik != 0.f;
@@ -1678,8 +1802,9 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
   MapArgs m;
   m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
   m.cfg = *cfg, m.eik_count = eik_count, m.partials = partials, m.sdf_out = sdf_out;
-  m.poison = partials + partial_floats();
+  m.poison = a_ext ? nullptr : partials + partial_floats();   // the step's own pass has already judged the keyframe ids
   m.jac = nullptr, m.gradx = nullptr, m.xw = nullptr;
+  m.a_ext = a_ext, m.fd_n = fd_n, m.fd_eps = fd_eps;
   fill_scales(field, m);
   m.dbg = tuning().dbg;
   int nblocks = 0;
@@ -1708,6 +1833,7 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
     });
   }
   if (int e = check_launch("mapping_step")) return e;
+  if (a_ext) return MISO_OK;   // backward-only pass: no loss terms to finalize
   mapping_finalize_kernel<<<1, kThreads, 0, s>>>(partials, nblocks, N, *cfg, eik_count, loss_out, m.poison);
   return check_launch("mapping_finalize");
 }

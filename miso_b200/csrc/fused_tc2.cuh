@@ -302,6 +302,8 @@ __device__ __forceinline__ void scatter_group4_paired(const miso_level_t& lv, co
   }
 }
 
+// kMode: 3 = backward pass with a per-point cotangent given by the caller (m.a_ext) over displaced "virtual" points
+// (finite-difference eikonal, miso_mapping_step_fd); mode 2 also understands virtual points.
 // kMode: 0 = whole mapping step (losses + scatter), 1 = forward with Jacobian / grad_x outputs (miso_sdf_forward with
 // jac / gradx), 2 = forward only (dense queries: no derivative gather, no backward products)
 template <int L, int C, int G, bool kPaired, int kMode>
@@ -394,7 +396,10 @@ __global__ void __launch_bounds__(G * 256, 1)
   uint64_t* const bar = &s->bar[grp];
   uint32_t parity = 0;
 
-  const bool eik_on = kMode == 1 ? true : (m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f);
+  constexpr bool kStep = kMode == 0 || kMode == 3;   // scatters gradients
+  constexpr bool kExt = kMode == 3;                  // cotangent given by the caller, no loss terms
+  constexpr bool kVirt = kMode == 2 || kMode == 3;   // may run over displaced virtual points
+  const bool eik_on = kMode == 1 ? true : (kExt ? false : (m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f));
   const bool eik_filter = m.cfg.eik_trunc_dist >= 0.f;
 
   // this half's slice of the feature vector
@@ -410,8 +415,23 @@ __global__ void __launch_bounds__(G * 256, 1)
     const int n2 = t2 * 128 + pt;
     float p[3] = {0.f, 0.f, 0.f};
     if (n2 < N32) {
-      load_point_smem(m.x, fr, n2, poses_in_smem ? s->poses : nullptr, p, kMode == 0 ? m.poison : nullptr);
-      if constexpr (kMode != 0) {
+      // finite-difference passes (miso_mapping_step_fd) run over 6 N "virtual" points: virtual index k N + i is
+      // sample i displaced by +eps (k even) / -eps (k odd) along axis k / 2, in world coordinates (diff.py:18-26)
+      int nb = n2, k = -1;
+      if constexpr (kVirt) {
+        if (m.fd_n > 0) {
+          k = n2 / m.fd_n;
+          nb = n2 - k * m.fd_n;
+        }
+      }
+      load_point_smem(m.x, fr, nb, poses_in_smem ? s->poses : nullptr, p, kMode == 0 ? m.poison : nullptr);
+      if constexpr (kVirt) {
+        if (k >= 0) {
+          const float d = (k & 1) ? -m.fd_eps : m.fd_eps;
+          p[0] += (k >> 1) == 0 ? d : 0.f, p[1] += (k >> 1) == 1 ? d : 0.f, p[2] += (k >> 1) == 2 ? d : 0.f;
+        }
+      }
+      if constexpr (kMode == 1 || kMode == 2) {
         if (m.xw) m.xw[3 * (int64_t)n2] = p[0], m.xw[3 * (int64_t)n2 + 1] = p[1], m.xw[3 * (int64_t)n2 + 2] = p[2];
       }
     }
@@ -606,11 +626,15 @@ __global__ void __launch_bounds__(G * 256, 1)
     // loss inputs: fetched here so their latency hides behind the MMA round trip
     float gt = 0.f, wgt = 1.f, sgn = 0.f;
     unsigned vld = 0;
-    if (kMode == 0 && active) {
-      gt = ldg_early_f32(m.gt_sdf + n);
-      vld = ldg_early_u8(m.gt_valid + n);
-      sgn = ldg_early_f32(m.gt_sign + n);
-      if (m.weights) wgt = ldg_early_f32(m.weights + n);
+    if (kStep && active) {
+      if constexpr (kExt) {
+        gt = ldg_early_f32(m.a_ext + n);   // backward with a given cotangent: d total / d sdf(n) arrives here
+      } else {
+        gt = ldg_early_f32(m.gt_sdf + n);
+        vld = ldg_early_u8(m.gt_valid + n);
+        sgn = ldg_early_f32(m.gt_sign + n);
+        if (m.weights) wgt = ldg_early_f32(m.weights + n);
+      }
     }
     if ((warp_u & 7) == 0) tc::mbar_wait(bar, parity);   // one warp polls the mbarrier ...
     group_barrier(grp);                                   // ... the other seven sleep here instead of spinning
@@ -687,7 +711,7 @@ __global__ void __launch_bounds__(G * 256, 1)
       stage_point(tile + tile_stride);
     } else {
       const int n3 = n + 2 * tile_stride * 128;   // two tiles ahead: pull the per-point inputs towards this SM
-      if (n3 < N32) {
+      if (n3 < N32 && !kVirt) {
         prefetch_l1(m.x + 3 * (int64_t)n3);
         prefetch_l1(m.x + 3 * (int64_t)n3 + 2);
         if (fr.ids) prefetch_l1(fr.ids + n3);
@@ -764,6 +788,7 @@ __global__ void __launch_bounds__(G * 256, 1)
       a += up > lo ? m.cfg.weight_fs : (lo > up ? -m.cfg.weight_fs : 0.f);
     }
     a *= sc.y;
+    if constexpr (kExt) a = gt;   // backward with a given cotangent (finite-difference passes): no loss terms of its own
     float v[3] = {0.f, 0.f, 0.f};
     if (eik_on) {
       const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);

@@ -5,8 +5,10 @@
 Two execution paths, both on the GPU:
   * fused   -- ONE kernel does frame->world transform, interpolation of every level, the MLP, its
                analytic spatial gradient, the three loss terms and the scatter of d(total)/d(grid)
-               (miso_mapping_step).  Taken when the model exposes a fused spec (decoder fixed),
-               keyframe poses are locked, grad_method is 'autograd' (or the eikonal weight is 0).
+               (miso_mapping_step).  Taken when the model exposes a fused spec (decoder fixed) and
+               keyframe poses are locked.  grad_method 'finitediff' (the shipped default) runs as
+               four launches (miso_mapping_step_fd): step, six displaced forwards in one launch,
+               eikonal epilogue, six backward scatters in one launch.
   * generic -- the reference's op sequence on torch tensors; the per-level interpolation is the
                twice-differentiable miso_b200.cuda_gridsample op, the eikonal gradient comes from
                miso_b200.diff.gradient3d.  Handles trainable decoders, unlocked poses, finite
@@ -84,6 +86,7 @@ class MappingWorkspace:
         lib = _lib.load()
         self.partials = torch.zeros(int(lib.miso_mapping_workspace_floats()), dtype=torch.float32, device=device)
         self.eik_count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.fd = None   # (12 N) floats of the finite-difference step, grown on demand
 
     @classmethod
     def get(cls, device):
@@ -95,9 +98,10 @@ class MappingWorkspace:
 
 def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
                      weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None,
-                     n_total=0, count_allreduce=None):
+                     n_total=0, count_allreduce=None, fd_eps=None):
     """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
-    terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped)."""
+    terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped).
+    `fd_eps` selects the finite-difference eikonal term (miso_mapping_step_fd) instead of the analytic one."""
     lib = _lib.load()
     dev = x.device
     N = x.shape[0]
@@ -124,10 +128,20 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
         if PROFILE_EVENTS is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(dev))
-        _lib.check(lib.miso_mapping_step(
-            C.byref(fld), C.byref(dec), C.byref(fr) if fr is not None else None, x.data_ptr(), N, gt_sdf.data_ptr(),
-            gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg), ws.eik_count.data_ptr(),
-            ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out), stream), "mapping_step")
+        if fd_eps is not None and cfg.eik_mode == 1:
+            if ws.fd is None or ws.fd.numel() < 12 * N:
+                ws.fd = torch.empty(12 * N, dtype=torch.float32, device=dev)
+            _lib.check(lib.miso_mapping_step_fd(
+                C.byref(fld), C.byref(dec), C.byref(fr) if fr is not None else None, x.data_ptr(), N,
+                gt_sdf.data_ptr(), gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg),
+                ws.eik_count.data_ptr(), ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out),
+                float(fd_eps), ws.fd.data_ptr(), stream), "mapping_step_fd")
+        else:
+            _lib.check(lib.miso_mapping_step(
+                C.byref(fld), C.byref(dec), C.byref(fr) if fr is not None else None, x.data_ptr(), N,
+                gt_sdf.data_ptr(), gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg),
+                ws.eik_count.data_ptr(), ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out), stream),
+                "mapping_step")
         if PROFILE_EVENTS is not None:
             e1.record(torch.cuda.current_stream(dev))
             PROFILE_EVENTS.append((e0, e1))
@@ -220,9 +234,16 @@ class MisoLossMappingBase:
         if self.loss_type not in ("L1", "L2"):
             return False
         if self.weight_eik > 0 and self.grad_method != "autograd":
-            return False
+            # finite differences run fused (miso_mapping_step_fd) where the two-threads-per-point kernel applies
+            if self.grad_method != "finitediff" or not self._fd_kernel_covers(model):
+                return False
         R, t, _ = self.frame_table(model)
         return not (R.requires_grad or t.requires_grad)
+
+    @staticmethod
+    def _fd_kernel_covers(model) -> bool:
+        shape_ok = (model.num_levels, model.fdim) in {(2, 4), (4, 4), (1, 8), (2, 8), (1, 16)}
+        return shape_ok and all(f.numel() + 4 * f.stride(2) < 2 ** 31 - 1 for f in model.level_tensors())
 
     def compute(self, model, model_input: dict, gt: dict) -> dict:
         coords_frame = model_input["coords_frame"][0]
@@ -244,7 +265,8 @@ class MisoLossMappingBase:
     def _step_cfg(self):
         return dict(loss_type=self.loss_type, weight_sdf=self.weight_sdf, weight_fs=self.weight_fs,
                     weight_eik=self.weight_eik, trunc_dist=self.trunc_dist, eik_trunc_dist=self.eik_trunc_dist,
-                    eik_on=self.weight_eik > 0)
+                    eik_on=self.weight_eik > 0,
+                    fd_eps=self.finite_diff_eps if (self.weight_eik > 0 and self.grad_method == "finitediff") else None)
 
     def _frames(self, model, sample_frame_ids):
         R, t, lut = self.frame_table(model)

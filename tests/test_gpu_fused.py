@@ -443,3 +443,29 @@ def test_locked_keyframes_get_no_pose_gradient_in_mixed_batches():
     lo = O.mapping_loss(o1, mi, gt, poses, "L2", 1.0, 0.0, 0.5, 0.15)
     sum(lo.values()).backward()
     assert rel_err(gr[2], w.grad[0]) < TOL_G and rel_err(gtr[2], tau.grad) < TOL_G
+
+
+@pytest.mark.parametrize("loss_type,eik_trunc,n", [("L1", None, 6000), ("L2", 0.1, 6000), ("L1", None, 50000)])
+def test_mapping_step_fused_finite_difference_eikonal(loss_type, eik_trunc, n):
+    """grad_method='finitediff' (the shipped default, scannet.yaml:48-49) on the FUSED path (fixed decoder): every
+    term and d(total)/d(grid) against the oracle's restatement of diff.py:18-26 + loss.py:754-813."""
+    from miso_b200.loss import MisoLossMapping
+    net, o1, _ = make_pair()
+    mi, gt, (R, t) = _batch(n)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type=loss_type, weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="finitediff", finite_diff_eps=0.024, eik_trunc_dist=eik_trunc)
+    assert L._fused_ok(net)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    sum(v.mean() for v in ld.values()).backward()
+    lo = O.mapping_loss(o1, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, loss_type, 1.0, 0.5, 0.1, 0.15,
+                        finite_diff_eps=0.024, grad_method="finitediff", eik_trunc_dist=eik_trunc)
+    sum(lo.values()).backward()
+    assert set(ld) == set(lo)
+    for k in lo:
+        assert rel_err(ld[k], lo[k]) < TOL_G, k
+    for l in range(2):
+        assert rel_err(net.features[l].feature.grad, o1.features[l].grad) < TOL_G, l

@@ -340,3 +340,27 @@ def test_alignment_variant_rejections():
         pairwise_loss_latent(atlas, None, 0, 1, level=0, align_loss="huber")
     with pytest.raises(NotImplementedError):
         pairwise_loss_latent(atlas, None, 0, 1, level=0, stability_thresh=0.5)
+
+
+def test_fused_finite_difference_step_against_reference_outputs():
+    """miso_mapping_step_fd (four launches) against the reference's own miso_loss_eikonal(..., 'finitediff', 0.024)
+    value and grid gradients: sdf / free-space terms switched off (no valid sample, weight_fs 0) isolate the eikonal."""
+    from miso_b200 import loss as mloss
+    z, gz = load("mapping.npz"), load("gridnet.npz")
+    net = gpu_net(z, gz, num_poses=3)
+    net.unlock_feature()
+    spec = net.fused_spec()
+    assert spec is not None
+    x = T(z["eik.x"]).cuda().contiguous()
+    gts = T(z["eik.gt"]).cuda().reshape(-1).contiguous()
+    N = x.shape[0]
+    feats = net.level_tensors()
+    grads = [torch.zeros_like(f) for f in feats]
+    out = mloss.mapping_step_raw(feats, grads, spec, None, x, gts, torch.zeros(N, dtype=torch.uint8, device="cuda"),
+                                 torch.zeros(N, device="cuda"), None, loss_type="L1", weight_sdf=1.0, weight_fs=0.0,
+                                 weight_eik=1.0, trunc_dist=0.15, eik_trunc_dist=0.05, eik_on=True, fd_eps=0.024)
+    assert float(out[0]) == 0.0 and float(out[1]) == 0.0
+    assert rel_err(out[2], T(z["eik.fd_value"])) < 1e-4
+    assert rel_err(out[3], T(z["eik.fd_value"])) < 1e-4
+    for l in range(2):
+        assert rel_err(grads[l], T(z[f"eik.fd_grad_feat{l}"])) < 1e-4
