@@ -295,8 +295,8 @@ def run_ours(args):
     if not args.no_extras:
         del dev_batches
         torch.cuda.empty_cache()
+        ncd = bench_ncd(device, steps=max(100, min(args.steps, 200)) if world == 1 else 30, world=world, rank=rank)
         if world == 1:
-            ncd = bench_ncd(device, steps=max(100, min(args.steps, 200)))
             torch_gpu = torch_gpu_arm(device)
         align = bench_align(device, iters=10, warmup=2, world=world, rank=rank)
         if world > 1:
@@ -556,42 +556,102 @@ def build_ncd_model(device, poses):
     return net
 
 
-def bench_ncd(device, steps=100, warmup=5):
-    """One GPU: fused step + Adam on the NCD quad grid (levels 20x90x90 + 100x450x450 x C4: the 324 MB fine level, its
-    gradient and the Adam moments are NOT L2-resident, so dram traffic is meaningful here), 2^22 LiDAR-sampled points."""
-    from miso_b200 import loss as mloss, synth
+def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
+    """Fused step + Adam on the NCD quad grid (levels 20x90x90 + 100x450x450 x C4: the 324 MB fine level, its gradient
+    and the Adam moments are NOT L2-resident, so dram traffic is meaningful here), 2^22 LiDAR-sampled points per step.
+    One GPU: the whole batch.  N GPUs (strong scaling, same global batch): (a) the north star's split -- contiguous
+    point chunks + all_reduce of the dense grid gradients + replicated Adam; (b) the domain-decomposed split of
+    miso_b200.sharded_fit -- z-slabs of the fine level, one-plane halos.  Every rank also times the single-GPU step, so
+    the speed-ups are measured inside one run; parameters after the timed steps are compared with the single-GPU run."""
+    import torch.distributed as dist
+    from miso_b200 import dist as mdist, loss as mloss, synth
     from miso_b200.loss import MisoLossMapping
+    from miso_b200.sharded_fit import SlabShardedFit
     from miso_b200.trainer import GridTrainer
     mi, gt, poses = synth.lidar_batch(NCD_POINTS, num_kf=NCD_KF, seed=3)
-    net = build_ncd_model(device, poses)
-    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net, MisoLossMapping(**NCD_LOSS), None,
-                     device=device)
     dmi = {k: v.to(device) for k, v in mi.items()}
     dgt = {k: v.to(device) for k, v in gt.items()}
-    for _ in range(warmup):
-        tr.train_step(dmi, dgt)
-    torch.cuda.synchronize()
+
+    def sync_max(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, n):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            terms = step_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return sync_max(e0.elapsed_time(e1) / n), terms
+
+    # ---- one GPU, whole batch ----
+    net1 = build_ncd_model(device, poses)
+    tr1 = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net1, MisoLossMapping(**NCD_LOSS), None,
+                      device=device)
     mloss.PROFILE_EVENTS = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        terms = tr.train_step(dmi, dgt)
-    e1.record()
-    torch.cuda.synchronize()
-    kms = float(np.mean([a.elapsed_time(b) for a, b in mloss.PROFILE_EVENTS]))
+    ms1, terms1 = timed(lambda: tr1.train_step(dmi, dgt), steps)
+    kms = float(np.mean([a.elapsed_time(b) for a, b in mloss.PROFILE_EVENTS[warmup:]]))
     mloss.PROFILE_EVENTS = None
-    ms = e0.elapsed_time(e1) / steps
     peak, peak_src = measured_hbm_peak()
     achieved = BYTES_PER_POINT * NCD_POINTS / (kms * 1e-3) / 1e9
     traffic, tsrc = ncu_traffic("ncd_2p22")
     out = {"workload": "Newer-College-quad single grid (20x90x90 + 100x450x450 x C4, decoder 8-64-64-1 fixed), 2^22 "
-                       "LiDAR-sampled pts/step, L2 sdf + 0.5 free-space (trunc 0.5), Adam joint; one GPU",
-           "steps": steps, "ms_per_step": ms, "points_per_s": NCD_POINTS / (ms * 1e-3),
-           "loss_terms": [float(v) for v in terms.tolist()],
+                       "LiDAR-sampled pts/step, L2 sdf + 0.5 free-space (trunc 0.5), Adam joint",
+           "steps": steps, "ms_per_step": ms1, "points_per_s": NCD_POINTS / (ms1 * 1e-3),
+           "loss_terms": [float(v) for v in terms1.tolist()],
            "roofline": {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved, "peak": peak, "peak_source": peak_src,
                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
-                        "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kms, "kernel_share_of_step": kms / ms}}
-    del tr, net, dmi, dgt
+                        "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kms, "kernel_share_of_step": kms / ms1}}
+    if world > 1:
+        ref_params = [p.detach().clone() for p in net1.level_tensors()]
+        del tr1, net1
+        torch.cuda.empty_cache()
+        total_steps = warmup + steps
+        # ---- (a) point chunks + dense-gradient all_reduce + replicated Adam ----
+        b0, b1 = mdist.shard_points(NCD_POINTS, rank, world)
+        smi = {k: v[:, b0:b1].contiguous() for k, v in dmi.items()}
+        sgt = {k: v[:, b0:b1].contiguous() for k, v in dgt.items()}
+        net_a = build_ncd_model(device, poses)
+        tr_a = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net_a, MisoLossMapping(**NCD_LOSS), None,
+                           device=device)
+        ms_a, terms_a = timed(lambda: tr_a.train_step(smi, sgt, n_total=NCD_POINTS, allreduce=mdist.allreduce_sum_), steps)
+        rel_a = [float((a - b).norm() / b.norm()) for a, b in zip(net_a.level_tensors(), ref_params)]
+        out["point_sharded_allreduce"] = {
+            "ms_per_step": ms_a, "points_per_s": NCD_POINTS / (ms_a * 1e-3), "speedup_vs_1gpu": ms1 / ms_a,
+            "collective": "ncclAllReduce(sum, f32) of both grid levels' dense gradients",
+            "collective_bytes_per_step": sum(p.numel() * 4 for p in net_a.level_tensors()),
+            "param_rel_err_vs_1gpu": rel_a, "loss_rel_err_vs_1gpu": abs(float(terms_a[3]) - float(terms1[3])) / abs(float(terms1[3]))}
+        del tr_a, net_a, smi, sgt
+        torch.cuda.empty_cache()
+        # ---- (b) z-slabs of the fine level, one-plane halos ----
+        net_b = build_ncd_model(device, poses)
+        fit = SlabShardedFit(net_b, MisoLossMapping(**NCD_LOSS), lr=1e-3)
+        bounds = fit.calibrate(dmi)
+        ms_b, terms_b = timed(lambda: fit.step(dmi, dgt), steps)
+        own = int(fit._bufs["count"].item())
+        fit.gather_model()
+        rel_b = [float((a - b).norm() / b.norm()) for a, b in zip(net_b.level_tensors(), ref_params)]
+        cnt = torch.tensor([own], dtype=torch.float64, device=device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+        out["slab_sharded"] = {
+            "ms_per_step": ms_b, "points_per_s": NCD_POINTS / (ms_b * 1e-3), "speedup_vs_1gpu": ms1 / ms_b,
+            "slab_bounds_z_planes": bounds, "max_samples_per_rank": int(cnt.item()),
+            "load_imbalance": float(cnt.item()) * world / NCD_POINTS,
+            "collective": "P2P halo: one z-plane of fine-level gradients up + one plane of parameters down per neighbour, "
+                          "ncclAllReduce of the coarse level's gradient and the 4 loss terms",
+            "collective_bytes_per_step": 2 * fit.plane_elems * 4 + net_b.level_tensors()[0].numel() * 4 + 16,
+            "param_rel_err_vs_1gpu": rel_b, "loss_rel_err_vs_1gpu": abs(float(terms_b[3]) - float(terms1[3])) / abs(float(terms1[3]))}
+        assert max(rel_a) < 1e-4 and max(rel_b) < 1e-4, (rel_a, rel_b)
+        del fit, net_b
     torch.cuda.empty_cache()
     return out
 

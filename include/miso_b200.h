@@ -150,6 +150,9 @@ typedef struct miso_mapping_cfg {
   float grad_scale;       /* upstream d(total) (normally 1) */
   int64_t n_total;        /* denominator of the means; 0 = N.  Point-sharded multi-GPU fits pass the global
                              batch size so that per-rank gradients / loss terms simply sum (all_reduce). */
+  const int32_t* n_device; /* optional DEVICE int32: only the first *n_device (<= N) samples are processed -- the
+                             batch was compacted on the device (miso_slab_select) and the host never learns its
+                             size; requires n_total > 0.  NULL = all N. */
 } miso_mapping_cfg_t;
 
 /* gt arrays are (N) float; valid is uint8/bool (N).  eik_count: device int32 counter holding the
@@ -274,6 +277,16 @@ int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t n
 /* ------------------------------------------------------------------------------------------
  * 4. Helpers around the path.
  * ------------------------------------------------------------------------------------------ */
+/* Domain-decomposed multi-GPU fit: keep the samples of a (replicated) batch whose trilinear cell of one level starts in
+ * z-planes [z_begin, z_end) of that level (Z planes over [zmin, zmax], z = slowest axis of the channels-last level),
+ * compacted to the front of the *_out arrays in batch order within 256-sample chunks; *count (device int32) receives
+ * their number.  Same index arithmetic as the fused kernels, so each sample is owned by exactly one rank and touches
+ * only planes [z_begin, z_end] of that level.  frames / weights / ids_out / weights_out may be NULL. */
+int miso_slab_select(const miso_frames_t* frames, const float* x, int64_t N, float zmin, float zmax, int32_t Z,
+                     int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid, const float* gt_sign,
+                     const float* weights, float* x_out, int64_t* ids_out, float* sdf_out, uint8_t* valid_out,
+                     float* sign_out, float* weights_out, int32_t* count, miso_stream_t stream);
+
 /* 30-bit (10 bits/axis) Morton key of each point inside bound, for L2-local batch ordering. */
 int miso_morton_keys(const float* x, int64_t N, const float bound[6], uint32_t* keys, miso_stream_t stream);
 

@@ -42,7 +42,7 @@ class Frames(C.Structure):
 class MappingCfg(C.Structure):
     _fields_ = [("loss_type", C.c_int32), ("weight_sdf", C.c_float), ("weight_fs", C.c_float),
                 ("weight_eik", C.c_float), ("trunc_dist", C.c_float), ("eik_trunc_dist", C.c_float),
-                ("eik_mode", C.c_int32), ("grad_scale", C.c_float), ("n_total", C.c_int64)]
+                ("eik_mode", C.c_int32), ("grad_scale", C.c_float), ("n_total", C.c_int64), ("n_device", C.c_void_p)]
 
 
 class AlignPair(C.Structure):
@@ -88,6 +88,9 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "miso_align_pose_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "miso_slab_select": (C.c_int, [C.POINTER(Frames), C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "miso_morton_keys": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "miso_transform_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                         C.c_void_p, C.c_void_p]),

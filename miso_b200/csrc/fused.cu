@@ -1473,7 +1473,9 @@ static int launch_tc2(const miso_field_t* field, const miso_decoder_t* dec, cons
                       cudaStream_t s) {
   constexpr size_t smem = sizeof(Tc2Smem<L * C, G>) + 128;
   auto k = m.a_ext ? mapping_step_tc2_kernel<L, C, G, true, 3>
-                   : (tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true, 0> : mapping_step_tc2_kernel<L, C, G, false, 0>);
+                   : (m.cfg.n_device ? mapping_step_tc2_kernel<L, C, G, true, 4>
+                                     : (tc2_paired() ? mapping_step_tc2_kernel<L, C, G, true, 0>
+                                                     : mapping_step_tc2_kernel<L, C, G, false, 0>));
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nblocks = grid_for((m.N + G * 128 - 1) / (G * 128), 1, sm_count());
   k<<<nblocks, G * 256, smem, s>>>(*field, *dec, fr, m);
@@ -1809,7 +1811,11 @@ static int mapping_step_impl(const miso_field_t* field, const miso_decoder_t* de
   m.dbg = tuning().dbg;
   int nblocks = 0;
   const int F_ = field->num_levels * field->level[0].C;
-  if (use_tensor_cores() && fits_int32(field) && tc2_groups() != 0 && F_ % 8 == 0 && N < ((int64_t)1 << 31) - ((int64_t)1 << 26)) {
+  const bool tc2_route = use_tensor_cores() && fits_int32(field) && tc2_groups() != 0 && F_ % 8 == 0 &&
+                         N < ((int64_t)1 << 31) - ((int64_t)1 << 26);
+  MISO_REQUIRE(!cfg->n_device || (tc2_route && cfg->n_total > 0),
+               "mapping_step: n_device needs the two-threads-per-point kernel and an explicit n_total");
+  if (tc2_route) {
     const int G_ = tc2_groups();
     MISO_DISPATCH_LC_TC2(field->num_levels, field->level[0].C, {
       nblocks = G_ == 3 ? launch_tc2<L, C, 3>(field, dec, fr, m, s) : launch_tc2<L, C, 4>(field, dec, fr, m, s);

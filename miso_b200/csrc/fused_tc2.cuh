@@ -302,6 +302,7 @@ __device__ __forceinline__ void scatter_group4_paired(const miso_level_t& lv, co
   }
 }
 
+// kMode: 4 = mode 0 with the number of samples read from device memory (m.cfg.n_device: batch compacted on the device);
 // kMode: 3 = backward pass with a per-point cotangent given by the caller (m.a_ext) over displaced "virtual" points
 // (finite-difference eikonal, miso_mapping_step_fd); mode 2 also understands virtual points.
 // kMode: 0 = whole mapping step (losses + scatter), 1 = forward with Jacobian / grad_x outputs (miso_sdf_forward with
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(G * 256, 1)
   uint64_t* const bar = &s->bar[grp];
   uint32_t parity = 0;
 
-  constexpr bool kStep = kMode == 0 || kMode == 3;   // scatters gradients
+  constexpr bool kStep = kMode == 0 || kMode == 3 || kMode == 4;   // scatters gradients
   constexpr bool kExt = kMode == 3;                  // cotangent given by the caller, no loss terms
   constexpr bool kVirt = kMode == 2 || kMode == 3;   // may run over displaced virtual points
   const bool eik_on = kMode == 1 ? true : (kExt ? false : (m.cfg.eik_mode != 0 && m.cfg.weight_eik != 0.f));
@@ -407,7 +408,10 @@ __global__ void __launch_bounds__(G * 256, 1)
 
   float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
   const int tile_stride = (int)gridDim.x * G;   // 32-bit point indices: the host routes N >= 2^31 - 2^24 elsewhere
-  const int N32 = (int)m.N;
+  // device-side sample count (batch compacted by miso_slab_select): the launch is sized for m.N, tiles past it exit
+  // (kMode 4; mode 0 keeps the count in the constant bank -- one more live register spills in this 64-register kernel)
+  int N32 = (int)m.N;
+  if constexpr (kMode == 4) N32 = min(N32, *m.cfg.n_device);
   // Point work (load, frame->world, normalise) is done ONCE per point, by half 1, one tile ahead: the result is
   // parked in the idle A_lo operand and picked up by both halves after the next group barrier, so the dependent
   // id -> pose -> transform chain and its global-load latency are off the tile's critical path.
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(G * 256, 1)
           nb = n2 - k * m.fd_n;
         }
       }
-      load_point_smem(m.x, fr, nb, poses_in_smem ? s->poses : nullptr, p, kMode == 0 ? m.poison : nullptr);
+      load_point_smem(m.x, fr, nb, poses_in_smem ? s->poses : nullptr, p, (kMode == 0 || kMode == 4) ? m.poison : nullptr);
       if constexpr (kVirt) {
         if (k >= 0) {
           const float d = (k & 1) ? -m.fd_eps : m.fd_eps;
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(G * 256, 1)
         prefetch_l1(m.x + 3 * (int64_t)n3);
         prefetch_l1(m.x + 3 * (int64_t)n3 + 2);
         if (fr.ids) prefetch_l1(fr.ids + n3);
-        if constexpr (kMode == 0) {
+        if constexpr (kMode == 0 || kMode == 4) {
           prefetch_l1(m.gt_sdf + n3);
           prefetch_l1(m.gt_sign + n3);
           prefetch_l1(m.gt_valid + n3);
@@ -813,7 +817,7 @@ __global__ void __launch_bounds__(G * 256, 1)
         scatter_group4(lv, cells[ci], ch, (nz && lv.grad) ? 1u : 0u, a, v[0] * kx, v[1] * ky, v[2] * kz, J + 4 * j);
     }
   }
-  if constexpr (kMode == 0) {
+  if constexpr (kMode == 0 || kMode == 4) {
     float s0 = block_sum(acc_sdf, red);
     float s1 = block_sum(acc_fs, red);
     float s2 = block_sum(acc_eik, red);

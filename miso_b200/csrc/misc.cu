@@ -149,6 +149,71 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Slab selection of a replicated batch (domain-decomposed multi-GPU fit, miso_b200/sharded_fit.py): every rank reads
+// the whole batch and keeps the samples whose trilinear cell of `level` starts in its range of z-planes
+// [z_begin, z_end) (z = the slowest axis of the channels-last level, so a range of planes is one contiguous piece of the
+// level, of its gradient and of the Adam moments).  The z index is computed with the fused kernels' own arithmetic
+// (frame -> world, normalize_coord, unnormalize_nc, floor), so a sample is owned by exactly one rank and every corner
+// it touches lies in planes [z_begin, z_end].  Compaction keeps the order of the samples inside a 256-sample chunk
+// (consecutive ray samples stay adjacent for the merged reductions of the step kernel); the number kept lands in *count.
+__global__ void __launch_bounds__(kThreads)
+    slab_select_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ R,
+                       const float* __restrict__ t, int num_frames, int64_t N, float zmin, float zmax, int Z,
+                       int z_begin, int z_end, const float* __restrict__ sdf, const uint8_t* __restrict__ valid,
+                       const float* __restrict__ sign, const float* __restrict__ weights, float* __restrict__ x_out,
+                       int64_t* __restrict__ ids_out, float* __restrict__ sdf_out, uint8_t* __restrict__ valid_out,
+                       float* __restrict__ sign_out, float* __restrict__ weights_out, int32_t* __restrict__ count) {
+  __shared__ int warp_tot[kThreads / 32];
+  __shared__ int chunk_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t chunks = (N + kThreads - 1) / kThreads;
+  for (int64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const int64_t n = c * kThreads + threadIdx.x;
+    bool keep = false;
+    float a = 0.f, b = 0.f, cc = 0.f;
+    int64_t id = 0;
+    if (n < N) {
+      a = x[3 * n], b = x[3 * n + 1], cc = x[3 * n + 2];
+      float zw = cc;
+      if (ids) {
+        id = ids[n];
+        const int64_t q = (id < 0 || id >= num_frames) ? 0 : id;
+        zw = fmaf(cc, R[q * 9 + 8], fmaf(b, R[q * 9 + 7], a * R[q * 9 + 6])) + t[q * 3 + 2];
+      }
+      const float iz = unnormalize_nc(normalize_coord(zw, zmin, zmax), Z);
+      // NaN (a keyframe without a pose) and far-away samples go to the edge planes: some rank must own them
+      float fz = floorf(iz);
+      fz = fz == fz ? fminf(fmaxf(fz, 0.f), (float)(Z - 1)) : 0.f;
+      const int plane = (int)fz;
+      keep = plane >= z_begin && plane < z_end;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; ++k) {
+        const int v = warp_tot[k];
+        warp_tot[k] = tot;
+        tot += v;
+      }
+      chunk_base = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    if (keep) {
+      const int64_t o = chunk_base + warp_tot[w] + __popc(bal & ((1u << lane) - 1u));
+      x_out[3 * o] = a, x_out[3 * o + 1] = b, x_out[3 * o + 2] = cc;
+      if (ids_out) ids_out[o] = id;
+      sdf_out[o] = sdf[n];
+      valid_out[o] = valid[n];
+      sign_out[o] = sign[n];
+      if (weights_out) weights_out[o] = weights ? weights[n] : 1.f;
+    }
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
   v &= 0x3ffu;
   v = (v | (v << 16)) & 0x030000ffu;
@@ -250,6 +315,28 @@ extern "C" int miso_transform_points(const float* x, const int64_t* ids, const f
   if (N == 0) return MISO_OK;
   transform_kernel<<<grid_for(N, kThreads, sm_count() * 8), kThreads, 0, (cudaStream_t)stream>>>(x, ids, R, t, num_frames, N, y);
   return check_launch("transform_points");
+}
+
+extern "C" int miso_slab_select(const miso_frames_t* frames, const float* x, int64_t N, float zmin, float zmax,
+                                int32_t Z, int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid,
+                                const float* gt_sign, const float* weights, float* x_out, int64_t* ids_out,
+                                float* sdf_out, uint8_t* valid_out, float* sign_out, float* weights_out,
+                                int32_t* count, miso_stream_t stream) {
+  MISO_REQUIRE(count && N >= 0 && (N == 0 || (x && gt_sdf && gt_valid && gt_sign && x_out && sdf_out && valid_out && sign_out)),
+               "slab_select: null argument");
+  MISO_REQUIRE(Z > 0 && zmax > zmin && z_begin >= 0 && z_end <= Z && z_begin <= z_end, "slab_select: bad slab [%d,%d) of %d", z_begin, z_end, Z);
+  const bool have_frames = frames && frames->ids;
+  MISO_REQUIRE(!have_frames || (frames->R && frames->t && frames->num_frames > 0 && ids_out), "slab_select: frames without poses / ids_out");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+  if (N == 0) return check_launch("slab_select(memset)");
+  MISO_REQUIRE(N < ((int64_t)1 << 31), "slab_select: N must fit int32");
+  const int blocks = grid_for((N + kThreads - 1) / kThreads, 1, sm_count() * 8);
+  slab_select_kernel<<<blocks, kThreads, 0, s>>>(x, have_frames ? frames->ids : nullptr, have_frames ? frames->R : nullptr,
+                                                 have_frames ? frames->t : nullptr, have_frames ? frames->num_frames : 0, N,
+                                                 zmin, zmax, Z, z_begin, z_end, gt_sdf, gt_valid, gt_sign, weights, x_out,
+                                                 ids_out, sdf_out, valid_out, sign_out, weights_out, count);
+  return check_launch("slab_select");
 }
 
 extern "C" int miso_morton_keys(const float* x, int64_t N, const float bound[6], uint32_t* keys, miso_stream_t stream) {

@@ -98,10 +98,12 @@ class MappingWorkspace:
 
 def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
                      weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None,
-                     n_total=0, count_allreduce=None, fd_eps=None):
+                     n_total=0, count_allreduce=None, fd_eps=None, n_device=None, count_on=None):
     """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
     terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped).
-    `fd_eps` selects the finite-difference eikonal term (miso_mapping_step_fd) instead of the analytic one."""
+    `fd_eps` selects the finite-difference eikonal term (miso_mapping_step_fd) instead of the analytic one.
+    `n_device` (device int32 tensor) limits the step to the first *n_device samples (batch compacted on the device,
+    miso_b200.sharded_fit); `count_on` is then the FULL batch's gt sdf for the |gt| < eik_trunc count."""
     lib = _lib.load()
     dev = x.device
     N = x.shape[0]
@@ -114,6 +116,7 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
     cfg.eik_mode = 1 if (eik_on and weight_eik > 0) else 0
     cfg.grad_scale = float(grad_scale)
     cfg.n_total = int(n_total)
+    cfg.n_device = n_device.data_ptr() if n_device is not None else None
     fld = _field.make_field(feats, spec.bound, grads, spec.ignore_mask)
     dec = spec.decoder.struct()
     fr = frames.struct() if frames is not None else None
@@ -121,8 +124,9 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
     stream = _lib.stream_ptr(dev)
     with torch.cuda.device(dev):
         if cfg.eik_mode == 1 and eik_trunc_dist is not None:
-            _lib.check(lib.miso_mapping_count(gt_sdf.data_ptr(), N, cfg.eik_trunc_dist, ws.eik_count.data_ptr(),
-                                              stream), "mapping_count")
+            cnt_src = gt_sdf if count_on is None else count_on
+            _lib.check(lib.miso_mapping_count(cnt_src.data_ptr(), cnt_src.numel(), cfg.eik_trunc_dist,
+                                              ws.eik_count.data_ptr(), stream), "mapping_count")
             if count_allreduce is not None:
                 count_allreduce([ws.eik_count])   # point-sharded fit: the eikonal mean runs over all ranks
         if PROFILE_EVENTS is not None:

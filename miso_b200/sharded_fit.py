@@ -1,0 +1,225 @@
+"""Large single-grid fit over several GPUs (BASELINE.json configs[3]) -- domain decomposition.
+
+The reference's loss is a mean over the batch (grid_opt/loss.py:634), so the batch can be split across ranks any way
+that lets the per-rank terms and gradients sum.  Two splits are implemented:
+
+  * `GridTrainer.train_step(n_total=, allreduce=)`  (miso_b200.trainer) -- contiguous point chunks, the dense grid
+    gradients all-reduced before a replicated Adam step.  This is the split the north star names; its cost per step
+    is the all_reduce of the whole fine level (324 MB for the NCD quad grid) plus a full Adam sweep on every rank,
+    neither of which shrinks with the number of GPUs: measured 0.94x at 2 GPUs (profiles/r01_ncd_point_sharded.json).
+
+  * `SlabShardedFit` (this file) -- the batch is split by WHERE the samples fall.  The largest level is cut into
+    contiguous ranges of z-planes (z is the slowest axis of the channels-last layout, so a range of planes is one
+    contiguous piece of the level, of its gradient and of its Adam moments); every rank reads the whole batch (it is
+    replicated: in the reference every process would load the same dataset) and keeps the samples whose cell of that
+    level starts in its planes (`miso_slab_select`, device-side compaction, no host sync), runs the fused step on
+    them with the GLOBAL batch size as denominator, and owns the Adam update of its planes.  A sample touches planes
+    [z, z+1], so what crosses ranks per step is ONE plane of gradients up and one plane of parameters down per
+    neighbour (0.8 MB for the NCD quad grid instead of 324 MB), plus an all_reduce of the small replicated levels'
+    gradients and of the four loss terms.  Slab boundaries balance the sample count (`calibrate`).
+
+Both reproduce the single-GPU step up to the order of the float32 atomics.  `gather_model` re-assembles the full level
+on every rank (checkpointing / meshing).
+"""
+import ctypes as C
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import dist as mdist
+from . import field as _field
+from .loss import MisoLossMapping, _flat_f32, _flat_u8, mapping_step_raw
+from .optim import FusedAdam
+
+
+# ------------------------------------------------------------------------------------------------
+# host logic (device-agnostic torch: exercised by the gloo tests)
+# ------------------------------------------------------------------------------------------------
+def slab_bounds_from_histogram(hist: torch.Tensor, world: int) -> List[int]:
+    """world+1 plane indices b[0]=0 <= ... <= b[world]=Z such that the slabs [b[r], b[r+1]) hold about the same share
+    of `hist` (samples per z-plane) and every slab has at least one plane."""
+    Z = int(hist.numel())
+    if world > Z:
+        raise ValueError(f"{world} ranks for a level of {Z} planes")
+    cum = torch.cumsum(hist.double().cpu(), 0)
+    total = float(cum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        z = int(torch.searchsorted(cum, torch.tensor(target, dtype=torch.float64)).item()) + 1
+        z = max(z, bounds[-1] + 1)              # at least one plane per slab
+        z = min(z, Z - (world - r))             # leave a plane for every later slab
+        bounds.append(z)
+    bounds.append(Z)
+    return bounds
+
+
+def plane_of_points(z_world: torch.Tensor, zmin: float, zmax: float, Z: int) -> torch.Tensor:
+    """z-plane that owns a sample: floor of the level's z index, clamped into [0, Z-1] (NaN -> 0).  Torch restatement
+    of the arithmetic in `slab_select_kernel` / `make_cell` (normalize, unnormalize with align_corners=False, floor);
+    used for the calibration histogram and by the CPU tests."""
+    zn = 2 * (z_world - zmin) / (zmax - zmin) - 1
+    iz = ((zn + 1) * Z - 1) / 2
+    return torch.nan_to_num(torch.floor(iz), nan=0.0).clamp(0, Z - 1).long()
+
+
+def exchange_halo_planes(send_up: Optional[torch.Tensor], recv_from_below: Optional[torch.Tensor],
+                         rank: int, world: int, group=None):
+    """One step of the nearest-neighbour exchange along the slab axis: rank r sends `send_up` to r+1 and receives into
+    `recv_from_below` from r-1 (each None at the ends).  Batched P2P (NCCL on the box, gloo in the tests)."""
+    ops = []
+    if send_up is not None and rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, send_up, rank + 1, group))
+    if recv_from_below is not None and rank > 0:
+        ops.append(dist.P2POp(dist.irecv, recv_from_below, rank - 1, group))
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+
+
+def exchange_halo_planes_down(send_down: Optional[torch.Tensor], recv_from_above: Optional[torch.Tensor],
+                              rank: int, world: int, group=None):
+    """The opposite direction: rank r sends to r-1, receives from r+1."""
+    ops = []
+    if send_down is not None and rank > 0:
+        ops.append(dist.P2POp(dist.isend, send_down, rank - 1, group))
+    if recv_from_above is not None and rank + 1 < world:
+        ops.append(dist.P2POp(dist.irecv, recv_from_above, rank + 1, group))
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+
+
+# ------------------------------------------------------------------------------------------------
+# the trainer
+# ------------------------------------------------------------------------------------------------
+class SlabShardedFit:
+    """Adam fit of one GridNet on a replicated batch, the largest level cut into z-slabs over the ranks."""
+
+    def __init__(self, model, loss: MisoLossMapping, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 rank: Optional[int] = None, world: Optional[int] = None, bounds: Optional[Sequence[int]] = None):
+        r, w = mdist.world()
+        self.rank = r if rank is None else rank
+        self.world = w if world is None else world
+        self.model, self.loss, self.lr, self.betas, self.eps = model, loss, float(lr), betas, float(eps)
+        feats = model.level_tensors()
+        self.slab_level = max(range(len(feats)), key=lambda l: feats[l].numel())
+        f = feats[self.slab_level]
+        _, self.Cc, self.Z, self.Y, self.X = f.shape
+        if f.stride(1) != 1 or f.stride(2) != self.Y * self.X * self.Cc:
+            raise RuntimeError("SlabShardedFit needs the channels_last_3d level layout (z slowest)")
+        self.plane_elems = self.Y * self.X * self.Cc
+        self.zmin, self.zmax = model._bound_host[4], model._bound_host[5]
+        self.bounds = list(bounds) if bounds is not None else [round(self.Z * k / self.world) for k in range(self.world + 1)]
+        self._set_slab()
+        self.step_count = 0
+        self.other = FusedAdam([p for l, p in enumerate(feats) if l != self.slab_level and p.requires_grad],
+                               lr=lr, betas=betas, eps=eps)
+        self._bufs = None
+
+    # ---- slabs ---------------------------------------------------------------------------------------
+    def _set_slab(self):
+        self.zb, self.ze = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        n = (self.ze - self.zb) * self.plane_elems
+        dev = self.model.level_tensors()[self.slab_level].device
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+
+    def _flat(self, t: torch.Tensor) -> torch.Tensor:
+        """(1,C,Z,Y,X) channels-last tensor -> flat (Z, plane_elems) view of its memory."""
+        return t.detach().permute(0, 2, 3, 4, 1).reshape(self.Z, self.plane_elems)
+
+    def calibrate(self, model_input: dict):
+        """Choose slab boundaries that balance the sample count of this batch over the ranks (identical on every rank:
+        the batch is replicated).  Resets the slab's Adam moments; call before the first step."""
+        coords = model_input["coords_frame"][0]
+        ids = model_input["sample_frame_ids"][0, :, 0]
+        R, t, _ = self.loss.frame_table(self.model)
+        zw = torch.einsum("nj,nj->n", R[ids][:, 2, :], coords) + t[ids][:, 2, 0]
+        hist = torch.bincount(plane_of_points(zw, self.zmin, self.zmax, self.Z), minlength=self.Z)
+        self.bounds = slab_bounds_from_histogram(hist, self.world)
+        self._set_slab()
+        return self.bounds
+
+    # ---- one step --------------------------------------------------------------------------------------
+    def _buffers(self, N, dev, need_w):
+        if self._bufs is None or self._bufs["N"] != N:
+            self._bufs = {"N": N, "x": torch.empty((N, 3), dtype=torch.float32, device=dev),
+                          "ids": torch.empty(N, dtype=torch.int64, device=dev),
+                          "sdf": torch.empty(N, dtype=torch.float32, device=dev),
+                          "valid": torch.empty(N, dtype=torch.uint8, device=dev),
+                          "sign": torch.empty(N, dtype=torch.float32, device=dev),
+                          "w": torch.empty(N, dtype=torch.float32, device=dev),
+                          "count": torch.zeros(1, dtype=torch.int32, device=dev),
+                          "halo": torch.empty(self.plane_elems, dtype=torch.float32, device=dev)}
+        return self._bufs
+
+    def step(self, model_input: dict, gt: dict) -> torch.Tensor:
+        """One fit step on the (replicated, device-resident) batch.  Returns the GLOBAL (4,) loss terms
+        [sdf, fs, eik, total]; nothing is synchronised with the host."""
+        lib, m, L = _lib.load(), self.model, self.loss
+        if not L._fused_ok(m) or (L.weight_eik > 0 and L.grad_method != "autograd"):
+            raise RuntimeError("SlabShardedFit runs the fused analytic step (fixed decoder, locked poses)")
+        coords = _field._prep_x(model_input["coords_frame"][0])
+        ids = model_input["sample_frame_ids"][0, :, 0]
+        sdf, valid, sign = _flat_f32(gt["sdf"][0]), _flat_u8(gt["sdf_valid"][0]), _flat_f32(gt["sdf_signs"][0])
+        w = _flat_f32(model_input["weights"][0])
+        N, dev = coords.shape[0], coords.device
+        b = self._buffers(N, dev, True)
+        frames = L._frames(m, ids)
+        fr = frames.struct()
+        stream = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.miso_slab_select(
+                C.byref(fr), coords.data_ptr(), N, float(self.zmin), float(self.zmax), self.Z, self.zb, self.ze,
+                sdf.data_ptr(), valid.data_ptr(), sign.data_ptr(), w.data_ptr(), b["x"].data_ptr(), b["ids"].data_ptr(),
+                b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(),
+                b["count"].data_ptr(), stream), "slab_select")
+        feats = m.level_tensors()
+        grads = []
+        for f in feats:
+            if f.requires_grad and f.grad is None:
+                f.grad = torch.zeros_like(f)
+            grads.append(f.grad if f.requires_grad else None)
+        cfg = L._step_cfg()
+        cfg.pop("fd_eps", None)
+        own_frames = _field.FramesSpec(b["ids"], frames.R, frames.t)
+        # the |gt| < eik_trunc count runs over the FULL batch inside mapping_step_raw when gt_sdf_count is given
+        terms = mapping_step_raw(feats, grads, m.fused_spec(), own_frames, b["x"], b["sdf"], b["valid"], b["sign"], b["w"],
+                                 n_total=N, n_device=b["count"], count_on=sdf, **cfg)
+        self._exchange_and_update(feats, grads, terms, b)
+        return terms
+
+    def _exchange_and_update(self, feats, grads, terms, b):
+        lib = _lib.load()
+        sl, r, W = self.slab_level, self.rank, self.world
+        g, p = self._flat(grads[sl]), self._flat(feats[sl])
+        if W > 1:
+            mdist.allreduce_sum_([gr for l, gr in enumerate(grads) if l != sl and gr is not None] + [terms])
+            # gradient halo: my samples also wrote plane `ze`, which rank r+1 owns
+            exchange_halo_planes(g[self.ze] if self.ze < self.Z else None, b["halo"] if r > 0 else None, r, W)
+            if r > 0:
+                g[self.zb].add_(b["halo"])
+            if self.ze < self.Z:
+                g[self.ze].zero_()
+        self.other.step()
+        self.step_count += 1
+        n = (self.ze - self.zb) * self.plane_elems
+        off = self.zb * self.plane_elems * 4
+        dev = feats[sl].device
+        with torch.cuda.device(dev):
+            _lib.check(lib.miso_adam_step(feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), n, self.lr, float(self.betas[0]), float(self.betas[1]),
+                                          self.eps, self.step_count, 1, _lib.stream_ptr(dev)), "adam_step")
+        if W > 1:
+            # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)
+            exchange_halo_planes_down(p[self.zb] if r > 0 else None, p[self.ze] if self.ze < self.Z else None, r, W)
+
+    @torch.no_grad()
+    def gather_model(self):
+        """Every rank ends up with the full slab level (one broadcast per slab from its owner)."""
+        if self.world == 1:
+            return
+        p = self._flat(self.model.level_tensors()[self.slab_level])
+        for owner in range(self.world):
+            dist.broadcast(p[self.bounds[owner]:self.bounds[owner + 1]], src=owner)

@@ -142,3 +142,76 @@ def test_world2_gloo_partitions_match_single_process():
         assert torch.allclose(a, ref, rtol=1e-3, atol=1e-5)
     assert res["gathered"] == [0, 1, 2, 3, 4] and res["owners"] == [0, 1, 0, 1, 0]
     assert res["mine"] == [(0, 1), (1, 2)]
+
+
+# ------------------------------------------------------------------------------------------------
+# domain-decomposed fit (miso_b200.sharded_fit): slab ownership + one-plane halos == the full gradient
+# ------------------------------------------------------------------------------------------------
+def _slab_worker(rank, world, port, q):
+    from miso_b200 import sharded_fit as sf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    try:
+        model = _model()
+        N = 3001
+        mi, gt, (R, t) = synth.rgbd_batch(N, num_kf=3, bound=BOUND, seed=6, wall_margin=0.3)
+        poses = {k: (R[k], t[k]) for k in range(3)}
+        ids = mi["sample_frame_ids"][0, :, 0]
+        zw = torch.einsum("nj,nj->n", R[ids][:, 2, :], mi["coords_frame"][0]) + t[ids][:, 2, 0]
+        fine = model.features[1]
+        Z = fine.shape[2]
+        plane = sf.plane_of_points(zw, BOUND[2][0], BOUND[2][1], Z)
+        bounds = sf.slab_bounds_from_histogram(torch.bincount(plane, minlength=Z), world)
+        zb, ze = bounds[rank], bounds[rank + 1]
+        own = torch.nonzero((plane >= zb) & (plane < ze))[:, 0]
+        sel = lambda d: {k: v[:, own] for k, v in d.items()}
+        ld = O.mapping_loss(model, sel(mi), sel(gt), poses, "L1", 1.0, 0.0, 0.1, 0.15)
+        (sum(ld.values()) * mdist.sharded_loss_scale(own.numel(), N)).backward()
+        gf = fine.grad.permute(0, 2, 3, 4, 1).reshape(Z, -1).contiguous()        # (Z, plane) like SlabShardedFit._flat
+        touched = torch.nonzero(gf.abs().sum(1))[:, 0]
+        assert touched.numel() > 0 and int(touched.min()) >= zb and int(touched.max()) <= min(ze, Z - 1)   # planes [zb, ze]
+        halo = torch.zeros_like(gf[0])
+        sf.exchange_halo_planes(gf[ze].clone() if ze < Z else None, halo if rank > 0 else None, rank, world)
+        if rank > 0:
+            gf[zb] += halo
+        coarse = model.features[0].grad.clone()
+        mdist.allreduce_sum_([coarse])
+        # fake optimiser step on the owned planes, then the parameter halo
+        pf = fine.detach().permute(0, 2, 3, 4, 1).reshape(Z, -1).clone()
+        pf[zb:ze] -= 0.5 * gf[zb:ze]
+        recv = torch.zeros_like(pf[0])
+        sf.exchange_halo_planes_down(pf[zb].clone() if rank > 0 else None, recv if ze < Z else None, rank, world)
+        q.put({"rank": rank, "bounds": bounds, "own": own.numel(), "grad_slab": gf[zb:ze].clone(), "coarse": coarse,
+               "param_first_plane": pf[zb].clone(), "param_halo": recv if ze < Z else None})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_world2_gloo_slab_sharded_fit_matches_single_process():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=500) for _ in range(2)], key=lambda d: d["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    model = _model()
+    N = 3001
+    mi, gt, (R, t) = synth.rgbd_batch(N, num_kf=3, bound=BOUND, seed=6, wall_margin=0.3)
+    sum(O.mapping_loss(model, mi, gt, {k: (R[k], t[k]) for k in range(3)}, "L1", 1.0, 0.0, 0.1, 0.15).values()).backward()
+    Z = model.features[1].shape[2]
+    full = model.features[1].grad.permute(0, 2, 3, 4, 1).reshape(Z, -1)
+    b = res[0]["bounds"]
+    assert b == res[1]["bounds"] and b[0] == 0 and b[-1] == Z and res[0]["own"] + res[1]["own"] == N
+    assert min(res[0]["own"], res[1]["own"]) > 0.25 * N                     # boundaries balance the sample count
+    for r in range(2):
+        assert torch.allclose(res[r]["grad_slab"], full[b[r]:b[r + 1]], rtol=1e-3, atol=1e-7), r
+        assert torch.allclose(res[r]["coarse"], model.features[0].grad, rtol=1e-3, atol=1e-7)
+    # rank 0 received rank 1's freshly updated first plane
+    assert torch.equal(res[0]["param_halo"], res[1]["param_first_plane"])

@@ -469,3 +469,48 @@ def test_mapping_step_fused_finite_difference_eikonal(loss_type, eik_trunc, n):
         assert rel_err(ld[k], lo[k]) < TOL_G, k
     for l in range(2):
         assert rel_err(net.features[l].feature.grad, o1.features[l].grad) < TOL_G, l
+
+
+def test_slab_sharded_fit_single_rank_equals_trainer():
+    """miso_b200.sharded_fit on one rank (slab = the whole level): device-side slab selection + device sample count +
+    slab Adam reproduce GridTrainer.train_step; and a HALF slab keeps exactly the samples the ownership rule names."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.sharded_fit import SlabShardedFit, plane_of_points
+    from miso_b200.trainer import GridTrainer
+    mi, gt, (R, t) = _batch(20000)
+    nets = []
+    for _ in range(2):
+        net, _, _ = make_pair()
+        for k in range(R.shape[0]):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        net.lock_pose()
+        nets.append(net)
+    mk = lambda: MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                                 grad_method="autograd", eik_trunc_dist=0.1)
+    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, nets[0], mk(), None, device="cuda")
+    fit = SlabShardedFit(nets[1], mk(), lr=1e-3, rank=0, world=1)
+    dmi, dgt = _to_cuda(mi), _to_cuda(gt)
+    assert fit.calibrate(dmi) == [0, fit.Z]
+    for _ in range(3):
+        a = tr.train_step(dmi, dgt)
+        b = fit.step(dmi, dgt)
+        assert rel_err(b, a) < 1e-5
+    assert int(fit._bufs["count"].item()) == 20000
+    for pa, pb in zip(nets[0].level_tensors(), nets[1].level_tensors()):
+        assert rel_err(pb, pa) < 1e-5
+    # ownership rule of a half slab, bit-exact against the torch restatement
+    half = SlabShardedFit(nets[1], mk(), lr=1e-3, rank=1, world=2, bounds=[0, fit.Z // 2, fit.Z])
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    half._exchange_and_update = lambda *a, **k: None          # selection + kernel only: no process group here
+    half.step(dmi, dgt)
+    ids = mi["sample_frame_ids"][0, :, 0]
+    zw = torch.einsum("nj,nj->n", R[ids][:, 2, :], mi["coords_frame"][0]) + t[ids][:, 2, 0]
+    plane = plane_of_points(zw.cuda(), SMALL_BOUND[2][0], SMALL_BOUND[2][1], fit.Z)
+    want = torch.nonzero(plane >= fit.Z // 2)[:, 0]
+    n = int(half._bufs["count"].item())
+    assert abs(n - want.numel()) <= 2          # fma contraction in the torch restatement can move a boundary sample
+    got_sdf = torch.sort(half._bufs["sdf"][:n]).values
+    if n == want.numel():
+        assert torch.equal(got_sdf, torch.sort(gt["sdf"][0, :, 0].cuda()[want]).values)
