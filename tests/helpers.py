@@ -99,7 +99,7 @@ def oracle_like(omodel, dtype=torch.float64):
                            second_order=omodel.second_order)
 
 
-def drop_fragile_points(omodel, mi, gt, poses, n_keep, trunc, margin=2e-5):
+def drop_fragile_points(omodel, mi, gt, poses, n_keep, trunc, margin=2e-5, fd_eps=None):
     """Remove the samples that sit on a kink of the loss, then keep the first `n_keep` of the rest.
 
     d(total)/d(grid) is discontinuous where a ReLU pre-activation of the decoder, the L1 residual, or the
@@ -122,6 +122,14 @@ def drop_fragile_points(omodel, mi, gt, poses, n_keep, trunc, margin=2e-5):
             pre.clear()
             pred = omodel(xw[b:e])[:, 0]
             h_min = torch.minimum(pre[0].abs().min(1).values, pre[1].abs().min(1).values)
+            if fd_eps is not None:   # the finite-difference eikonal also evaluates the decoder at x +- eps e_d
+                for d in range(3):
+                    for sgn in (1.0, -1.0):
+                        off = torch.zeros(3)
+                        off[d] = sgn * fd_eps
+                        pre.clear()
+                        omodel(xw[b:e] + off)
+                        h_min = torch.minimum(h_min, torch.minimum(pre[0].abs().min(1).values, pre[1].abs().min(1).values))
             g = gt["sdf"][0, b:e, 0]
             up, lo = torch.relu(pred - g), torch.relu(trunc - pred)
             fragile = (h_min < margin) | ((pred - g).abs() < margin) | ((up - lo).abs() < margin) \

@@ -450,8 +450,13 @@ def test_mapping_step_fused_finite_difference_eikonal(loss_type, eik_trunc, n):
     """grad_method='finitediff' (the shipped default, scannet.yaml:48-49) on the FUSED path (fixed decoder): every
     term and d(total)/d(grid) against the oracle's restatement of diff.py:18-26 + loss.py:754-813."""
     from miso_b200.loss import MisoLossMapping
+    from helpers import drop_fragile_points
     net, o1, _ = make_pair()
-    mi, gt, (R, t) = _batch(n)
+    mi, gt, (R, t) = _batch(n + n // 4)
+    # samples within rounding distance of a ReLU / L1 kink (at x or at one of the six displaced points) get a
+    # one-sided derivative that depends on the summation order; one such flip is ~1e-3 of the gradient norm at this
+    # batch size, so they are taken out of the batch for BOTH sides (tests/test_gpu_baseline_sizes.py, module doc)
+    mi, gt, _ = drop_fragile_points(o1, mi, gt, (R, t), n, 0.15, fd_eps=0.024)
     for k in range(R.shape[0]):
         net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
     net.unlock_feature()
