@@ -11,6 +11,8 @@
 // the block-level reduction (float partials -> float64 atomics, 24 or 51 values per pair).
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace miso {
@@ -118,7 +120,10 @@ __global__ void __launch_bounds__(kThreads)
     align_batch_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
                        const float* __restrict__ poses, double* __restrict__ out) {
   constexpr int NACC = kAlignAcc + (kGN ? kGnAcc : 0);
-  __shared__ float red[NACC][kThreads / 32];
+  // L1 / cos weigh a sample by 1/|r| resp. 1/(|f_s||f_d|): per-sample magnitudes spread over orders of magnitude and
+  // the pose-gradient sums cancel heavily, so these two variants accumulate in float64 (the L2 hot path stays float32)
+  using AccT = typename std::conditional<kLoss != 0, double, float>::type;
+  __shared__ AccT red[NACC][kThreads / 32];
   const int pi = blockIdx.y;
   const miso_align_pair_t pr = pairs[pi];
   if (pr.enabled && *pr.enabled == 0) return;
@@ -138,9 +143,9 @@ __global__ void __launch_bounds__(kThreads)
   const int LU = pr.levels_used;
   const int K = LU * C;
 
-  float acc[NACC];
+  AccT acc[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NACC; ++i) acc[i] = 0;
 
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < pr.M; n += (int64_t)gridDim.x * blockDim.x) {
     float p[3] = {pr.p[3 * n], pr.p[3 * n + 1], pr.p[3 * n + 2]};
@@ -297,8 +302,13 @@ __global__ void __launch_bounds__(kThreads)
       acc[2 + i] += gam[i];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        acc[5 + 3 * i + j] = fmaf(gam[i], u[j], acc[5 + 3 * i + j]);
-        acc[14 + 3 * i + j] = fmaf(gam[i], p[j], acc[14 + 3 * i + j]);
+        if constexpr (kLoss != 0) {
+          acc[5 + 3 * i + j] += (double)gam[i] * (double)u[j];
+          acc[14 + 3 * i + j] += (double)gam[i] * (double)p[j];
+        } else {
+          acc[5 + 3 * i + j] = fmaf(gam[i], u[j], acc[5 + 3 * i + j]);
+          acc[14 + 3 * i + j] = fmaf(gam[i], p[j], acc[14 + 3 * i + j]);
+        }
       }
     }
   }
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kThreads)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < NACC; ++i) {
-    float v = acc[i];
+    AccT v = acc[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[i][w] = v;
@@ -381,18 +391,16 @@ __global__ void __launch_bounds__(kThreads)
   const int row_len = pr0.levels_used & 0xffff;
   const int rows_per_plane = pr0.levels_used >> 16;
   if (row_len > 0) {
-    // Lattice path.  A thread takes a segment of kS consecutive vertices of one row.  The map vertex -> q is affine
-    // along the row (up to fp32 rounding) and the destination bound is convex, so
-    //   * both end points inside the bound shrunk by a margin  => every vertex of the segment is inside,
-    //   * both end points outside the SAME face grown by the margin => every vertex is outside,
-    //   * otherwise the interior vertices are tested one by one, with the very same arithmetic as the plain path.
-    // The margin (1e-3 + 1e-5 |bound|) is two orders above the rounding error of the two chained transforms, so the
-    // count is the exact per-vertex count; ~85 % of the segments of two overlapping room-sized submaps are decided
-    // by their end points alone.
-    constexpr int kS = 16;
-    const int segs_per_row = (row_len + kS - 1) / kS;
+    // Lattice path.  A thread takes one ROW of the lattice (row_len collinear, equispaced vertices).  Along the row the
+    // map vertex index -> q is affine up to fp32 rounding, and the destination bound is convex, so the inside indices
+    // form an interval.  For every destination the thread intersects the row with the bound twice in closed form:
+    // with the bound SHRUNK by a margin (indices in that interval are surely inside) and GROWN by it (indices outside
+    // that interval are surely outside); only the few indices between the two intervals are tested one by one, with
+    // the very same arithmetic as the plain path.  The margin (1e-3 + 1e-5 |bound|) is two orders above the rounding
+    // error of the two chained transforms and of the linear model, so the count is the exact per-vertex count; a row
+    // that runs (nearly) parallel to a face inside the margin band simply has a long uncertain interval and is
+    // counted vertex by vertex.  Work per source drops from O(vertices) transforms to O(rows x destinations).
     const int64_t rows = pr0.M / row_len;
-    const int64_t nseg = rows * segs_per_row;
     // Whole-lattice pre-test per destination: every vertex lies in the hull of the lattice's 8 extreme corners (first
     // and last vertex give the per-axis extremes); if all 8 are beyond the same face of the destination bound (same
     // margin as below) the pair's count is exactly 0 and the destination drops out of the loops.  Most pairs of a
@@ -433,32 +441,22 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
     const int nact = s_nact;
     if (nact == 0) return;
-    // whole warps stay in the loop together (the reduction below is warp-wide): iterate on the warp's first segment
-    for (int64_t sg0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); sg0 < nseg; sg0 += stride) {
-      const int64_t sg = sg0 + lane;
-      const bool live = sg < nseg;
-      const int64_t row = live ? sg / segs_per_row : 0;
-      const int x0 = live ? (int)(sg - row * segs_per_row) * kS : 0;
-      const int len = live ? min(kS, row_len - x0) : 0;
-      // coordinates from the three per-axis tables inside p (a few KB, cache-resident) instead of streaming the
-      // 12 B/vertex list: the kernel no longer touches HBM at all
-      const int64_t iz = row / rows_per_plane, iy = row - iz * rows_per_plane;
+    const float last = (float)(row_len - 1);
+    const float inv_last = row_len > 1 ? 1.0f / last : 0.f;
+    // whole warps stay in the loop together (the reduction below is warp-wide): iterate on the warp's first row
+    for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); r0 < rows; r0 += stride) {
+      const int64_t row = r0 + lane;
+      const bool live = row < rows;
+      // coordinates from the three per-axis tables inside p (a few KB, cache-resident): the kernel never streams the
+      // 12 B/vertex list
+      const int64_t iz = live ? row / rows_per_plane : 0, iy = live ? row - iz * rows_per_plane : 0;
       const float py = __ldg(pr0.p + 3 * (iy * row_len) + 1);
       const float pz = __ldg(pr0.p + 3 * (iz * row_len * rows_per_plane) + 2);
-      float u[kS][3];
-#pragma unroll
-      for (int v = 0; v < kS; ++v) {
-        float p[3] = {0.f, py, pz};
-        if (v < len) p[0] = __ldg(pr0.p + 3 * (x0 + v));
-        xform(A1, b1, p, u[v]);
-      }
-      // last live vertex of the segment (len is almost always kS; the selects keep the code branch-free)
-      float ul[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        ul[i] = u[0][i];
-#pragma unroll
-        for (int v = 1; v < kS; ++v) ul[i] = (v == len - 1) ? u[v][i] : ul[i];
+      float u0[3], u1[3];
+      {
+        const float pa[3] = {__ldg(pr0.p), py, pz}, pb[3] = {__ldg(pr0.p + 3 * (row_len - 1)), py, pz};
+        xform(A1, b1, pa, u0);
+        xform(A1, b1, pb, u1);
       }
       for (int ja = 0; ja < nact; ++ja) {
         const int j = s_act[ja];
@@ -470,27 +468,44 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int i = 0; i < 6; ++i) bd[i] = s_bound[j][i];
         unsigned hits = 0;
-        float qa[3], qb[3];
-        xform(A2, b2, u[0], qa);
-        xform(A2, b2, ul, qb);
-        bool all_in = true, all_out = false;
+        if (live) {
+          float q0[3], q1[3];
+          xform(A2, b2, u0, q0);
+          xform(A2, b2, u1, q1);
+          // index intervals: [slo, shi] surely inside (shrunk bound), [plo, phi] possibly inside (grown bound)
+          float slo = 0.f, shi = last, plo = 0.f, phi = last;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float lo = bd[2 * k], hi = bd[2 * k + 1];
-          const float eps = s_eps[j][k];
-          all_in = all_in && fminf(qa[k], qb[k]) >= lo + eps && fmaxf(qa[k], qb[k]) <= hi - eps;
-          all_out = all_out || fmaxf(qa[k], qb[k]) < lo - eps || fminf(qa[k], qb[k]) > hi + eps;
-        }
-        // decide per WARP (32 adjacent segments = 256 lattice vertices) so the branch never diverges
-        if (__all_sync(0xffffffffu, all_in || len == 0)) {
-          hits = (unsigned)len;
-        } else if (!__all_sync(0xffffffffu, all_out || len == 0)) {
-          if (len > 0) hits = (in_bound(qa, bd) ? 1u : 0u) + ((len > 1 && in_bound(qb, bd)) ? 1u : 0u);
-#pragma unroll
-          for (int v = 1; v < kS - 1; ++v) {
-            float q[3];
-            xform(A2, b2, u[v], q);
-            hits += (v < len - 1 && in_bound(q, bd)) ? 1u : 0u;
+          for (int k = 0; k < 3; ++k) {
+            const float lo = bd[2 * k], hi = bd[2 * k + 1], eps = s_eps[j][k];
+            const float d = (q1[k] - q0[k]) * inv_last;   // change of q_k per index step
+            if (fabsf(d) < 1e-12f) {
+              if (!(q0[k] >= lo + eps && q0[k] <= hi - eps)) slo = 1.f, shi = 0.f;   // not surely inside anywhere
+              if (!(q0[k] >= lo - eps && q0[k] <= hi + eps)) plo = 1.f, phi = 0.f;   // surely outside everywhere
+            } else {
+              const float inv = 1.0f / d;
+              float a = (lo + eps - q0[k]) * inv, b = (hi - eps - q0[k]) * inv;
+              slo = fmaxf(slo, fminf(a, b)), shi = fminf(shi, fmaxf(a, b));
+              a = (lo - eps - q0[k]) * inv, b = (hi + eps - q0[k]) * inv;
+              plo = fmaxf(plo, fminf(a, b)), phi = fminf(phi, fmaxf(a, b));
+            }
+          }
+          // one more index of slack on each side for the rounding of the interval arithmetic itself
+          int i_slo = (int)ceilf(slo) + 1, i_shi = (int)floorf(shi) - 1;
+          int i_plo = max(0, (int)floorf(plo) - 1), i_phi = min(row_len - 1, (int)ceilf(phi) + 1);
+          if (!(phi >= plo)) i_plo = 1, i_phi = 0;          // empty (also catches NaN)
+          if (!(shi >= slo) || i_shi < i_slo) i_slo = i_phi + 1, i_shi = i_phi;   // no sure part: test all of [plo, phi]
+          i_slo = max(i_slo, i_plo), i_shi = min(i_shi, i_phi);
+          if (i_shi >= i_slo) hits = (unsigned)(i_shi - i_slo + 1);
+          for (int i = i_plo; i <= i_phi; ++i) {
+            if (i == i_slo && i_shi >= i_slo) {   // skip the sure part
+              i = i_shi;
+              continue;
+            }
+            const float p[3] = {__ldg(pr0.p + 3 * i), py, pz};
+            float uu[3], q[3];
+            xform(A1, b1, p, uu);
+            xform(A2, b2, uu, q);
+            hits += in_bound(q, bd) ? 1u : 0u;
           }
         }
         const unsigned tot = __reduce_add_sync(0xffffffffu, hits);
