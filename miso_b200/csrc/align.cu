@@ -200,34 +200,38 @@ __global__ void __launch_bounds__(kThreads)
           gq[l * C + ch][0] = dx[ch] * kx, gq[l * C + ch][1] = dy[ch] * ky, gq[l * C + ch][2] = dz[ch] * kz;
         }
       }
-      float ss = 0.f, dd = 0.f, sd = 0.f, r2 = 0.f;
+      // the per-sample factors cancel heavily where |f_d| is small (1/|f_d| weights against a projection that removes
+      // the f_d direction): the few scalars per sample are formed in float64, the interpolation stays float32
+      double ss = 0, dd = 0, sd = 0, r2 = 0;
 #pragma unroll
       for (int k = 0; k < MISO_MAX_LEVELS * C; ++k) {
         if (k >= K) continue;
-        const float r = fsv[k] - fdv[k];
-        r2 = fmaf(r, r, r2), ss = fmaf(fsv[k], fsv[k], ss), dd = fmaf(fdv[k], fdv[k], dd), sd = fmaf(fsv[k], fdv[k], sd);
+        const double a = fsv[k], b = fdv[k];
+        r2 += (a - b) * (a - b), ss += a * a, dd += b * b, sd += a * b;
       }
-      float a_s = 0.f, a_d = 0.f;   // d(loss_i)/d(f_d) = a_s * f_s + a_d * f_d
+      double a_s = 0, a_d = 0;   // d(loss_i)/d(f_d) = a_s * f_s + a_d * f_d
       if constexpr (kLoss == 1) {
-        const float nr = sqrtf(r2);
-        rr = nr;                                   // loss_i = |r|_2 ; d/df_d = -(f_s - f_d)/|r| (0 at r = 0, as autograd)
-        if (nr > 0.f) a_s = -1.f / nr, a_d = 1.f / nr;
+        const double nr = sqrt(r2);
+        rr = (float)nr;                            // loss_i = |r|_2 ; d/df_d = -(f_s - f_d)/|r| (0 at r = 0, as autograd)
+        if (nr > 0) a_s = -1.0 / nr, a_d = 1.0 / nr;
       } else {
-        const float eps = 1e-8f;
-        const float ns = sqrtf(ss), nd = sqrtf(dd);
-        const float cs_ = fmaxf(ns, eps), cd_ = fmaxf(nd, eps);
-        rr = 1.f - sd / (cs_ * cd_);
+        const double eps = 1e-8;
+        const double ns = sqrt(ss), nd = sqrt(dd);
+        const double cs_ = fmax(ns, eps), cd_ = fmax(nd, eps);
+        rr = (float)(1.0 - sd / (cs_ * cd_));
         // cos = (f_s/cs).(f_d/cd), cd = max(|f_d|, eps):  d cos/d f_d = f_s/(cs cd) - [|f_d| > eps] (f_s.f_d) f_d/(cs cd^2 |f_d|)
-        a_s = -1.f / (cs_ * cd_);
-        a_d = nd > eps ? sd / (cs_ * cd_ * cd_ * nd) : 0.f;
+        a_s = -1.0 / (cs_ * cd_);
+        a_d = nd > eps ? sd / (cs_ * cd_ * cd_ * nd) : 0.0;
       }
+      double g0 = 0, g1 = 0, g2 = 0;
 #pragma unroll
       for (int k = 0; k < MISO_MAX_LEVELS * C; ++k) {
         if (k >= K) continue;
-        const float c = fmaf(a_s, fsv[k], a_d * fdv[k]);
-        gam[0] = fmaf(c, gq[k][0], gam[0]), gam[1] = fmaf(c, gq[k][1], gam[1]), gam[2] = fmaf(c, gq[k][2], gam[2]);
+        const double c = a_s * (double)fsv[k] + a_d * (double)fdv[k];
+        g0 += c * (double)gq[k][0], g1 += c * (double)gq[k][1], g2 += c * (double)gq[k][2];
       }
-      acc[23] += sqrtf(r2);
+      gam[0] = (float)g0, gam[1] = (float)g1, gam[2] = (float)g2;
+      acc[23] += sqrt(r2);
     } else {
     for (int l = 0; l < LU; ++l) {
       float fs[C], fd[C], dx[C], dy[C], dz[C];

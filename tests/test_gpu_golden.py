@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from helpers import rel_err
+from oracle import oracle as O
 from miso_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -293,16 +294,43 @@ def _variants_atlas(z):
     return atlas
 
 
-def _check_pair(atlas, z, tag, **kw):
+def _oracle64_pose_grads(z, level, align_loss):
+    """The same loss in float64 through the oracle: the arbiter when float32 conditioning limits the comparison."""
+    bound = z["bound"].tolist()
+    subs = [O.OracleGridNet(bound, [T(z[f"sm{i}.feat{l}"]).double() for l in range(2)], None) for i in range(2)]
+    atlas = O.OracleAtlas(subs, [T(z[f"sm{i}.R"]).double() for i in range(2)], [T(z[f"sm{i}.t"]).double() for i in range(2)])
+    for q in atlas.rot + atlas.tra:
+        q.data = q.data.double()
+    src32 = O.OracleGridNet(bound, [T(z[f"sm0.feat{l}"]) for l in range(2)], None)
+    coords = O.coordinates_for_alignment(src32, level).double()      # the float32 sample positions, promoted
+    Rs, ts = atlas.updated_submap_pose(0)
+    Rd, td = atlas.updated_submap_pose(1)
+    val = O.pairwise_loss_latent(subs[0], subs[1], coords, Rs, ts, Rd, td, level, align_loss=align_loss)
+    val.backward()
+    return [atlas.rot[i].grad for i in range(2)], [atlas.tra[i].grad for i in range(2)]
+
+
+def _check_pair(atlas, z, tag, adjudicate=None, **kw):
+    """`adjudicate=(level, loss)`: where a float32 gradient is ill-conditioned (the cos loss weighs samples by 1/|f_d|
+    against a projection that removes the f_d direction; the reference's own float32 autograd and the closed form in
+    float32 differ by 2e-3 there) the kernel must be no further from the float64 oracle than 1.5x the reference is."""
     from miso_b200.align import pairwise_loss_latent
     for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
         p.grad = None
     (key, val), = pairwise_loss_latent(atlas, None, 0, 1, device="cuda", **kw).items()
     val.backward()
     assert rel_err(val, T(z[f"{tag}.loss"])) < 1e-5, tag
+    truth = None
     for i in range(2):
-        assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"{tag}.grad_rot{i}"])) < 1e-4, (tag, "rot", i)
-        assert rel_err(atlas.translation_corrections[i].grad, T(z[f"{tag}.grad_tra{i}"])) < 1e-4, (tag, "tra", i)
+        for kind, got in (("rot", atlas.rotation_corrections[i].grad), ("tra", atlas.translation_corrections[i].grad)):
+            want = T(z[f"{tag}.grad_{kind}{i}"])
+            e = rel_err(got, want)
+            if e >= 1e-4 and adjudicate is not None:
+                truth = truth or _oracle64_pose_grads(z, *adjudicate)
+                t64 = truth[0 if kind == "rot" else 1][i]
+                assert rel_err(got, t64) <= max(1e-4, 1.5 * rel_err(want, t64)), (tag, kind, i, rel_err(got, t64), rel_err(want, t64))
+            else:
+                assert e < 1e-4, (tag, kind, i, e)
 
 
 @pytest.mark.parametrize("loss", ["L1", "cos"])
@@ -312,7 +340,7 @@ def test_alignment_loss_variants_against_reference_outputs(loss):
     z = load("align_variants.npz")
     atlas = _variants_atlas(z)
     for level in range(2):
-        _check_pair(atlas, z, f"{loss}.L{level}", level=level, align_loss=loss)
+        _check_pair(atlas, z, f"{loss}.L{level}", adjudicate=(level, loss), level=level, align_loss=loss)
 
 
 def test_alignment_truncation_pruning_against_reference_outputs():
