@@ -96,3 +96,37 @@ def test_tracker_normal_equations_follow_reference_formula():
     b = J.T @ (w * r)
     Ho, bo, _ = O.lm_normal_equations(om2, xf, gt_sdf, Rwf, twf, loss_type="GM", gm_scale=0.1, lm_lambda=1e-4)
     assert rel_err(Ho, H) < 1e-5 and rel_err(bo, b) < 1e-5
+
+
+def test_adapter_patches_reference_classes_and_leaves_cpu_behaviour_alone():
+    """miso_b200.adapter.patch_reference(): the reference's own GridNet / FeatureGrid / loss gain the CUDA routes, CPU
+    tensors keep flowing through the reference's original methods (bit-identical results), unpatch restores them."""
+    import grid_opt.diff as rdiff
+    import grid_opt.loss as rloss
+    import grid_opt.models.grid_modules as rgm
+    import grid_opt.models.grid_net as rgn
+    from miso_b200 import adapter
+    net = _ref_net(3)
+    mi, gt, (R, t) = synth.rgbd_batch(2000, num_kf=4, bound=BOUND, seed=3, wall_margin=0.3)
+    for k in range(4):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    x = torch.rand(500, 3) * 2 - 1
+    L = rloss.MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.0, weight_fs=0.1, trunc_dist=0.15)
+    before = (net(x).detach().clone(), net.query_feature(x).detach().clone(),
+              {k: float(v) for k, v in L.compute(net, mi, gt).items()})
+    originals = (rgn.GridNet.forward, rgm.FeatureGrid.interpolate, rloss.MisoLossMappingBase.compute, rdiff.gradient3d)
+    names = adapter.patch_reference()
+    try:
+        assert {"forward", "interpolate", "query_feature", "compute", "gradient3d"} <= set(names)
+        assert rgn.GridNet.forward is not originals[0] and hasattr(rgn.GridNet, "forward_with_gradient")
+        assert net.fused_spec() is None                      # CPU model: the fused path does not apply ...
+        after = (net(x).detach(), net.query_feature(x).detach(), {k: float(v) for k, v in L.compute(net, mi, gt).items()})
+        assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1]) and before[2] == after[2]   # ... and nothing changes
+        Rk, tk = net.all_kf_poses()
+        R0, t0 = net.updated_kf_pose(2)
+        assert torch.allclose(Rk[2], R0) and torch.equal(tk[2], t0)
+    finally:
+        adapter.unpatch_reference()
+    assert (rgn.GridNet.forward, rgm.FeatureGrid.interpolate, rloss.MisoLossMappingBase.compute, rdiff.gradient3d) == originals
+    assert not hasattr(rgn.GridNet, "forward_with_gradient")
