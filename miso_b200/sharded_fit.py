@@ -124,6 +124,8 @@ class SlabShardedFit:
         dev = self.model.level_tensors()[self.slab_level].device
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        # "ever touched" bitmap of the slab (one bit per 4-float voxel): never-touched voxels cost one gradient read
+        self.touched = torch.zeros((n // 4 + 31) // 32, dtype=torch.int32, device=dev)
 
     def _flat(self, t: torch.Tensor) -> torch.Tensor:
         """(1,C,Z,Y,X) channels-last tensor -> flat (Z, plane_elems) view of its memory."""
@@ -208,9 +210,10 @@ class SlabShardedFit:
         off = self.zb * self.plane_elems * 4
         dev = feats[sl].device
         with torch.cuda.device(dev):
-            _lib.check(lib.miso_adam_step(feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), n, self.lr, float(self.betas[0]), float(self.betas[1]),
-                                          self.eps, self.step_count, 1, _lib.stream_ptr(dev)), "adam_step")
+            _lib.check(lib.miso_adam_step_tracked(
+                feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), self.touched.data_ptr(), n, self.lr, float(self.betas[0]),
+                float(self.betas[1]), self.eps, self.step_count, 1, _lib.stream_ptr(dev)), "adam_step")
         if W > 1:
             # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)
             exchange_halo_planes_down(p[self.zb] if r > 0 else None, p[self.ze] if self.ze < self.Z else None, r, W)
