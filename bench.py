@@ -580,11 +580,14 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         return float(t.item())
 
     def timed(step_fn, n):
+        terms = None
         for _ in range(warmup):
-            step_fn()
+            terms = step_fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        if n == 0:
+            return 0.0, terms
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
@@ -636,7 +639,18 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         net_b = build_ncd_model(device, poses)
         fit = SlabShardedFit(net_b, MisoLossMapping(**NCD_LOSS), lr=1e-3)
         bounds = fit.calibrate(dmi)
-        ms_b, terms_b = timed(lambda: fit.step(dmi, dgt), steps)
+        ms_b_eager, _ = timed(lambda: fit.step(dmi, dgt), 0)        # warm-up steps only, eager
+        replay = fit.graphed_step(dmi, dgt)                            # + 2 steps (one eager, one during capture)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_b = steps - 2
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(n_b):
+            terms_b = replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_b = sync_max(e0.elapsed_time(e1) / n_b)
         own = int(fit._bufs["count"].item())
         fit.gather_model()
         rel_b = [float((a - b).norm() / b.norm()) for a, b in zip(net_b.level_tensors(), ref_params)]
@@ -644,7 +658,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
         out["slab_sharded"] = {
             "ms_per_step": ms_b, "points_per_s": NCD_POINTS / (ms_b * 1e-3), "speedup_vs_1gpu": ms1 / ms_b,
-            "slab_bounds_z_planes": bounds, "max_samples_per_rank": int(cnt.item()),
+            "cuda_graph": True, "slab_bounds_z_planes": bounds, "max_samples_per_rank": int(cnt.item()),
             "load_imbalance": float(cnt.item()) * world / NCD_POINTS,
             "collective": "P2P halo: one z-plane of fine-level gradients up + one plane of parameters down per neighbour, "
                           "ncclAllReduce of the coarse level's gradient and the 4 loss terms",

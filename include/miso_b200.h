@@ -322,6 +322,13 @@ int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* tou
 int miso_set_tuning(const char* key, int32_t value);
 int miso_get_tuning(const char* key);
 
+/* The same step (tracked when `touched` != NULL) with the step count kept on the DEVICE: *step_counter (int32) is
+ * incremented and the bias-correction scalars are written to scalars[2] by a one-thread kernel in front of the sweep,
+ * so the launch sequence is identical every step and a whole training step can be captured in a CUDA graph. */
+int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr, float beta1,
+                       float beta2, float eps, int32_t* step_counter, float* scalars, int32_t zero_grad,
+                       miso_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the
  *    3xTF32 split, activations in TMEM, weights in shared memory): D (M,64) = A (M,64) * W^T

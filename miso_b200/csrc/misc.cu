@@ -45,7 +45,9 @@ int sm_count() {
 //   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(kThreads)
     adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
-                int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero) {
+                int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero,
+                const float* __restrict__ dev_scalars) {
+  if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];   // device-side step counter (CUDA graphs)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 gv = reinterpret_cast<float4*>(g)[i];
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     adam_tracked_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         uint32_t* __restrict__ touched, int64_t n4, float lr, float b1, float b2, float eps,
-                        float step_size, float bc2_sqrt, int zero) {
+                        float step_size, float bc2_sqrt, int zero, const float* __restrict__ dev_scalars) {
+  if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int64_t n4r = (n4 + 31) & ~(int64_t)31;   // whole warps stay in the loop (ballot below)
@@ -288,8 +291,38 @@ extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n,
   const float bc2_sqrt = (float)sqrt(bc2);
   const int blocks = grid_for(n4 > 0 ? n4 : n, kThreads, sm_count() * 8);
   adam_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, step_size,
-                                                             bc2_sqrt, zero_grad);
+                                                             bc2_sqrt, zero_grad, nullptr);
   return check_launch("adam_step");
+}
+
+// step = ++(*counter); scalars = {lr / (1 - b1^step), sqrt(1 - b2^step)} in float64, exactly the host formula above
+__global__ void adam_tick_kernel(int32_t* __restrict__ counter, float lr, float b1, float b2, float* __restrict__ scalars) {
+  const int step = *counter + 1;
+  *counter = step;
+  scalars[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
+  scalars[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+}
+
+extern "C" int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, int32_t* step_counter, float* scalars,
+                                  int32_t zero_grad, miso_stream_t stream) {
+  MISO_REQUIRE(p && g && m && v && step_counter && scalars, "adam_step_dev: null tensor");
+  MISO_REQUIRE(n >= 0, "adam_step_dev: n >= 0 required");
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, s>>>(step_counter, lr, beta1, beta2, scalars);
+  if (n == 0) return check_launch("adam_step_dev(tick)");
+  const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
+  if (touched) {
+    MISO_REQUIRE(aligned && n % 4 == 0, "adam_step_dev: the tracked variant needs 16-byte aligned tensors and n % 4 == 0");
+    const int64_t n4 = n / 4;
+    adam_tracked_kernel<<<grid_for(n4, kThreads, sm_count() * 8), kThreads, 0, s>>>(p, g, m, v, touched, n4, lr, beta1, beta2,
+                                                                                   eps, 0.f, 1.f, zero_grad, scalars);
+  } else {
+    const int64_t n4 = aligned ? n / 4 : 0;
+    adam_kernel<<<grid_for(n4 > 0 ? n4 : n, kThreads, sm_count() * 8), kThreads, 0, s>>>(p, g, m, v, n4, n, lr, beta1, beta2,
+                                                                                         eps, 0.f, 1.f, zero_grad, scalars);
+  }
+  return check_launch("adam_step_dev");
 }
 
 extern "C" int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
@@ -304,7 +337,8 @@ extern "C" int miso_adam_step_tracked(float* p, float* g, float* m, float* v, ui
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const int blocks = grid_for(n4, kThreads, sm_count() * 8);
   adam_tracked_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, touched, n4, lr, beta1, beta2, eps,
-                                                                     (float)((double)lr / bc1), (float)sqrt(bc2), zero_grad);
+                                                                     (float)((double)lr / bc1), (float)sqrt(bc2), zero_grad,
+                                                                     nullptr);
   return check_launch("adam_step_tracked");
 }
 

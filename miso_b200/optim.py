@@ -13,11 +13,14 @@ from . import _lib
 
 class FusedAdam:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 zero_grad_in_step=True, track_touched=True):
+                 zero_grad_in_step=True, track_touched=True, device_step=False):
         self.params = [p for p in params]
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.zero_grad_in_step = zero_grad_in_step
         self.track_touched = track_touched
+        # device_step: the per-tensor step counter lives on the GPU (miso_adam_step_dev), so `step()` enqueues the same
+        # launches every time and can be captured in a CUDA graph; state["step"] then mirrors the number of calls
+        self.device_step = device_step
         self.state = {}
         self.param_groups = [{"params": self.params, "lr": self.lr}]
 
@@ -28,6 +31,9 @@ class FusedAdam:
             if self.track_touched and p.numel() % 4 == 0 and p.data_ptr() % 16 == 0:
                 # one bit per 4-float voxel: never-touched voxels are skipped after reading only their gradient
                 st["touched"] = torch.zeros((p.numel() // 4 + 31) // 32, dtype=torch.int32, device=p.device)
+            if self.device_step:
+                st["step_dev"] = torch.zeros(1, dtype=torch.int32, device=p.device)
+                st["scalars"] = torch.zeros(2, dtype=torch.float32, device=p.device)
             self.state[p] = st
         return st
 
@@ -56,6 +62,15 @@ class FusedAdam:
             m, v = st["exp_avg"], st["exp_avg_sq"]
             if m.stride() != p.stride() or v.stride() != p.stride():
                 raise RuntimeError("FusedAdam: optimizer state layout diverged from the parameter layout")
+            if self.device_step:
+                tracked = "touched" in st and g.data_ptr() % 16 == 0
+                with torch.cuda.device(p.device):
+                    _lib.check(lib.miso_adam_step_dev(
+                        p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                        st["touched"].data_ptr() if tracked else None, p.numel(), self.lr, self.betas[0], self.betas[1],
+                        self.eps, st["step_dev"].data_ptr(), st["scalars"].data_ptr(), int(self.zero_grad_in_step),
+                        _lib.stream_ptr(p.device)), "adam_step")
+                continue
             if "touched" in st and g.data_ptr() % 16 == 0:
                 with torch.cuda.device(p.device):
                     _lib.check(lib.miso_adam_step_tracked(

@@ -114,7 +114,7 @@ class SlabShardedFit:
         self._set_slab()
         self.step_count = 0
         self.other = FusedAdam([p for l, p in enumerate(feats) if l != self.slab_level and p.requires_grad],
-                               lr=lr, betas=betas, eps=eps)
+                               lr=lr, betas=betas, eps=eps, device_step=True)
         self._bufs = None
 
     # ---- slabs ---------------------------------------------------------------------------------------
@@ -126,6 +126,9 @@ class SlabShardedFit:
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         # "ever touched" bitmap of the slab (one bit per 4-float voxel): never-touched voxels cost one gradient read
         self.touched = torch.zeros((n // 4 + 31) // 32, dtype=torch.int32, device=dev)
+        # step counter + bias-correction scalars on the device: every step enqueues the same launches (CUDA graph)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
 
     def _flat(self, t: torch.Tensor) -> torch.Tensor:
         """(1,C,Z,Y,X) channels-last tensor -> flat (Z, plane_elems) view of its memory."""
@@ -210,13 +213,36 @@ class SlabShardedFit:
         off = self.zb * self.plane_elems * 4
         dev = feats[sl].device
         with torch.cuda.device(dev):
-            _lib.check(lib.miso_adam_step_tracked(
+            _lib.check(lib.miso_adam_step_dev(
                 feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
                 self.exp_avg_sq.data_ptr(), self.touched.data_ptr(), n, self.lr, float(self.betas[0]),
-                float(self.betas[1]), self.eps, self.step_count, 1, _lib.stream_ptr(dev)), "adam_step")
+                float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), 1,
+                _lib.stream_ptr(dev)), "adam_step")
         if W > 1:
             # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)
             exchange_halo_planes_down(p[self.zb] if r > 0 else None, p[self.ze] if self.ze < self.Z else None, r, W)
+
+    def graphed_step(self, model_input: dict, gt: dict):
+        """Capture `step` on these (device-resident, fixed-address) batch tensors into a CUDA graph -- slab selection,
+        fused step, the NCCL halo exchanges / all_reduce and both Adam sweeps -- after one eager step on a side stream
+        (module loading, NCCL channel setup; it counts as a training step).  Returns `replay() -> loss terms`: one
+        graph launch per step, which matters here because a step is ~15 short launches and collectives."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.step(model_input, gt)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            terms = self.step(model_input, gt)
+        self._graph = graph   # keep alive
+
+        def replay():
+            graph.replay()
+            return terms
+        return replay
 
     @torch.no_grad()
     def gather_model(self):
