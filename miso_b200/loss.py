@@ -129,7 +129,8 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
                                               ws.eik_count.data_ptr(), stream), "mapping_count")
             if count_allreduce is not None:
                 count_allreduce([ws.eik_count])   # point-sharded fit: the eikonal mean runs over all ranks
-        if PROFILE_EVENTS is not None:
+        profile = PROFILE_EVENTS is not None and not torch.cuda.is_current_stream_capturing()
+        if profile:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(dev))
         if fd_eps is not None and cfg.eik_mode == 1:
@@ -146,7 +147,7 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
                 gt_sdf.data_ptr(), gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg),
                 ws.eik_count.data_ptr(), ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out), stream),
                 "mapping_step")
-        if PROFILE_EVENTS is not None:
+        if profile:
             e1.record(torch.cuda.current_stream(dev))
             PROFILE_EVENTS.append((e0, e1))
     return loss_out

@@ -207,6 +207,10 @@ class GridTrainer:
         self.grid_training_mode = cfg.get("grid_training_mode", "coordinate+joint")
         if cfg.get("optimizer", "adam") != "adam":
             raise NotImplementedError("fused trainer implements optimizer: adam (the shipped configs)")
+        # cuda_graph: Adam keeps its step counters on the device and `graphed_train_step` replays one captured graph
+        # per (batch buffers, level schedule state) instead of issuing the step's launches from Python
+        self.cuda_graph = bool(cfg.get("cuda_graph", False))
+        self._graphs = {}
         self.train_dict = {"loss": []}
         self.total_steps = 0
         self.set_optimizer()
@@ -216,8 +220,8 @@ class GridTrainer:
         self.level_optimizers: List[FusedAdam] = []
         if self.grid_training_mode != "joint":
             for level in range(m.num_levels):
-                self.level_optimizers.append(FusedAdam(m.params_at_level(level), lr=self.lr))
-        self.joint_optimizer = FusedAdam(list(m.parameters()), lr=self.lr)
+                self.level_optimizers.append(FusedAdam(m.params_at_level(level), lr=self.lr, device_step=self.cuda_graph))
+        self.joint_optimizer = FusedAdam(list(m.parameters()), lr=self.lr, device_step=self.cuda_graph)
         self.reset_convergence_check()
         if self.grid_training_mode in ("coordinate", "coordinate+joint"):
             self.active_level = 0
@@ -263,6 +267,32 @@ class GridTrainer:
         self.total_steps += 1
         return terms
 
+    def graphed_train_step(self, model_input, gt) -> torch.Tensor:
+        """`train_step` on device batch tensors that live at FIXED addresses (a resident batch, a staging slot), as ONE
+        CUDA-graph launch: the first call for a given (buffers, active level, optimizer) runs eagerly (module loading,
+        first-use allocations), the second captures the step and replays it, later calls only replay.  Every call is
+        exactly one training step.  The returned (4,) loss tensor is the graph's static output: read or copy it before
+        the next replay of the same graph."""
+        if not self.cuda_graph:
+            raise RuntimeError("GridTrainer was built without cfg['cuda_graph'] = True (Adam needs device-side step counters)")
+        key = (tuple(v.data_ptr() for v in model_input.values()), tuple(v.data_ptr() for v in gt.values()),
+               self.active_level, id(self.optimizer))
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "warm"
+            return self.train_step(model_input, gt)
+        if entry == "warm":
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                terms = self.train_step(model_input, gt)
+            self.total_steps -= 1           # the capture itself ran nothing
+            entry = self._graphs[key] = (graph, terms)
+        graph, terms = entry
+        graph.replay()
+        self.total_steps += 1
+        return terms
+
     def train_epoch(self, epoch):
         model_input, gt = self.batch_fn(epoch)
         model_input, gt = prepare_batch(model_input, gt, self.device)
@@ -287,7 +317,7 @@ class GridTrainer:
             nxt = next(it, None)
             nslot = st.stage(nxt) if nxt is not None else None
             model_input, gt = st.acquire(slot)
-            terms = self.train_step(model_input, gt)
+            terms = self.graphed_train_step(model_input, gt) if self.cuda_graph else self.train_step(model_input, gt)
             st.release(slot)
             if loss_sink is not None:
                 loss_sink[i].copy_(terms, non_blocking=True)
