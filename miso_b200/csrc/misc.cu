@@ -95,43 +95,58 @@ __global__ void __launch_bounds__(kThreads)
                         uint32_t* __restrict__ touched, int64_t n4, float lr, float b1, float b2, float eps,
                         float step_size, float bc2_sqrt, int zero, const float* __restrict__ dev_scalars) {
   if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // A warp takes kU consecutive bitmap words = kU x 32 voxels per trip and issues all of their loads before it touches
+  // any of them: with one voxel per thread per trip the sweep over a mostly-untouched level (one 16-byte gradient load
+  // and nothing else per voxel) ran at ~1.2 TB/s, latency-bound; kU independent loads per thread bring it to the HBM rate.
+  constexpr int kU = 4;
   const int lane = threadIdx.x & 31;
-  const int64_t n4r = (n4 + 31) & ~(int64_t)31;   // whole warps stay in the loop (ballot below)
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t word_next = i0 < n4r ? touched[i0 >> 5] : 0u;
-  for (int64_t i = i0; i < n4r; i += stride) {
-    const bool live = i < n4;
-    const uint32_t word = word_next;                                        // fetched one iteration ahead, so the
-    if (i + stride < n4r) word_next = touched[(i + stride) >> 5];            // data loads below do not wait for it
-    const bool was = (word >> lane) & 1u;
-    // a voxel that was touched before needs p, m, v whatever its gradient is now: issue those loads together with
-    // the gradient's instead of after it (one memory round trip per iteration instead of two)
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), mv = gv, vv = gv, pv = gv;
-    if (live) gv = reinterpret_cast<float4*>(g)[i];
-    if (live && was) {
-      mv = reinterpret_cast<float4*>(m)[i];
-      vv = reinterpret_cast<float4*>(v)[i];
-      pv = reinterpret_cast<float4*>(p)[i];
-    }
-    const bool gnz = gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f;
-    const uint32_t now = __ballot_sync(0xffffffffu, was || gnz);
-    if (lane == 0 && now != word) touched[i >> 5] = now;
-    if (!live || !(was || gnz)) continue;
-    if (!was) pv = reinterpret_cast<float4*>(p)[i];   // first touch: m = v = 0 by construction
-    float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
-          va[4] = {vv.x, vv.y, vv.z, vv.w};
+  const int64_t nwords = (n4 + 31) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w0 = warp0 * kU; w0 < nwords; w0 += nwarps * kU) {
+    uint32_t word[kU];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ma[e] = ma[e] + (ga[e] - ma[e]) * (1.f - b1);
-      va[e] = va[e] * b2 + (1.f - b2) * ga[e] * ga[e];
-      float denom = sqrtf(va[e]) / bc2_sqrt + eps;
-      pa[e] = pa[e] - step_size * (ma[e] / denom);
+    for (int u = 0; u < kU; ++u) word[u] = (w0 + u < nwords) ? touched[w0 + u] : 0u;
+    float4 gv[kU], mv[kU], vv[kU], pv[kU];
+    bool live[kU], was[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = (w0 + u) * 32 + lane;
+      live[u] = (w0 + u < nwords) && i < n4;
+      was[u] = (word[u] >> lane) & 1u;
+      gv[u] = mv[u] = vv[u] = pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[u]) gv[u] = reinterpret_cast<float4*>(g)[i];
+      // a voxel that was touched before needs p, m, v whatever its gradient is now: issue those loads together with
+      // the gradient's instead of after it (one memory round trip per trip instead of two)
+      if (live[u] && was[u]) {
+        mv[u] = reinterpret_cast<float4*>(m)[i];
+        vv[u] = reinterpret_cast<float4*>(v)[i];
+        pv[u] = reinterpret_cast<float4*>(p)[i];
+      }
     }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
-    if (zero && gnz) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (w0 + u >= nwords) continue;          // warp-uniform
+      const int64_t i = (w0 + u) * 32 + lane;
+      const bool gnz = gv[u].x != 0.f || gv[u].y != 0.f || gv[u].z != 0.f || gv[u].w != 0.f;
+      const uint32_t now = __ballot_sync(0xffffffffu, was[u] || gnz);
+      if (lane == 0 && now != word[u]) touched[w0 + u] = now;
+      if (!live[u] || !(was[u] || gnz)) continue;
+      if (!was[u]) pv[u] = reinterpret_cast<float4*>(p)[i];   // first touch: m = v = 0 by construction
+      float pa[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, ga[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w},
+            ma[4] = {mv[u].x, mv[u].y, mv[u].z, mv[u].w}, va[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ma[e] = ma[e] + (ga[e] - ma[e]) * (1.f - b1);
+        va[e] = va[e] * b2 + (1.f - b2) * ga[e] * ga[e];
+        float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+        pa[e] = pa[e] - step_size * (ma[e] / denom);
+      }
+      reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+      reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+      reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+      if (zero && gnz) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
