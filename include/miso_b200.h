@@ -279,7 +279,7 @@ int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t n
  * ------------------------------------------------------------------------------------------ */
 /* Domain-decomposed multi-GPU fit: keep the samples of a (replicated) batch whose trilinear cell of one level starts in
  * z-planes [z_begin, z_end) of that level (Z planes over [zmin, zmax], z = slowest axis of the channels-last level),
- * compacted to the front of the *_out arrays in batch order within 256-sample chunks; *count (device int32) receives
+ * compacted to the front of the *_out arrays in batch order within 1024-sample chunks; *count (device int32) receives
  * their number.  Same index arithmetic as the fused kernels, so each sample is owned by exactly one rank and touches
  * only planes [z_begin, z_end] of that level.  frames / weights / ids_out / weights_out may be NULL. */
 int miso_slab_select(const miso_frames_t* frames, const float* x, int64_t N, float zmin, float zmax, int32_t Z,

@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(kThreads)
 // [z_begin, z_end) (z = the slowest axis of the channels-last level, so a range of planes is one contiguous piece of the
 // level, of its gradient and of the Adam moments).  The z index is computed with the fused kernels' own arithmetic
 // (frame -> world, normalize_coord, unnormalize_nc, floor), so a sample is owned by exactly one rank and every corner
-// it touches lies in planes [z_begin, z_end].  Compaction keeps the order of the samples inside a 256-sample chunk
+// it touches lies in planes [z_begin, z_end].  Compaction keeps the order of the samples inside a 1024-sample chunk
 // (consecutive ray samples stay adjacent for the merged reductions of the step kernel); the number kept lands in *count.
+constexpr int kSelPer = 4;   // consecutive samples per thread: a block trip covers 1024 samples with two barriers
+
 __global__ void __launch_bounds__(kThreads)
     slab_select_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ R,
                        const float* __restrict__ t, int num_frames, int64_t N, float zmin, float zmax, int Z,
@@ -184,29 +186,47 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ int warp_tot[kThreads / 32];
   __shared__ int chunk_base;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t chunks = (N + kThreads - 1) / kThreads;
+  constexpr int kChunk = kThreads * kSelPer;
+  const int64_t chunks = (N + kChunk - 1) / kChunk;
   for (int64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
-    const int64_t n = c * kThreads + threadIdx.x;
-    bool keep = false;
-    float a = 0.f, b = 0.f, cc = 0.f;
-    int64_t id = 0;
-    if (n < N) {
-      a = x[3 * n], b = x[3 * n + 1], cc = x[3 * n + 2];
-      float zw = cc;
+    const int64_t n0 = c * kChunk + (int64_t)threadIdx.x * kSelPer;
+    float px[kSelPer][3];
+    int64_t id[kSelPer];
+    unsigned keep = 0;
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+      const int64_t n = n0 + k;
+      id[k] = 0;
+      px[k][0] = px[k][1] = px[k][2] = 0.f;
+      if (n < N) {
+        px[k][0] = x[3 * n], px[k][1] = x[3 * n + 1], px[k][2] = x[3 * n + 2];
+        if (ids) id[k] = ids[n];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+      if (n0 + k >= N) continue;
+      float zw = px[k][2];
       if (ids) {
-        id = ids[n];
-        const int64_t q = (id < 0 || id >= num_frames) ? 0 : id;
-        zw = fmaf(cc, R[q * 9 + 8], fmaf(b, R[q * 9 + 7], a * R[q * 9 + 6])) + t[q * 3 + 2];
+        const int64_t q = (id[k] < 0 || id[k] >= num_frames) ? 0 : id[k];
+        zw = fmaf(px[k][2], R[q * 9 + 8], fmaf(px[k][1], R[q * 9 + 7], px[k][0] * R[q * 9 + 6])) + t[q * 3 + 2];
       }
       const float iz = unnormalize_nc(normalize_coord(zw, zmin, zmax), Z);
       // NaN (a keyframe without a pose) and far-away samples go to the edge planes: some rank must own them
       float fz = floorf(iz);
       fz = fz == fz ? fminf(fmaxf(fz, 0.f), (float)(Z - 1)) : 0.f;
       const int plane = (int)fz;
-      keep = plane >= z_begin && plane < z_end;
+      keep |= (plane >= z_begin && plane < z_end) ? (1u << k) : 0u;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_tot[w] = __popc(bal);
+    // exclusive prefix of the per-thread keep counts: inside the warp by shuffles, across warps through shared memory
+    const int mine = __popc(keep);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[w] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
       int tot = 0;
@@ -219,14 +239,18 @@ __global__ void __launch_bounds__(kThreads)
       chunk_base = tot ? atomicAdd(count, tot) : 0;
     }
     __syncthreads();
-    if (keep) {
-      const int64_t o = chunk_base + warp_tot[w] + __popc(bal & ((1u << lane) - 1u));
-      x_out[3 * o] = a, x_out[3 * o + 1] = b, x_out[3 * o + 2] = cc;
-      if (ids_out) ids_out[o] = id;
+    int64_t o = (int64_t)chunk_base + warp_tot[w] + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+      if (!((keep >> k) & 1u)) continue;
+      const int64_t n = n0 + k;
+      x_out[3 * o] = px[k][0], x_out[3 * o + 1] = px[k][1], x_out[3 * o + 2] = px[k][2];
+      if (ids_out) ids_out[o] = id[k];
       sdf_out[o] = sdf[n];
       valid_out[o] = valid[n];
       sign_out[o] = sign[n];
       if (weights_out) weights_out[o] = weights ? weights[n] : 1.f;
+      ++o;
     }
     __syncthreads();
   }
@@ -380,7 +404,7 @@ extern "C" int miso_slab_select(const miso_frames_t* frames, const float* x, int
   cudaMemsetAsync(count, 0, sizeof(int32_t), s);
   if (N == 0) return check_launch("slab_select(memset)");
   MISO_REQUIRE(N < ((int64_t)1 << 31), "slab_select: N must fit int32");
-  const int blocks = grid_for((N + kThreads - 1) / kThreads, 1, sm_count() * 8);
+  const int blocks = grid_for((N + kThreads * kSelPer - 1) / (kThreads * kSelPer), 1, sm_count() * 8);
   slab_select_kernel<<<blocks, kThreads, 0, s>>>(x, have_frames ? frames->ids : nullptr, have_frames ? frames->R : nullptr,
                                                  have_frames ? frames->t : nullptr, have_frames ? frames->num_frames : 0, N,
                                                  zmin, zmax, Z, z_begin, z_end, gt_sdf, gt_valid, gt_sign, weights, x_out,
