@@ -58,7 +58,7 @@ def _check(input, grid):
 def _out_strides(t_bpc):
     """(B,P,C) buffer -> strides in the (sB, sC, sP) order the ABI expects."""
     sB, sP, sC = t_bpc.stride()
-    return _lib.i64([sB, sC, sP])
+    return _lib.i64c([sB, sC, sP])
 
 
 class _GridSample3dForward(torch.autograd.Function):
@@ -72,10 +72,10 @@ class _GridSample3dForward(torch.autograd.Function):
         g = grid.detach().contiguous()
         inp = input.detach()
         out = torch.empty((B, P, Cc), dtype=input.dtype, device=input.device)
-        with torch.cuda.device(input.device):
+        with _lib.on_device(input.device):
             if P > 0:
                 _lib.check(lib.miso_grid_sample3d_fwd(
-                    _dtype_code(input), inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()), g.data_ptr(), P,
+                    _dtype_code(input), inp.data_ptr(), _lib.i64c(inp.shape), _lib.i64c(inp.stride()), g.data_ptr(), P,
                     out.data_ptr(), _out_strides(out), _lib.PAD_MODES.index(padding_mode), int(bool(align_corners)),
                     _lib.stream_ptr(input.device)), "grid_sample3d_fwd")
         ctx.save_for_backward(input, grid)
@@ -95,7 +95,7 @@ def _as_bcp(t5):
     """(B,C,Do,Ho,Wo) -> ((B,C,P) view-or-copy, ABI strides (sB,sC,sP)).  `reshape` only copies when
     the three spatial dims cannot be collapsed into one stride."""
     t = t5.reshape(t5.shape[0], t5.shape[1], -1) if t5.numel() > 0 else t5.new_zeros((t5.shape[0], t5.shape[1], 0))
-    return t, _lib.i64(t.stride())
+    return t, _lib.i64c(t.stride())
 
 
 class _GridSample3dBackward(torch.autograd.Function):
@@ -111,12 +111,12 @@ class _GridSample3dBackward(torch.autograd.Function):
         go, go_st = _as_bcp(grad_output.detach())
         grad_input = torch.zeros_like(inp) if need_input else None  # preserve_format keeps channels_last_3d
         grad_grid = torch.empty_like(g) if need_grid else None
-        with torch.cuda.device(input.device):
+        with _lib.on_device(input.device):
             if P > 0:
               _lib.check(lib.miso_grid_sample3d_bwd(
-                _dtype_code(input), go.data_ptr(), go_st, inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()),
+                _dtype_code(input), go.data_ptr(), go_st, inp.data_ptr(), _lib.i64c(inp.shape), _lib.i64c(inp.stride()),
                 g.data_ptr(), P, _lib.ptr(grad_input),
-                _lib.i64(grad_input.stride()) if grad_input is not None else None, _lib.ptr(grad_grid),
+                _lib.i64c(grad_input.stride()) if grad_input is not None else None, _lib.ptr(grad_grid),
                 padding_mode, int(align_corners),
                 _lib.stream_ptr(input.device)), "grid_sample3d_bwd")
         ctx.save_for_backward(grad_output, input, grid)
@@ -144,13 +144,13 @@ class _GridSample3dBackward(torch.autograd.Function):
         gg_out = torch.empty((B, P, Cc), dtype=inp.dtype, device=inp.device) if need_go else None
         g_input = torch.zeros_like(inp) if need_input else None
         g_grid = torch.empty_like(g) if need_grid else None
-        with torch.cuda.device(input.device):
+        with _lib.on_device(input.device):
             if P > 0:
               _lib.check(lib.miso_grid_sample3d_bwd_bwd(
-                _dtype_code(input), _lib.ptr(ggi), _lib.i64(ggi.stride()) if ggi is not None else None, _lib.ptr(ggg),
-                go.data_ptr(), go_st, inp.data_ptr(), _lib.i64(inp.shape), _lib.i64(inp.stride()), g.data_ptr(), P,
+                _dtype_code(input), _lib.ptr(ggi), _lib.i64c(ggi.stride()) if ggi is not None else None, _lib.ptr(ggg),
+                go.data_ptr(), go_st, inp.data_ptr(), _lib.i64c(inp.shape), _lib.i64c(inp.stride()), g.data_ptr(), P,
                 _lib.ptr(gg_out), _out_strides(gg_out) if gg_out is not None else None, _lib.ptr(g_input),
-                _lib.i64(g_input.stride()) if g_input is not None else None, _lib.ptr(g_grid), ctx.padding_mode, int(ctx.align_corners), _lib.stream_ptr(input.device)),
+                _lib.i64c(g_input.stride()) if g_input is not None else None, _lib.ptr(g_grid), ctx.padding_mode, int(ctx.align_corners), _lib.stream_ptr(input.device)),
                 "grid_sample3d_bwd_bwd")
         if gg_out is not None:
             gg_out = gg_out.permute(0, 2, 1).unflatten(2, (Do, Ho, Wo))
