@@ -97,6 +97,47 @@ __device__ __forceinline__ void gather4(const miso_level_t& lv, const Cell& c, f
   }
 }
 
+// Separable trilinear evaluation (lerp along x, then y, then z) of the value and its three index-space derivatives:
+// the 8 corner vectors are consumed channel group by channel group, no per-corner weight / derivative-weight arrays
+// (40 registers in gather4) -- out-of-range corners contribute zeros (zeros padding), exactly like masking their weights.
+template <int C, bool kDeriv>
+__device__ __forceinline__ void gather_sep(const miso_level_t& lv, const Cell& c, float* __restrict__ f,
+                                           float* __restrict__ dx, float* __restrict__ dy, float* __restrict__ dz) {
+#pragma unroll
+  for (int ch = 0; ch < C; ch += 4) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((c.valid >> k) & 1u) v[k] = ldg_f4(lv.feat + corner_off(lv, c, k) + ch);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a[4], d[4];
+#pragma unroll
+      for (int yz = 0; yz < 4; ++yz) {
+        const float lo = reinterpret_cast<const float*>(&v[2 * yz])[e], hi = reinterpret_cast<const float*>(&v[2 * yz + 1])[e];
+        d[yz] = hi - lo;
+        a[yz] = fmaf(c.fx, d[yz], lo);
+      }
+      float ay[2], ey[2], dxy[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        ey[z] = a[2 * z + 1] - a[2 * z];
+        ay[z] = fmaf(c.fy, ey[z], a[2 * z]);
+        if constexpr (kDeriv) dxy[z] = fmaf(c.fy, d[2 * z + 1] - d[2 * z], d[2 * z]);
+      }
+      const float ez = ay[1] - ay[0];
+      f[ch + e] = fmaf(c.fz, ez, ay[0]);
+      if constexpr (kDeriv) {
+        dz[ch + e] = ez;
+        dy[ch + e] = fmaf(c.fz, ey[1] - ey[0], ey[0]);
+        dx[ch + e] = fmaf(c.fz, dxy[1] - dxy[0], dxy[0]);
+      }
+    }
+  }
+}
+
 template <int C>
 __device__ __forceinline__ void scatter4(const miso_level_t& lv, const Cell& c, float coef, const float* r) {
 #pragma unroll
@@ -115,8 +156,11 @@ __device__ __forceinline__ void scatter4(const miso_level_t& lv, const Cell& c, 
 // 2 = cos (mean over points of 1 - cosine_similarity(f_s, f_d), :204-205; ATen clamps each norm at eps = 1e-8).
 // acc[0] always holds the sum of the per-point loss values and gamma = d(that sum)/dq, so the host-side
 // normalisation is weight / (count * K) for L2 and weight / count for the other two.
+#ifndef MISO_ALIGN_MIN_BLOCKS
+#define MISO_ALIGN_MIN_BLOCKS 3
+#endif
 template <int C, bool kGN, int kLoss>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (kGN || kLoss != 0) ? 1 : MISO_ALIGN_MIN_BLOCKS)
     align_batch_kernel(const miso_field_t* __restrict__ fields, const miso_align_pair_t* __restrict__ pairs,
                        const float* __restrict__ poses, double* __restrict__ out) {
   constexpr int NACC = kAlignAcc + (kGN ? kGnAcc : 0);
@@ -128,18 +172,26 @@ __global__ void __launch_bounds__(kThreads)
   const miso_align_pair_t pr = pairs[pi];
   if (pr.enabled && *pr.enabled == 0) return;
   if (pr.M <= 0) return;
-  const miso_field_t& src = fields[pr.src];
-  const miso_field_t& dst = fields[pr.dst];
-  Pose24 P;
-  load_pose(poses, pi, P);
-  float dbound[6], sbmin[3], sbmax[3], dbmin[3], dbmax[3];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) dbound[i] = dst.bound[i];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    sbmin[d] = src.bound[2 * d], sbmax[d] = src.bound[2 * d + 1];
-    dbmin[d] = dst.bound[2 * d], dbmax[d] = dst.bound[2 * d + 1];
+  // the two field descriptors and the pair's pose live in shared memory: level pointers / dims / strides and the 24 pose
+  // floats are read where they are used (broadcast LDS) instead of being pinned in ~80 registers for the whole loop --
+  // the kernel is latency-bound at 8 warps per SM with 231 registers (ncu: warps active 12.5 %, issue 33 %)
+  __shared__ miso_field_t s_field[2];
+  __shared__ Pose24 s_pose;
+  {
+    const uint32_t* gs = reinterpret_cast<const uint32_t*>(&fields[pr.src]);
+    const uint32_t* gd = reinterpret_cast<const uint32_t*>(&fields[pr.dst]);
+    uint32_t* ds = reinterpret_cast<uint32_t*>(&s_field[0]);
+    uint32_t* dd = reinterpret_cast<uint32_t*>(&s_field[1]);
+    for (int i = threadIdx.x; i < (int)(sizeof(miso_field_t) / 4); i += blockDim.x) ds[i] = gs[i], dd[i] = gd[i];
+    float* dp = reinterpret_cast<float*>(&s_pose);
+    for (int i = threadIdx.x; i < 24; i += blockDim.x) dp[i] = poses[(int64_t)pi * 24 + i];
   }
+  __syncthreads();
+  const miso_field_t& src = s_field[0];
+  const miso_field_t& dst = s_field[1];
+  const Pose24& P = s_pose;
+  const float* dbound = dst.bound;
+  const float* sbound = src.bound;
   const int LU = pr.levels_used;
   const int K = LU * C;
 
@@ -158,8 +210,8 @@ __global__ void __launch_bounds__(kThreads)
     float pn[3], qn[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      pn[d] = normalize_coord(p[d], sbmin[d], sbmax[d]);
-      qn[d] = normalize_coord(q[d], dbmin[d], dbmax[d]);
+      pn[d] = normalize_coord(p[d], sbound[2 * d], sbound[2 * d + 1]);
+      qn[d] = normalize_coord(q[d], dbound[2 * d], dbound[2 * d + 1]);
     }
     float gam[3] = {0.f, 0.f, 0.f};
     float rr = 0.f;
@@ -192,8 +244,8 @@ __global__ void __launch_bounds__(kThreads)
           Cell cd = make_cell(unnormalize_nc(qn[0], dl.X), unnormalize_nc(qn[1], dl.Y), unnormalize_nc(qn[2], dl.Z), dl);
           gather4<C>(dl, cd, fd, dx, dy, dz, true);
         }
-        const float kx = (float)dl.X / (dbmax[0] - dbmin[0]), ky = (float)dl.Y / (dbmax[1] - dbmin[1]),
-                    kz = (float)dl.Z / (dbmax[2] - dbmin[2]);
+        const float kx = (float)dl.X / (dbound[1] - dbound[0]), ky = (float)dl.Y / (dbound[3] - dbound[2]),
+                    kz = (float)dl.Z / (dbound[5] - dbound[4]);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
           fsv[l * C + ch] = fs[ch], fdv[l * C + ch] = fd[ch];
@@ -252,17 +304,17 @@ __global__ void __launch_bounds__(kThreads)
         for (int ch = 0; ch < C; ++ch) fs[ch] = 0.f;
       } else {
         cs = make_cell(unnormalize_nc(pn[0], sl.X), unnormalize_nc(pn[1], sl.Y), unnormalize_nc(pn[2], sl.Z), sl);
-        gather4<C>(sl, cs, fs, nullptr, nullptr, nullptr, false);
+        gather_sep<C, false>(sl, cs, fs, nullptr, nullptr, nullptr);
       }
       Cell cd = make_cell(unnormalize_nc(qn[0], dl.X), unnormalize_nc(qn[1], dl.Y), unnormalize_nc(qn[2], dl.Z), dl);
       if (dst_ignored) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) fd[ch] = dx[ch] = dy[ch] = dz[ch] = 0.f;
       } else {
-        gather4<C>(dl, cd, fd, dx, dy, dz, true);
+        gather_sep<C, true>(dl, cd, fd, dx, dy, dz);
       }
-      const float kx = (float)dl.X / (dbmax[0] - dbmin[0]), ky = (float)dl.Y / (dbmax[1] - dbmin[1]),
-                  kz = (float)dl.Z / (dbmax[2] - dbmin[2]);
+      const float kx = (float)dl.X / (dbound[1] - dbound[0]), ky = (float)dl.Y / (dbound[3] - dbound[2]),
+                  kz = (float)dl.Z / (dbound[5] - dbound[4]);
       float r[C];
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) {
@@ -310,7 +362,9 @@ __global__ void __launch_bounds__(kThreads)
           acc[5 + 3 * i + j] += (double)gam[i] * (double)u[j];
           acc[14 + 3 * i + j] += (double)gam[i] * (double)p[j];
         } else {
-          acc[5 + 3 * i + j] = fmaf(gam[i], u[j], acc[5 + 3 * i + j]);
+          // G1 = sum gamma u^T follows from u = A1 p + b1:  G1 = G2 A1^T + G0 b1^T -- formed once per block below
+          // instead of carrying nine more accumulators through the loop (the GN variant keeps the direct sum)
+          if constexpr (kGN) acc[5 + 3 * i + j] = fmaf(gam[i], u[j], acc[5 + 3 * i + j]);
           acc[14 + 3 * i + j] = fmaf(gam[i], p[j], acc[14 + 3 * i + j]);
         }
       }
@@ -326,12 +380,26 @@ __global__ void __launch_bounds__(kThreads)
     if (lane == 0) red[i][w] = v;
   }
   __syncthreads();
+  __shared__ double block_sum_[NACC];
   if (threadIdx.x < NACC) {
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) s += (double)red[threadIdx.x][k];
+    block_sum_[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double s = block_sum_[threadIdx.x];
     double* o = out + (int64_t)pi * MISO_ALIGN_OUT;
     int idx = threadIdx.x;
+    if constexpr (kLoss == 0 && !kGN) {
+      if (idx >= 5 && idx < 14) {
+        const int i = (idx - 5) / 3, j = (idx - 5) % 3;
+        s = block_sum_[2 + i] * (double)P.b1[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += block_sum_[14 + 3 * i + k] * (double)P.A1[3 * j + k];
+      }
+    }
     if (idx < kAlignAcc) {
       if (s != 0.0) atomicAdd(o + idx, s);
     } else if (idx < kAlignAcc + 6) {

@@ -227,3 +227,112 @@ def test_mapping_step_grid_beyond_int32_offsets():
     assert rel_err(gf[:, :, Z - zc_f:], o2.features[1].grad) < TOL_GRAD
     assert rel_err(gc[:, :, Z // 4 - zc_c:], o2.features[0].grad) < TOL_GRAD
     assert torch.count_nonzero(gf[:, :, :Z - zc_f]) == 0 and torch.count_nonzero(gc[:, :, :Z // 4 - zc_c]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: interpolation fwd / bwd / double-bwd at sweep sizes; configs[2]: full-size alignment pair
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n,channels", [(20, 4), (22, 4), (20, 16)])
+def test_interpolation_plugin_at_sweep_sizes_vs_aten(log2n, channels):
+    """grid_sample_3d forward + backward (grid and coordinate gradients) on 2^20 / 2^22 points of a ScanNet-fine-level
+    sized grid against ATen's own CUDA kernels on the same device (the reference's first-order path,
+    grid_modules.py:89-94); the scatter is compared at 1e-4 (both sides accumulate with float32 atomics)."""
+    import torch.nn.functional as F
+    from miso_b200 import cuda_gridsample as cu
+    N = 1 << log2n
+    g = torch.Generator(device="cuda").manual_seed(log2n + channels)
+    feat = (torch.randn(1, channels, 200, 100, 200, device="cuda", generator=g) * 1e-2)
+    ours_in = feat.contiguous(memory_format=torch.channels_last_3d).clone().requires_grad_(True)
+    aten_in = feat.clone().requires_grad_(True)
+    xn = (torch.rand(1, N, 1, 1, 3, device="cuda", generator=g) * 2.1 - 1.05)
+    go = torch.randn(1, channels, N, 1, 1, device="cuda", generator=g)
+    res = []
+    for fn, inp in ((cu.grid_sample_3d, ours_in), (F.grid_sample, aten_in)):
+        x = xn.clone().requires_grad_(True)
+        out = fn(inp, x, padding_mode="zeros", align_corners=False)
+        out.backward(go)
+        res.append((out.detach(), inp.grad, x.grad))
+    assert rel_err(res[0][0], res[1][0]) < 1e-5
+    assert rel_err(res[0][1], res[1][1]) < TOL_GRAD
+    assert rel_err(res[0][2], res[1][2]) < TOL_GRAD
+    _record(f"interp_2p{log2n}_C{channels}", fwd=rel_err(res[0][0], res[1][0]), grad_input=rel_err(res[0][1], res[1][1]),
+            grad_grid=rel_err(res[0][2], res[1][2]))
+
+
+def test_double_backward_at_sweep_size_vs_reference_extension():
+    """The eikonal pattern (gg_grid given) on 2^20 points: all three double-backward outputs against the reference's own
+    `grid_sampler_3d_grad2_kernel` (oracle/_ref, built unmodified for sm_100a)."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/gridsample_grad2.so not built")
+    from miso_b200 import cuda_gridsample as cu
+    N = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    feat = torch.randn(1, 4, 100, 50, 100, device="cuda", generator=g) * 1e-1
+    xn = torch.rand(1, N, 1, 1, 3, device="cuda", generator=g) * 2.1 - 1.05
+    go = torch.randn(1, 4, N, 1, 1, device="cuda", generator=g)
+    g2 = torch.randn(1, N, 1, 1, 3, device="cuda", generator=g)
+    res = []
+    for fn, inp0 in ((cu.grid_sample_3d, feat.contiguous(memory_format=torch.channels_last_3d)), (ref_gpu.grid_sample_3d, feat)):
+        inp = inp0.clone().requires_grad_(True)
+        x = xn.clone().requires_grad_(True)
+        gor = go.clone().requires_grad_(True)
+        out = fn(inp, x, padding_mode="zeros", align_corners=False)
+        (gx,) = torch.autograd.grad(out, x, gor, create_graph=True)
+        (gx * g2).sum().backward()
+        res.append((gx.detach(), inp.grad, x.grad, gor.grad))
+    for name, a, b in zip(("grad_grid", "dbl.g_input", "dbl.g_grid", "dbl.gg_output"), res[0], res[1]):
+        assert rel_err(a, b) < TOL_GRAD, (name, rel_err(a, b))
+
+
+def test_alignment_pair_at_full_scannet_size():
+    """BASELINE configs[2] sizes for ONE overlapping pair of ScanNet-shaped submaps: level 0 (32 k samples) and level 1
+    (4 M samples, 8 channels) of pairwise_loss_latent against the oracle: loss 1e-5, pose gradients 1e-4, in-bound
+    count and intersection verdict exact."""
+    from miso_b200.align import AlignBatch, pairwise_loss_latent
+    from miso_b200.models import GridAtlas
+    from oracle import oracle as O
+    bound = synth.SCANNET_SUBMAP_BOUND
+    Rt, tt = synth.submap_layout(2, spacing=(12.0, 12.0))
+    Rp, tp = synth.perturb_poses(Rt, tt, rot_deg=10.0, trans_m=0.5)
+    atlas = GridAtlas(synth.model_cfg(bound, num_poses=1), device="cuda")
+    subs = []
+    shapes = O.level_shapes(bound, 0.5, 5, 2, 4)
+    for i in range(2):
+        atlas.add_submap(torch.tensor(bound), Rp[i], tp[i])
+        feats = synth.fill_submap_from_field(shapes, bound, Rt[i], tt[i])
+        with torch.no_grad():
+            for l in range(2):
+                atlas.get_submap(i).features[l].feature.copy_(feats[l].cuda())
+        atlas.get_submap(i).lock_feature()
+        subs.append(O.OracleGridNet(bound, feats, None))
+    oat = O.OracleAtlas(subs, Rp, tp)
+    atlas.precompute_coordinates_for_alignment()
+    oat.precompute([0, 1])
+    for level in (0, 1):
+        assert torch.equal(atlas.coordinates_for_alignment(0, level).cpu(), oat.coords[(0, level)])
+        for p in list(atlas.rotation_corrections) + list(atlas.translation_corrections):
+            p.grad = None
+        for q in oat.rot + oat.tra:
+            q.grad = None
+        (_, val), = pairwise_loss_latent(atlas, None, 0, 1, level=level, device="cuda").items()
+        val.backward()
+        Rs, ts = oat.updated_submap_pose(0)
+        Rd, td = oat.updated_submap_pose(1)
+        lo, mask, _ = O.pairwise_loss_latent(subs[0], subs[1], oat.coords[(0, level)], Rs, ts, Rd, td, level, return_aux=True)
+        lo.backward()
+        batch = AlignBatch(atlas, [(0, 1)], level, check_intersection=True, want_masks=True, cache_src_features=False)
+        out = batch.launch(batch.pair_poses())
+        assert int(out[0, 1].item()) == int(mask.sum())                         # in-bound count, exact
+        assert torch.equal(batch.masks[0].bool().cpu(), mask[:, 0])
+        assert rel_err(val, lo) < 1e-5, (level, rel_err(val, lo))
+        for i in range(2):
+            assert rel_err(atlas.rotation_corrections[i].grad, oat.rot[i].grad) < TOL_GRAD, (level, "rot", i)
+            assert rel_err(atlas.translation_corrections[i].grad, oat.tra[i].grad) < TOL_GRAD, (level, "tra", i)
+        _record(f"align_pair_level{level}", samples=int(oat.coords[(0, level)].shape[0]), valid=int(mask.sum()),
+                loss_rel_err=rel_err(val, lo))
+    batch = AlignBatch(atlas, [(0, 1)], 1, check_intersection=True)
+    batch.update_intersections(batch.pair_poses())
+    Rs, ts = oat.updated_submap_pose(0)
+    Rd, td = oat.updated_submap_pose(1)
+    assert bool(batch.enabled[0].item()) == bool(O.check_submap_intersection(subs[0], subs[1], Rs, ts, Rd, td))
