@@ -65,7 +65,7 @@ def main():
         off = fit.zb * fit.plane_elems * 4
         _lib.check(lib.miso_adam_step_dev(feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, fit.exp_avg.data_ptr(),
                                           fit.exp_avg_sq.data_ptr(), fit.touched.data_ptr(), n, fit.lr, 0.9, 0.999, fit.eps,
-                                          fit.step_dev.data_ptr(), fit.scalars.data_ptr(), 1, _lib.stream_ptr(dev)), "adam_step")
+                                          fit.step_dev.data_ptr(), fit.scalars.data_ptr(), None, 1, _lib.stream_ptr(dev)), "adam_step")
         mark("adam_slab_done")
         if W > 1:
             sf.exchange_halo_planes_down(p[fit.zb] if r > 0 else None, p[fit.ze] if fit.ze < fit.Z else None, r, W)
@@ -113,7 +113,7 @@ def main():
     off = fit.zb * fit.plane_elems * 4
     acc["adam_slab_only_zero_grad"] = t_loop(lambda: lib.miso_adam_step_dev(
         feats[1].data_ptr() + off, feats[1].grad.data_ptr() + off, fit.exp_avg.data_ptr(), fit.exp_avg_sq.data_ptr(),
-        fit.touched.data_ptr(), n_sl, fit.lr, 0.9, 0.999, fit.eps, fit.step_dev.data_ptr(), fit.scalars.data_ptr(), 1,
+        fit.touched.data_ptr(), n_sl, fit.lr, 0.9, 0.999, fit.eps, fit.step_dev.data_ptr(), fit.scalars.data_ptr(), None, 1,
         _lib.stream_ptr(dev)))
     acc["touched_fraction_of_slab"] = float(sum(bin(int(x) & 0xffffffff).count("1") for x in fit.touched[:200000].tolist())) / (200000 * 32)
     print(json.dumps({"rank": rank, "world": world, "slab": [fit.zb, fit.ze], "own": int(fit._bufs["count"].item()), "ms": acc}), flush=True)

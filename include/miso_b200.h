@@ -323,11 +323,13 @@ int miso_set_tuning(const char* key, int32_t value);
 int miso_get_tuning(const char* key);
 
 /* The same step (tracked when `touched` != NULL) with the step count kept on the DEVICE: *step_counter (int32) is
- * incremented and the bias-correction scalars are written to scalars[2] by a one-thread kernel in front of the sweep,
- * so the launch sequence is identical every step and a whole training step can be captured in a CUDA graph. */
+ * incremented and the bias-correction scalars are written to scalars[3] by a one-thread kernel in front of the sweep,
+ * so the launch sequence is identical every step and a whole training step can be captured in a CUDA graph.
+ * gate (optional device float, the step's total loss): when it is not finite the update is skipped as the reference's
+ * trainer does (grid_opt/trainer.py:214-217) -- counter, p, m, v untouched, the gradient cleared when zero_grad. */
 int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr, float beta1,
-                       float beta2, float eps, int32_t* step_counter, float* scalars, int32_t zero_grad,
-                       miso_stream_t stream);
+                       float beta2, float eps, int32_t* step_counter, float* scalars, const float* gate,
+                       int32_t zero_grad, miso_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the

@@ -102,7 +102,8 @@ _SIGNATURES = {
     "miso_adam_step_tracked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                          C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "miso_adam_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
-                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_void_p]),
     "miso_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
     "miso_get_tuning": (C.c_int, [C.c_char_p]),
     "miso_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,

@@ -40,6 +40,13 @@ int sm_count() {
   return cached;
 }
 
+__device__ __forceinline__ bool adam_skipped(const float* dev_scalars, float* g, int64_t n, int zero) {
+  if (!dev_scalars || dev_scalars[2] == 0.f) return false;
+  if (zero)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] = 0.f;
+  return true;
+}
+
 // torch.optim.Adam._single_tensor_adam (no amsgrad / weight decay / maximize):
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
 //   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
@@ -47,6 +54,7 @@ __global__ void __launch_bounds__(kThreads)
     adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
                 int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero,
                 const float* __restrict__ dev_scalars) {
+  if (adam_skipped(dev_scalars, g, n, zero)) return;
   if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];   // device-side step counter (CUDA graphs)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -94,11 +102,15 @@ __global__ void __launch_bounds__(kThreads)
     adam_tracked_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         uint32_t* __restrict__ touched, int64_t n4, float lr, float b1, float b2, float eps,
                         float step_size, float bc2_sqrt, int zero, const float* __restrict__ dev_scalars) {
+  if (adam_skipped(dev_scalars, g, n4 * 4, zero)) return;
   if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];
   // A warp takes kU consecutive bitmap words = kU x 32 voxels per trip and issues all of their loads before it touches
   // any of them: with one voxel per thread per trip the sweep over a mostly-untouched level (one 16-byte gradient load
   // and nothing else per voxel) ran at ~1.2 TB/s, latency-bound; kU independent loads per thread bring it to the HBM rate.
-  constexpr int kU = 4;
+#ifndef MISO_ADAM_U
+#define MISO_ADAM_U 4
+#endif
+  constexpr int kU = MISO_ADAM_U;
   const int lane = threadIdx.x & 31;
   const int64_t nwords = (n4 + 31) >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -335,20 +347,29 @@ extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n,
 }
 
 // step = ++(*counter); scalars = {lr / (1 - b1^step), sqrt(1 - b2^step)} in float64, exactly the host formula above
-__global__ void adam_tick_kernel(int32_t* __restrict__ counter, float lr, float b1, float b2, float* __restrict__ scalars) {
+// `gate` (optional): the step's total loss.  A non-finite total skips the update like the reference's trainer does
+// (`if not torch.isnan(total_loss): backward(); step()`, grid_opt/trainer.py:214-217): the counter does not advance,
+// scalars[2] = 1 tells the sweep to leave p / m / v alone and only clear the (poisoned) gradient.
+__global__ void adam_tick_kernel(int32_t* __restrict__ counter, float lr, float b1, float b2, float* __restrict__ scalars,
+                                 const float* __restrict__ gate) {
+  if (gate && !isfinite(*gate)) {
+    scalars[2] = 1.f;
+    return;
+  }
   const int step = *counter + 1;
   *counter = step;
   scalars[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
   scalars[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+  scalars[2] = 0.f;
 }
 
 extern "C" int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
                                   float beta1, float beta2, float eps, int32_t* step_counter, float* scalars,
-                                  int32_t zero_grad, miso_stream_t stream) {
+                                  const float* gate, int32_t zero_grad, miso_stream_t stream) {
   MISO_REQUIRE(p && g && m && v && step_counter && scalars, "adam_step_dev: null tensor");
   MISO_REQUIRE(n >= 0, "adam_step_dev: n >= 0 required");
   cudaStream_t s = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, s>>>(step_counter, lr, beta1, beta2, scalars);
+  adam_tick_kernel<<<1, 1, 0, s>>>(step_counter, lr, beta1, beta2, scalars, gate);
   if (n == 0) return check_launch("adam_step_dev(tick)");
   const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
   if (touched) {

@@ -33,7 +33,7 @@ class FusedAdam:
                 st["touched"] = torch.zeros((p.numel() // 4 + 31) // 32, dtype=torch.int32, device=p.device)
             if self.device_step:
                 st["step_dev"] = torch.zeros(1, dtype=torch.int32, device=p.device)
-                st["scalars"] = torch.zeros(2, dtype=torch.float32, device=p.device)
+                st["scalars"] = torch.zeros(3, dtype=torch.float32, device=p.device)
             self.state[p] = st
         return st
 
@@ -46,7 +46,9 @@ class FusedAdam:
                     p.grad.zero_()
 
     @torch.no_grad()
-    def step(self):
+    def step(self, gate=None):
+        """`gate` (device_step only): a device scalar, normally the step's total loss -- a non-finite value skips the
+        update on the device (no host sync), as the reference's trainer does on a NaN total (trainer.py:214-217)."""
         lib = _lib.load()
         for p in self.params:
             g = p.grad
@@ -68,7 +70,8 @@ class FusedAdam:
                     _lib.check(lib.miso_adam_step_dev(
                         p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
                         st["touched"].data_ptr() if tracked else None, p.numel(), self.lr, self.betas[0], self.betas[1],
-                        self.eps, st["step_dev"].data_ptr(), st["scalars"].data_ptr(), int(self.zero_grad_in_step),
+                        self.eps, st["step_dev"].data_ptr(), st["scalars"].data_ptr(),
+                        gate.data_ptr() if gate is not None else None, int(self.zero_grad_in_step),
                         _lib.stream_ptr(p.device)), "adam_step")
                 continue
             if "touched" in st and g.data_ptr() % 16 == 0:

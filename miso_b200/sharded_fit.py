@@ -128,7 +128,7 @@ class SlabShardedFit:
         self.touched = torch.zeros((n // 4 + 31) // 32, dtype=torch.int32, device=dev)
         # step counter + bias-correction scalars on the device: every step enqueues the same launches (CUDA graph)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.scalars = torch.zeros(3, dtype=torch.float32, device=dev)
 
     def _flat(self, t: torch.Tensor) -> torch.Tensor:
         """(1,C,Z,Y,X) channels-last tensor -> flat (Z, plane_elems) view of its memory."""
@@ -219,7 +219,7 @@ class SlabShardedFit:
             _lib.check(lib.miso_adam_step_dev(
                 feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
                 self.exp_avg_sq.data_ptr(), self.touched.data_ptr(), n, self.lr, float(self.betas[0]),
-                float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), 1,
+                float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), None, 1,
                 _lib.stream_ptr(dev)), "adam_step")
         if W > 1:
             # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)

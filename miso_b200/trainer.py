@@ -263,7 +263,10 @@ class GridTrainer:
                                                count_allreduce=allreduce)
         if allreduce is not None:
             allreduce([p.grad for p in self.optimizer.params if p.grad is not None] + [terms])
-        self.optimizer.step()
+        if self.cuda_graph:
+            self.optimizer.step(gate=terms[3:4])    # NaN total (e.g. a keyframe without a pose): update skipped on the device
+        else:
+            self.optimizer.step()
         self.total_steps += 1
         return terms
 

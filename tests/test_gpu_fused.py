@@ -555,3 +555,37 @@ def test_graphed_train_step_equals_eager_steps():
         opt.step()
     for l in range(2):
         assert rel_err(out[1][1][l], o2.features[l]) < TOL_G
+
+
+def test_nan_total_skips_the_update_on_the_device():
+    """grid_opt/trainer.py:214-217 (`if not isnan(total): backward(); step()`): a step whose total is NaN (here: a
+    keyframe without a pose poisons it) leaves parameters, moments and the Adam step counter untouched and clears the
+    gradient; the next clean step continues as if the bad one never happened (cuda_graph trainer, device-side gate)."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    mi, gt, (R, t) = _batch(4000)
+    bad = {k: v.clone() for k, v in mi.items()}
+    bad["sample_frame_ids"][0, :50, 0] = 99
+    mk = lambda: MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                                 grad_method="autograd", eik_trunc_dist=None)
+    params = []
+    for inject in (False, True):
+        net, _, _ = make_pair()
+        for k in range(R.shape[0]):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        net.lock_pose()
+        tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint", "cuda_graph": True}, net, mk(), None,
+                         device="cuda")
+        tr.train_step(_to_cuda(mi), _to_cuda(gt))
+        if inject:
+            before = [p.detach().clone() for p in net.level_tensors()]
+            terms = tr.train_step(_to_cuda(bad), _to_cuda(gt))
+            assert torch.isnan(terms).all()
+            for p, b in zip(net.level_tensors(), before):
+                assert torch.equal(p.detach(), b)
+                assert torch.count_nonzero(p.grad) == 0
+        tr.train_step(_to_cuda(mi), _to_cuda(gt))
+        params.append([p.detach().clone() for p in net.level_tensors()])
+    for a, b in zip(params[0], params[1]):
+        assert rel_err(b, a) < 1e-5
