@@ -104,7 +104,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     acc["select_only"] = t_loop(lambda: lib.miso_slab_select(
-        C.byref(fr), coords.data_ptr(), coords.shape[0], float(fit.zmin), float(fit.zmax), fit.Z, fit.zb, fit.ze,
+        C.byref(fr), coords.data_ptr(), coords.shape[0], float(fit.zmin), float(fit.zmax), fit.Z, fit.axis, fit.zb, fit.ze,
         sdf.data_ptr(), valid.data_ptr(), sign.data_ptr(), w.data_ptr(), b["x"].data_ptr(), b["ids"].data_ptr(),
         b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(), b["count"].data_ptr(),
         _lib.stream_ptr(dev)))

@@ -278,12 +278,13 @@ int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t n
  * 4. Helpers around the path.
  * ------------------------------------------------------------------------------------------ */
 /* Domain-decomposed multi-GPU fit: keep the samples of a (replicated) batch whose trilinear cell of one level starts in
- * z-planes [z_begin, z_end) of that level (Z planes over [zmin, zmax], z = slowest axis of the channels-last level),
+ * planes [z_begin, z_end) of that level along `axis` (0 = x, 1 = y, 2 = z; Z planes over [zmin, zmax] on that axis --
+ * the caller stores the level with that axis slowest, so a range of planes is one contiguous piece of memory),
  * compacted to the front of the *_out arrays in batch order within 1024-sample chunks; *count (device int32) receives
  * their number.  Same index arithmetic as the fused kernels, so each sample is owned by exactly one rank and touches
  * only planes [z_begin, z_end] of that level.  frames / weights / ids_out / weights_out may be NULL. */
 int miso_slab_select(const miso_frames_t* frames, const float* x, int64_t N, float zmin, float zmax, int32_t Z,
-                     int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid, const float* gt_sign,
+                     int32_t axis, int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid, const float* gt_sign,
                      const float* weights, float* x_out, int64_t* ids_out, float* sdf_out, uint8_t* valid_out,
                      float* sign_out, float* weights_out, int32_t* count, miso_stream_t stream);
 

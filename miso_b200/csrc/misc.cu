@@ -190,7 +190,7 @@ constexpr int kSelPer = 4;   // consecutive samples per thread: a block trip cov
 
 __global__ void __launch_bounds__(kThreads)
     slab_select_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, const float* __restrict__ R,
-                       const float* __restrict__ t, int num_frames, int64_t N, float zmin, float zmax, int Z,
+                       const float* __restrict__ t, int num_frames, int64_t N, float zmin, float zmax, int Z, int axis,
                        int z_begin, int z_end, const float* __restrict__ sdf, const uint8_t* __restrict__ valid,
                        const float* __restrict__ sign, const float* __restrict__ weights, float* __restrict__ x_out,
                        int64_t* __restrict__ ids_out, float* __restrict__ sdf_out, uint8_t* __restrict__ valid_out,
@@ -218,10 +218,11 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int k = 0; k < kSelPer; ++k) {
       if (n0 + k >= N) continue;
-      float zw = px[k][2];
+      float zw = axis == 0 ? px[k][0] : (axis == 1 ? px[k][1] : px[k][2]);   // world coordinate along the slab axis
       if (ids) {
         const int64_t q = (id[k] < 0 || id[k] >= num_frames) ? 0 : id[k];
-        zw = fmaf(px[k][2], R[q * 9 + 8], fmaf(px[k][1], R[q * 9 + 7], px[k][0] * R[q * 9 + 6])) + t[q * 3 + 2];
+        const float* Rr = R + q * 9 + 3 * axis;
+        zw = fmaf(px[k][2], Rr[2], fmaf(px[k][1], Rr[1], px[k][0] * Rr[0])) + t[q * 3 + axis];
       }
       const float iz = unnormalize_nc(normalize_coord(zw, zmin, zmax), Z);
       // NaN (a keyframe without a pose) and far-away samples go to the edge planes: some rank must own them
@@ -412,13 +413,14 @@ extern "C" int miso_transform_points(const float* x, const int64_t* ids, const f
 }
 
 extern "C" int miso_slab_select(const miso_frames_t* frames, const float* x, int64_t N, float zmin, float zmax,
-                                int32_t Z, int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid,
+                                int32_t Z, int32_t axis, int32_t z_begin, int32_t z_end, const float* gt_sdf, const uint8_t* gt_valid,
                                 const float* gt_sign, const float* weights, float* x_out, int64_t* ids_out,
                                 float* sdf_out, uint8_t* valid_out, float* sign_out, float* weights_out,
                                 int32_t* count, miso_stream_t stream) {
   MISO_REQUIRE(count && N >= 0 && (N == 0 || (x && gt_sdf && gt_valid && gt_sign && x_out && sdf_out && valid_out && sign_out)),
                "slab_select: null argument");
   MISO_REQUIRE(Z > 0 && zmax > zmin && z_begin >= 0 && z_end <= Z && z_begin <= z_end, "slab_select: bad slab [%d,%d) of %d", z_begin, z_end, Z);
+  MISO_REQUIRE(axis >= 0 && axis <= 2, "slab_select: axis must be 0 (x), 1 (y) or 2 (z)");
   const bool have_frames = frames && frames->ids;
   MISO_REQUIRE(!have_frames || (frames->R && frames->t && frames->num_frames > 0 && ids_out), "slab_select: frames without poses / ids_out");
   cudaStream_t s = (cudaStream_t)stream;
@@ -428,7 +430,7 @@ extern "C" int miso_slab_select(const miso_frames_t* frames, const float* x, int
   const int blocks = grid_for((N + kThreads * kSelPer - 1) / (kThreads * kSelPer), 1, sm_count() * 8);
   slab_select_kernel<<<blocks, kThreads, 0, s>>>(x, have_frames ? frames->ids : nullptr, have_frames ? frames->R : nullptr,
                                                  have_frames ? frames->t : nullptr, have_frames ? frames->num_frames : 0, N,
-                                                 zmin, zmax, Z, z_begin, z_end, gt_sdf, gt_valid, gt_sign, weights, x_out,
+                                                 zmin, zmax, Z, axis, z_begin, z_end, gt_sdf, gt_valid, gt_sign, weights, x_out,
                                                  ids_out, sdf_out, valid_out, sign_out, weights_out, count);
   return check_launch("slab_select");
 }

@@ -9,8 +9,10 @@ that lets the per-rank terms and gradients sum.  Two splits are implemented:
     neither of which shrinks with the number of GPUs: measured 0.94x at 2 GPUs (profiles/r01_ncd_point_sharded.json).
 
   * `SlabShardedFit` (this file) -- the batch is split by WHERE the samples fall.  The largest level is cut into
-    contiguous ranges of z-planes (z is the slowest axis of the channels-last layout, so a range of planes is one
-    contiguous piece of the level, of its gradient and of its Adam moments); every rank reads the whole batch (it is
+    contiguous ranges of planes along ONE axis -- z or y, whichever balances this scene better (an outdoor LiDAR batch
+    has a third of its samples in the two z-planes of the ground) -- and is stored with that axis slowest, so a range
+    of planes is one contiguous piece of the level, of its gradient and of its Adam moments (the kernels take arbitrary
+    strides; only channels must stay innermost); every rank reads the whole batch (it is
     replicated: in the reference every process would load the same dataset) and keeps the samples whose cell of that
     level starts in its planes (`miso_slab_select`, device-side compaction, no host sync), runs the fused step on
     them with the GLOBAL batch size as denominator, and owns the Adam update of its planes.  A sample touches planes
@@ -105,11 +107,10 @@ class SlabShardedFit:
         feats = model.level_tensors()
         self.slab_level = max(range(len(feats)), key=lambda l: feats[l].numel())
         f = feats[self.slab_level]
-        _, self.Cc, self.Z, self.Y, self.X = f.shape
-        if f.stride(1) != 1 or f.stride(2) != self.Y * self.X * self.Cc:
-            raise RuntimeError("SlabShardedFit needs the channels_last_3d level layout (z slowest)")
-        self.plane_elems = self.Y * self.X * self.Cc
-        self.zmin, self.zmax = model._bound_host[4], model._bound_host[5]
+        if f.stride(1) != 1:
+            raise RuntimeError("SlabShardedFit needs channels innermost (channels_last_3d or a permutation of it)")
+        self.axis = 2                        # slab axis in (x, y, z) numbering; z is slowest in channels_last_3d
+        self._configure_axis(2 if f.stride(2) > f.stride(3) else 1)
         self.bounds = list(bounds) if bounds is not None else [round(self.Z * k / self.world) for k in range(self.world + 1)]
         self._set_slab()
         self.step_count = 0
@@ -118,6 +119,30 @@ class SlabShardedFit:
         self._bufs = None
 
     # ---- slabs ---------------------------------------------------------------------------------------
+    def _configure_axis(self, axis: int):
+        """Slab axis 2 (z) or 1 (y): `Z` = planes along it, `plane_elems` = floats per plane, [zmin, zmax] its bound."""
+        f = self.model.level_tensors()[self.slab_level]
+        self.axis = axis
+        self.Z = f.shape[2] if axis == 2 else f.shape[3]
+        self.plane_elems = f.numel() // self.Z
+        self.zmin, self.zmax = self.model._bound_host[2 * axis], self.model._bound_host[2 * axis + 1]
+
+    def _relayout(self, axis: int):
+        """Store the slab level (and its gradient) with `axis` slowest: logical shape (1,C,Z,Y,X) and values unchanged."""
+        p = self.model.features[self.slab_level].feature
+        order = (0, 2, 3, 4, 1) if axis == 2 else (0, 3, 2, 4, 1)        # physical order: slab axis, other, x, channels
+        back = (0, 4, 1, 2, 3) if axis == 2 else (0, 4, 2, 1, 3)
+        with torch.no_grad():
+            p.data = p.data.permute(order).contiguous().permute(back)
+            if p.grad is not None:
+                p.grad = p.grad.permute(order).contiguous().permute(back)
+        self._configure_axis(axis)
+
+    def restore_layout(self):
+        """Back to channels_last_3d (z slowest), e.g. before saving a checkpoint."""
+        if self.axis != 2:
+            self._relayout(2)
+
     def _set_slab(self):
         self.zb, self.ze = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         n = (self.ze - self.zb) * self.plane_elems
@@ -131,21 +156,38 @@ class SlabShardedFit:
         self.scalars = torch.zeros(3, dtype=torch.float32, device=dev)
 
     def _flat(self, t: torch.Tensor) -> torch.Tensor:
-        """(1,C,Z,Y,X) channels-last tensor -> flat (Z, plane_elems) view of its memory."""
-        return t.detach().permute(0, 2, 3, 4, 1).reshape(self.Z, self.plane_elems)
+        """(1,C,Z,Y,X) tensor stored slab-axis-slowest -> flat (planes, plane_elems) view of its memory."""
+        order = (0, 2, 3, 4, 1) if self.axis == 2 else (0, 3, 2, 4, 1)
+        return t.detach().permute(order).reshape(self.Z, self.plane_elems)
 
-    def calibrate(self, model_input: dict, voxel_cost: float = 1.0 / 56.0):
+    def calibrate(self, model_input: dict, voxel_cost: float = 1.0 / 56.0, axes=None):
         """Choose slab boundaries that balance the per-step work of this batch over the ranks (identical on every rank:
         the batch is replicated): a plane costs its sample count (fused step, ~0.19 ns per sample on B200) plus
         `voxel_cost` sample-equivalents per parameter it holds (the Adam sweep streams the slab's gradient and, for
-        touched voxels, p / m / v: ~0.0034 ns per float measured on the NCD quad grid).  Resets the slab's Adam
-        moments; call before the first step."""
+        touched voxels, p / m / v: ~0.0034 ns per float measured on the NCD quad grid).  Both candidate slab axes
+        (z, y) are tried and the one whose heaviest slab is lightest wins; the level is re-laid with that axis slowest.
+        Resets the slab's Adam moments; call before the first step."""
         coords = model_input["coords_frame"][0]
         ids = model_input["sample_frame_ids"][0, :, 0]
         R, t, _ = self.loss.frame_table(self.model)
-        zw = torch.einsum("nj,nj->n", R[ids][:, 2, :], coords) + t[ids][:, 2, 0]
-        hist = torch.bincount(plane_of_points(zw, self.zmin, self.zmax, self.Z), minlength=self.Z)
-        self.bounds = slab_bounds_from_histogram(hist.double() + voxel_cost * self.plane_elems, self.world)
+        f = self.model.level_tensors()[self.slab_level]
+        best = None
+        for axis in ((2, 1) if axes is None else axes):
+            n_planes = f.shape[2] if axis == 2 else f.shape[3]
+            if n_planes < self.world:
+                continue
+            lo, hi = self.model._bound_host[2 * axis], self.model._bound_host[2 * axis + 1]
+            w = torch.einsum("nj,nj->n", R[ids][:, axis, :], coords) + t[ids][:, axis, 0]
+            cost = torch.bincount(plane_of_points(w, lo, hi, n_planes), minlength=n_planes).double() \
+                + voxel_cost * (f.numel() // n_planes)
+            bounds = slab_bounds_from_histogram(cost, self.world)
+            cum = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(cost.cpu(), 0)])
+            worst = max(float(cum[b1] - cum[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:]))
+            if best is None or worst < best[0]:
+                best = (worst, axis, bounds)
+        _, axis, self.bounds = best
+        if axis != self.axis:
+            self._relayout(axis)
         self._set_slab()
         return self.bounds
 
@@ -179,7 +221,7 @@ class SlabShardedFit:
         stream = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
             _lib.check(lib.miso_slab_select(
-                C.byref(fr), coords.data_ptr(), N, float(self.zmin), float(self.zmax), self.Z, self.zb, self.ze,
+                C.byref(fr), coords.data_ptr(), N, float(self.zmin), float(self.zmax), self.Z, self.axis, self.zb, self.ze,
                 sdf.data_ptr(), valid.data_ptr(), sign.data_ptr(), w.data_ptr(), b["x"].data_ptr(), b["ids"].data_ptr(),
                 b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(),
                 b["count"].data_ptr(), stream), "slab_select")

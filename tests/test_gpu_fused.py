@@ -589,3 +589,46 @@ def test_nan_total_skips_the_update_on_the_device():
         params.append([p.detach().clone() for p in net.level_tensors()])
     for a, b in zip(params[0], params[1]):
         assert rel_err(b, a) < 1e-5
+
+
+def test_slab_sharded_fit_y_axis_layout_equals_trainer():
+    """The slab level stored y-slowest (SlabShardedFit picks z or y, whichever balances the batch): the fused kernels
+    take the permuted strides as they are, results equal the channels_last_3d run; a y half-slab owns the samples the
+    ownership rule names; restore_layout() returns to channels_last_3d with the same values."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.sharded_fit import SlabShardedFit, plane_of_points
+    from miso_b200.trainer import GridTrainer
+    mi, gt, (R, t) = _batch(20000)
+    nets = []
+    for _ in range(2):
+        net, _, _ = make_pair()
+        for k in range(R.shape[0]):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        net.lock_pose()
+        nets.append(net)
+    mk = lambda: MisoLossMapping(loss_type="L2", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.5, trunc_dist=0.15,
+                                 grad_method="autograd", eik_trunc_dist=None)
+    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, nets[0], mk(), None, device="cuda")
+    fit = SlabShardedFit(nets[1], mk(), lr=1e-3, rank=0, world=1)
+    dmi, dgt = _to_cuda(mi), _to_cuda(gt)
+    fit.calibrate(dmi, axes=(1,))
+    fine = nets[1].level_tensors()[1]
+    assert fit.axis == 1 and fine.stride(3) > fine.stride(2) > fine.stride(4) > fine.stride(1) == 1     # y slowest
+    for _ in range(3):
+        assert rel_err(fit.step(dmi, dgt), tr.train_step(dmi, dgt)) < 1e-5
+    for pa, pb in zip(nets[0].level_tensors(), nets[1].level_tensors()):
+        assert rel_err(pb, pa) < 1e-5
+    Y = fit.Z
+    half = SlabShardedFit(nets[1], mk(), lr=1e-3, rank=0, world=2, bounds=[0, Y // 2, Y])
+    assert half.axis == 1                                      # picked up from the strides
+    half._exchange_and_update = lambda *a, **k: None
+    half.step(dmi, dgt)
+    ids = mi["sample_frame_ids"][0, :, 0]
+    yw = torch.einsum("nj,nj->n", R[ids][:, 1, :], mi["coords_frame"][0]) + t[ids][:, 1, 0]
+    want = int((plane_of_points(yw.cuda(), SMALL_BOUND[1][0], SMALL_BOUND[1][1], Y) < Y // 2).sum())
+    assert abs(int(half._bufs["count"].item()) - want) <= 2
+    vals = fine.detach().clone()
+    fit.restore_layout()
+    fine2 = nets[1].level_tensors()[1]
+    assert fine2.stride(2) > fine2.stride(3) and torch.equal(fine2.detach(), vals)

@@ -8,5 +8,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches.log 2>&1
 # alignment level 1: one full capture of align_batch_kernel
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:align_batch_kernel -s 50 -c 1 -o gpurun_out/${tag}_ncu_align_l1 -f python benchmarks/align_breakdown.py > gpurun_out/${tag}_ncu_align.log 2>&1
-timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py --smoke > gpurun_out/${tag}_compute_sanitizer.txt 2>&1; tail -4 gpurun_out/${tag}_compute_sanitizer.txt
+# memcheck over every kernel family (smoke) and over a multi-tile mapping step + the new round-2 kernels
+timeout 900 compute-sanitizer --launch-timeout 600 --tool memcheck --print-limit 20 python __graft_entry__.py --smoke > gpurun_out/${tag}_compute_sanitizer.txt 2>&1; grep -E "ERROR SUMMARY|smoke\]" gpurun_out/${tag}_compute_sanitizer.txt | tail -4
+timeout 900 compute-sanitizer --launch-timeout 600 --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_fused.py -q -k "slab or finite_difference or graphed or nan_total or unregistered" >> gpurun_out/${tag}_compute_sanitizer.txt 2>&1; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${tag}_compute_sanitizer.txt | tail -3
 ls -la gpurun_out | grep ${tag}_
