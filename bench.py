@@ -669,6 +669,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         torch.cuda.synchronize()
         ms_b = sync_max(e0.elapsed_time(e1) / n_b)
         own = int(fit._bufs["count"].item())
+        slab_axis = "xyz"[fit.axis]
         fit.gather_model()
         fit.restore_layout()
         rel_b = [float((a - b).norm() / b.norm()) for a, b in zip(net_b.level_tensors(), ref_params)]
@@ -676,7 +677,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
         out["slab_sharded"] = {
             "ms_per_step": ms_b, "points_per_s": NCD_POINTS / (ms_b * 1e-3), "speedup_vs_1gpu": ms1 / ms_b,
-            "cuda_graph": True, "slab_axis": "xyz"[fit.axis], "slab_bounds_planes": bounds, "max_samples_per_rank": int(cnt.item()),
+            "cuda_graph": True, "slab_axis": slab_axis, "slab_bounds_planes": bounds, "max_samples_per_rank": int(cnt.item()),
             "load_imbalance": float(cnt.item()) * world / NCD_POINTS,
             "collective": "P2P halo: one z-plane of fine-level gradients up + one plane of parameters down per neighbour, "
                           "ncclAllReduce of the coarse level's gradient and the 4 loss terms",
