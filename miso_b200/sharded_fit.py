@@ -183,7 +183,7 @@ class SlabShardedFit:
             bounds = slab_bounds_from_histogram(cost, self.world)
             cum = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(cost.cpu(), 0)])
             worst = max(float(cum[b1] - cum[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:]))
-            if best is None or worst < best[0]:
+            if best is None or worst < 0.98 * best[0]:     # z (the native layout) unless y is clearly better
                 best = (worst, axis, bounds)
         _, axis, self.bounds = best
         if axis != self.axis:

@@ -510,6 +510,7 @@ def test_slab_sharded_fit_single_rank_equals_trainer():
     assert not dist.is_initialized()
     half._exchange_and_update = lambda *a, **k: None          # selection + kernel only: no process group here
     half.step(dmi, dgt)
+    assert half.axis == 2 and fit.axis == 2                    # a single rank keeps the native z-slowest layout
     ids = mi["sample_frame_ids"][0, :, 0]
     zw = torch.einsum("nj,nj->n", R[ids][:, 2, :], mi["coords_frame"][0]) + t[ids][:, 2, 0]
     plane = plane_of_points(zw.cuda(), SMALL_BOUND[2][0], SMALL_BOUND[2][1], fit.Z)
