@@ -183,8 +183,11 @@ __global__ void __launch_bounds__(kThreads) grid_sample_fwd_kernel(GridArgs<T> a
 // ---------------------------------------------------------------------------------------------
 // backward: grad_input (scatter, accumulated) and grad_grid
 // ---------------------------------------------------------------------------------------------
+#ifndef MISO_BWD_MIN_BLOCKS
+#define MISO_BWD_MIN_BLOCKS 2
+#endif
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? MISO_BWD_MIN_BLOCKS : 1)
     grid_sample_bwd_kernel(GridArgs<T> a, const T* __restrict__ go, int64_t gB, int64_t gC, int64_t gP,
                            T* __restrict__ grad_input, GStrides gs, T* __restrict__ grad_grid) {
   const int64_t total = a.B * a.P;
@@ -253,8 +256,11 @@ __global__ void __launch_bounds__(kThreads)
 // double backward (gridsample_cuda.cu:212-533): given cotangents gg_input (grid-shaped) and
 // gg_grid (per point) of the first backward's outputs, produce gg_output, g_input, g_grid.
 // ---------------------------------------------------------------------------------------------
+#ifndef MISO_BWD2_MIN_BLOCKS
+#define MISO_BWD2_MIN_BLOCKS 2   // 128 registers: 16 warps/SM instead of 8 at 189 registers (1.5-1.7x, profiles/r02_interp_sweep.csv)
+#endif
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? MISO_BWD2_MIN_BLOCKS : 1)
     grid_sample_bwd_bwd_kernel(GridArgs<T> a, const T* __restrict__ ggi, int64_t iN, int64_t iC, int64_t iD,
                                int64_t iH, int64_t iW, const T* __restrict__ ggg, const T* __restrict__ go,
                                int64_t gB, int64_t gC, int64_t gP, T* __restrict__ ggo, int64_t oB, int64_t oC,
