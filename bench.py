@@ -304,13 +304,14 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None   # sampled across all timed regions (value + e2e + e2e_compact)
     assert torch.isfinite(loss_host[wu:]).all(), "non-finite loss in the compact e2e run"
 
-    align, ncd, torch_gpu = None, None, None
+    align, ncd, torch_gpu, fd = None, None, None, None
     if not args.no_extras:
         del dev_batches
         torch.cuda.empty_cache()
         ncd = bench_ncd(device, steps=max(100, min(args.steps, 200)) if world == 1 else 30, world=world, rank=rank)
         if world == 1:
             torch_gpu = torch_gpu_arm(device)
+            fd = bench_fd(device)
         align = bench_align(device, iters=10, warmup=2, world=world, rank=rank)
         if world > 1:
             # pair-sharded: an iteration ends when the slowest rank is done
@@ -361,7 +362,7 @@ def run_ours(args):
                      "floors_ms": {"red_v4_scatter_only": 0.121, "gather_only": 0.041,
                                    "source": "profiles/r01_scatter_probe.json (benchmarks/scatter_probe.py, same batch)"}},
         "final_loss_terms": final_loss,
-        "extra": {"ncd": ncd, "torch_gpu_baseline": torch_gpu, "align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
+        "extra": {"ncd": ncd, "torch_gpu_baseline": torch_gpu, "finite_difference_step": fd, "align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
                   "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "
                   "<= 32 k samples/pair, level 1: <= 4 M samples/pair"},
     }
@@ -738,6 +739,67 @@ def torch_gpu_arm(device, steps=5, warmup=2):
             "first_step_total": first,
             "what": "reference op sequence on cuda: F.grid_sample + aten backward + grad2 plugin + cuBLAS MLP + torch Adam, "
                     "same batch / parameters as the product arm"}
+
+
+def bench_fd(device, steps=20, warmup=3):
+    """The same headline step with the eikonal term as the shipped configs define it (grad_method: finitediff, eps 0.024;
+    configs/rgbd/scannet.yaml:48-49): miso_mapping_step_fd (four launches) + Adam, against the reference's GPU op
+    sequence for it (7 x [F.grid_sample per level + cuBLAS MLP] forward and backward, torch Adam) on the same batch."""
+    from miso_b200 import synth
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    from oracle import oracle as O
+    cfg = dict(LOSS_CFG, grad_method="finitediff", finite_diff_eps=0.024)
+    mi, gt, poses = host_batch(0, 0)
+    dmi = {k: v.to(device) for k, v in mi.items()}
+    dgt = {k: v.to(device) for k, v in gt.items()}
+    net = build_model(device, poses, seed=0)
+    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net, MisoLossMapping(**cfg), None, device=device)
+
+    def timed(fn):
+        first = None
+        for i in range(warmup):
+            out = fn()
+            first = out if first is None else first
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, first
+
+    ms, first = timed(lambda: tr.train_step(dmi, dgt))
+    ours_total = float(first[3])
+    del tr, net
+    torch.cuda.empty_cache()
+    shapes = O.level_shapes(synth.SCANNET_SUBMAP_BOUND, 0.5, 5, 2, 4)
+    dec = O.make_decoder(8)
+    dec.load_state_dict({k.replace("network.", ""): v for k, v in synth.decoder_weights(8).items()})
+    model = O.OracleGridNet(synth.SCANNET_SUBMAP_BOUND, initial_features(shapes, 0), dec, second_order=False).to(device)
+    R, t = poses
+    kf = {k: (R[k].to(device), t[k].to(device)) for k in range(R.shape[0])}
+    opt = torch.optim.Adam(list(model.features.parameters()), lr=1e-3)
+
+    def ref_step():
+        opt.zero_grad()
+        ld = O.mapping_loss(model, dmi, dgt, kf, cfg["loss_type"], cfg["weight_sdf"], cfg["weight_eik"], cfg["weight_fs"],
+                            cfg["trunc_dist"], finite_diff_eps=0.024, grad_method="finitediff", eik_trunc_dist=None)
+        total = sum(ld.values())
+        total.backward()
+        opt.step()
+        return total.detach()
+
+    ms_ref, first_ref = timed(ref_step)
+    ref_total = float(first_ref)
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"what": "headline step with the finite-difference eikonal of the shipped configs (eps 0.024): fused four-launch step "
+                    "+ Adam vs the reference's GPU op sequence, same batch and parameters",
+            "ms_per_step": ms, "points_per_s": N_POINTS / (ms * 1e-3), "reference_gpu_ms_per_step": ms_ref,
+            "speedup_vs_reference_gpu": ms_ref / ms, "first_step_total": ours_total, "reference_first_step_total": ref_total,
+            "first_step_rel_err": abs(ours_total - ref_total) / abs(ref_total)}
 
 
 def run_torch_gpu(args):
