@@ -323,9 +323,10 @@ int miso_adam_step_tracked(float* p, float* g, float* m, float* v, uint32_t* tou
 int miso_set_tuning(const char* key, int32_t value);
 int miso_get_tuning(const char* key);
 
-/* The same step (tracked when `touched` != NULL) with the step count kept on the DEVICE: *step_counter (int32) is
- * incremented and the bias-correction scalars are written to scalars[3] by a one-thread kernel in front of the sweep,
- * so the launch sequence is identical every step and a whole training step can be captured in a CUDA graph.
+/* The same step (tracked when `touched` != NULL) with the step count kept on the DEVICE: every block derives the
+ * bias-correction scalars of step *step_counter + 1 itself and the last block to finish publishes the new count, so
+ * the optimizer step is ONE launch whose arguments never change and a whole training step can be captured in a CUDA
+ * graph.  scalars: 3 device floats of scratch, zero-initialised once by the caller (scalars[0] is the block ticket).
  * gate (optional device float, the step's total loss): when it is not finite the update is skipped as the reference's
  * trainer does (grid_opt/trainer.py:214-217) -- counter, p, m, v untouched, the gradient cleared when zero_grad. */
 int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr, float beta1,

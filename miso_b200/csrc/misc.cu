@@ -40,11 +40,48 @@ int sm_count() {
   return cached;
 }
 
-__device__ __forceinline__ bool adam_skipped(const float* dev_scalars, float* g, int64_t n, int zero) {
-  if (!dev_scalars || dev_scalars[2] == 0.f) return false;
+// Device-side step state of miso_adam_step_dev: {counter, gate, ticket}.  Every block derives the bias-correction
+// scalars of step = *counter + 1 itself (two float64 pow per block); the block that finishes LAST (ticket) publishes the
+// new count -- every block has read the old one by then -- so the optimizer step is ONE launch and the launch sequence
+// is identical every step (CUDA-graph capturable).  A non-finite *gate (the step's total loss) skips the update like
+// the reference's trainer (`if not torch.isnan(total_loss): backward(); step()`, grid_opt/trainer.py:214-217): p / m / v
+// and the counter stay, only the (poisoned) gradient is cleared.
+struct AdamDev {
+  int32_t* counter;
+  const float* gate;
+  unsigned* ticket;
+};
+
+__device__ __forceinline__ bool adam_dev_begin(const AdamDev& d, float lr, float b1, float b2, float& step_size,
+                                               float& bc2_sqrt, float* sh /* 3 floats of shared memory */) {
+  if (!d.counter) return false;
+  if (threadIdx.x == 0) {
+    const bool skip = d.gate && !isfinite(*d.gate);
+    const int step = *d.counter + 1;
+    sh[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
+    sh[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+    sh[2] = skip ? 1.f : 0.f;
+  }
+  __syncthreads();
+  step_size = sh[0], bc2_sqrt = sh[1];
+  return sh[2] != 0.f;
+}
+
+__device__ __forceinline__ void adam_dev_end(const AdamDev& d, bool skipped) {
+  if (!d.counter) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(d.ticket, 1u) == gridDim.x - 1) {
+      if (!skipped) *d.counter = *d.counter + 1;
+      *d.ticket = 0u;
+    }
+  }
+}
+
+__device__ __forceinline__ void adam_clear_grad(float* g, int64_t n, int zero) {
   if (zero)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] = 0.f;
-  return true;
 }
 
 // torch.optim.Adam._single_tensor_adam (no amsgrad / weight decay / maximize):
@@ -53,9 +90,13 @@ __device__ __forceinline__ bool adam_skipped(const float* dev_scalars, float* g,
 __global__ void __launch_bounds__(kThreads)
     adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
                 int64_t n, float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt, int zero,
-                const float* __restrict__ dev_scalars) {
-  if (adam_skipped(dev_scalars, g, n, zero)) return;
-  if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];   // device-side step counter (CUDA graphs)
+                AdamDev dev) {
+  __shared__ float sh_dev[3];
+  if (adam_dev_begin(dev, lr, b1, b2, step_size, bc2_sqrt, sh_dev)) {
+    adam_clear_grad(g, n, zero);
+    adam_dev_end(dev, true);
+    return;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 gv = reinterpret_cast<float4*>(g)[i];
@@ -92,6 +133,7 @@ __global__ void __launch_bounds__(kThreads)
     v[i] = vi;
     if (zero) g[i] = 0.f;
   }
+  adam_dev_end(dev, false);
 }
 
 // Same update with an "ever touched" bitmap (one bit per 4-float voxel): a voxel whose bit is clear has
@@ -101,9 +143,13 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     adam_tracked_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                         uint32_t* __restrict__ touched, int64_t n4, float lr, float b1, float b2, float eps,
-                        float step_size, float bc2_sqrt, int zero, const float* __restrict__ dev_scalars) {
-  if (adam_skipped(dev_scalars, g, n4 * 4, zero)) return;
-  if (dev_scalars) step_size = dev_scalars[0], bc2_sqrt = dev_scalars[1];
+                        float step_size, float bc2_sqrt, int zero, AdamDev dev) {
+  __shared__ float sh_dev[3];
+  if (adam_dev_begin(dev, lr, b1, b2, step_size, bc2_sqrt, sh_dev)) {
+    adam_clear_grad(g, n4 * 4, zero);
+    adam_dev_end(dev, true);
+    return;
+  }
   // A warp takes kU consecutive bitmap words = kU x 32 voxels per trip and issues all of their loads before it touches
   // any of them: with one voxel per thread per trip the sweep over a mostly-untouched level (one 16-byte gradient load
   // and nothing else per voxel) ran at ~1.2 TB/s, latency-bound; kU independent loads per thread bring it to the HBM rate.
@@ -160,6 +206,7 @@ __global__ void __launch_bounds__(kThreads)
       if (zero && gnz) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  adam_dev_end(dev, false);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -343,45 +390,28 @@ extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n,
   const float bc2_sqrt = (float)sqrt(bc2);
   const int blocks = grid_for(n4 > 0 ? n4 : n, kThreads, sm_count() * 8);
   adam_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, step_size,
-                                                             bc2_sqrt, zero_grad, nullptr);
+                                                             bc2_sqrt, zero_grad, AdamDev{nullptr, nullptr, nullptr});
   return check_launch("adam_step");
 }
 
 // step = ++(*counter); scalars = {lr / (1 - b1^step), sqrt(1 - b2^step)} in float64, exactly the host formula above
-// `gate` (optional): the step's total loss.  A non-finite total skips the update like the reference's trainer does
-// (`if not torch.isnan(total_loss): backward(); step()`, grid_opt/trainer.py:214-217): the counter does not advance,
-// scalars[2] = 1 tells the sweep to leave p / m / v alone and only clear the (poisoned) gradient.
-__global__ void adam_tick_kernel(int32_t* __restrict__ counter, float lr, float b1, float b2, float* __restrict__ scalars,
-                                 const float* __restrict__ gate) {
-  if (gate && !isfinite(*gate)) {
-    scalars[2] = 1.f;
-    return;
-  }
-  const int step = *counter + 1;
-  *counter = step;
-  scalars[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
-  scalars[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
-  scalars[2] = 0.f;
-}
-
 extern "C" int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
                                   float beta1, float beta2, float eps, int32_t* step_counter, float* scalars,
                                   const float* gate, int32_t zero_grad, miso_stream_t stream) {
   MISO_REQUIRE(p && g && m && v && step_counter && scalars, "adam_step_dev: null tensor");
-  MISO_REQUIRE(n >= 0, "adam_step_dev: n >= 0 required");
+  MISO_REQUIRE(n > 0, "adam_step_dev: n > 0 required");
   cudaStream_t s = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, s>>>(step_counter, lr, beta1, beta2, scalars, gate);
-  if (n == 0) return check_launch("adam_step_dev(tick)");
+  const AdamDev dev{step_counter, gate, reinterpret_cast<unsigned*>(scalars)};   // scalars[0]: the block ticket (zeroed by the caller once)
   const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0;
   if (touched) {
     MISO_REQUIRE(aligned && n % 4 == 0, "adam_step_dev: the tracked variant needs 16-byte aligned tensors and n % 4 == 0");
     const int64_t n4 = n / 4;
     adam_tracked_kernel<<<grid_for(n4, kThreads, sm_count() * 8), kThreads, 0, s>>>(p, g, m, v, touched, n4, lr, beta1, beta2,
-                                                                                   eps, 0.f, 1.f, zero_grad, scalars);
+                                                                                   eps, 0.f, 1.f, zero_grad, dev);
   } else {
     const int64_t n4 = aligned ? n / 4 : 0;
     adam_kernel<<<grid_for(n4 > 0 ? n4 : n, kThreads, sm_count() * 8), kThreads, 0, s>>>(p, g, m, v, n4, n, lr, beta1, beta2,
-                                                                                         eps, 0.f, 1.f, zero_grad, scalars);
+                                                                                         eps, 0.f, 1.f, zero_grad, dev);
   }
   return check_launch("adam_step_dev");
 }
@@ -399,7 +429,7 @@ extern "C" int miso_adam_step_tracked(float* p, float* g, float* m, float* v, ui
   const int blocks = grid_for(n4, kThreads, sm_count() * 8);
   adam_tracked_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, touched, n4, lr, beta1, beta2, eps,
                                                                      (float)((double)lr / bc1), (float)sqrt(bc2), zero_grad,
-                                                                     nullptr);
+                                                                     AdamDev{nullptr, nullptr, nullptr});
   return check_launch("adam_step_tracked");
 }
 
