@@ -695,6 +695,12 @@ __global__ void __launch_bounds__(kThreads)
 
 using namespace miso;
 
+// Blocks of disabled (non-intersecting) pairs exit at once and the host cannot know how many pairs are enabled (the
+// flags live on the device), so the grid is over-provisioned: ~32 blocks per SM spread over all pairs keeps the ~1/3
+// of pairs that do overlap in several waves of small blocks instead of less than one wave of big ones.
+#ifndef MISO_ALIGN_BLOCKS_PER_SM
+#define MISO_ALIGN_BLOCKS_PER_SM 32
+#endif
 extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, const miso_align_pair_t* pairs,
                                 int32_t num_pairs, int64_t max_M, const float* poses, double* out, int32_t flags,
                                 miso_stream_t stream) {
@@ -710,7 +716,7 @@ extern "C" int miso_align_batch(const miso_field_t* fields, int32_t num_fields, 
   MISO_REQUIRE(num_pairs <= 65535, "align_batch: too many pairs (%d)", num_pairs);
   // channel count is read on the host from nothing (fields live on the device): the ABI fixes C=4
   // per level for alignment (fdim=4, miso.py:122); other widths go through the generic path.
-  int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * 8) / std::max(1, std::min(num_pairs, sm_count() * 8))));
+  int bx = grid_for(max_M, kThreads, std::max(1, (sm_count() * MISO_ALIGN_BLOCKS_PER_SM) / std::max(1, std::min(num_pairs, sm_count() * MISO_ALIGN_BLOCKS_PER_SM))));
   dim3 grid(bx, num_pairs);
   if (want_gn)
     align_batch_kernel<4, true, 0><<<grid, kThreads, 0, s>>>(fields, pairs, poses, out);
