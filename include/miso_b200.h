@@ -168,6 +168,23 @@ int miso_mapping_step(const miso_field_t* field, const miso_decoder_t* dec, cons
                       const int32_t* eik_count, float* partials, float* loss_out, float* sdf_out,
                       miso_stream_t stream);
 
+/* Decoder-parameter gradients of miso_mapping_step's total (same arguments, same cfg; analytic eikonal term only):
+ * the `decoder.fix: False` case (grid_opt/models/grid_net.py:110,126,346-348), where autograd differentiates the MLP
+ * (modules.py:11-40) and, through create_graph=True (diff.py:27-33), the eikonal term's grad_x sdf w.r.t. the weights.
+ * d total / d {W1,b1,W2,b2,W3,b3} is ACCUMULATED into `grad` (NULL members are skipped; shapes as miso_decoder_t).
+ * A second pass over the batch, independent of miso_mapping_step (which yields the loss terms and the grid gradients);
+ * eik_count must hold the value miso_mapping_count wrote for this batch.  workspace: device
+ * float[miso_mapping_wgrad_workspace_floats()].  Two launches, deterministic (no atomics on the results). */
+typedef struct miso_decoder_grad {
+  float *W1, *b1, *W2, *b2, *W3, *b3;
+} miso_decoder_grad_t;
+int64_t miso_mapping_wgrad_workspace_floats(void);
+int miso_mapping_step_wgrad(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                            const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                            const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                            const int32_t* eik_count, const miso_decoder_grad_t* grad, float* workspace,
+                            miso_stream_t stream);
+
 /* The same step with the FINITE-DIFFERENCE eikonal term the shipped configs select (grad_method: finitediff,
  * configs/rgbd/scannet.yaml:48-49; grid_opt/diff.py:18-26 + loss.py:638-665):
  *   g_d = (f(x + eps e_d) - f(x - eps e_d)) / (2 eps), eik = mean (|g| - 1)^2, all six evaluations differentiated.

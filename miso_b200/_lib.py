@@ -35,6 +35,11 @@ class Decoder(C.Structure):
                 ("W3", C.c_void_p), ("b3", C.c_void_p), ("in_dim", C.c_int32), ("hidden_dim", C.c_int32)]
 
 
+class DecoderGrad(C.Structure):
+    _fields_ = [("W1", C.c_void_p), ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p),
+                ("W3", C.c_void_p), ("b3", C.c_void_p)]
+
+
 class Frames(C.Structure):
     _fields_ = [("ids", C.c_void_p), ("R", C.c_void_p), ("t", C.c_void_p), ("num_frames", C.c_int32)]
 
@@ -75,6 +80,10 @@ _SIGNATURES = {
     "miso_mapping_step_fd": (C.c_int, [C.POINTER(Field), C.POINTER(Decoder), C.POINTER(Frames), C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MappingCfg),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "miso_mapping_wgrad_workspace_floats": (C.c_int64, []),
+    "miso_mapping_step_wgrad": (C.c_int, [C.POINTER(Field), C.POINTER(Decoder), C.POINTER(Frames), C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MappingCfg),
+                                          C.c_void_p, C.POINTER(DecoderGrad), C.c_void_p, C.c_void_p]),
     "miso_align_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p]),
     "miso_align_intersections": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,

@@ -32,13 +32,14 @@ def _levels(net):
     return feats
 
 
-def _fused_spec(net):
+def _fused_spec(net, trainable_decoder_ok=False):
     dec = getattr(net, "decoder", None)
     feats = net.features
     ok = (dec is not None and getattr(net, "decoder_type", "mlp") == "mlp" and net.pos_invariant
           and net.decoder_hidden_dim == 64 and net.decoder_hidden_layers == 1 and net.decoder_out_dim == 1
           and (net.num_levels, net.fdim) in {(1, 4), (2, 4), (3, 4), (4, 4), (1, 8), (2, 8), (1, 16)}
-          and feats[0].feature.is_cuda and not any(p.requires_grad for p in dec.parameters())
+          and feats[0].feature.is_cuda
+          and (trainable_decoder_ok or not any(p.requires_grad for p in dec.parameters()))
           and getattr(net, "grid_type", "regular") == "regular")
     if not ok:
         return None

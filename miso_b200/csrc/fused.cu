@@ -822,6 +822,8 @@ __global__ void __launch_bounds__(kThreads, MISO_MAP_MIN_BLOCKS)
   }
 }
 
+#include "fused_wgrad.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // Decoder on the tensor cores (tcgen05, 3xTF32).
 //
@@ -1728,6 +1730,45 @@ extern "C" int miso_mapping_step(const miso_field_t* field, const miso_decoder_t
                                  miso_stream_t stream) {
   return mapping_step_impl(field, dec, frames, x, N, gt_sdf, gt_valid, gt_sign, weights, cfg, eik_count, partials,
                            loss_out, sdf_out, stream, nullptr, 0, 0.f);
+}
+
+// Decoder-parameter gradients of the same step (decoder.fix: False): second pass over the batch, see fused_wgrad.cuh.
+static int wgrad_blocks() { return sm_count() * 2; }
+extern "C" int64_t miso_mapping_wgrad_workspace_floats(void) {
+  return (int64_t)wgrad_blocks() * wgrad::row_stride<16>();   // widest supported decoder input
+}
+extern "C" int miso_mapping_step_wgrad(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,
+                                       const float* x, int64_t N, const float* gt_sdf, const uint8_t* gt_valid,
+                                       const float* gt_sign, const float* weights, const miso_mapping_cfg_t* cfg,
+                                       const int32_t* eik_count, const miso_decoder_grad_t* grad, float* workspace,
+                                       miso_stream_t stream) {
+  if (int e = validate_field(field, false)) return e;
+  if (int e = validate_decoder(dec, field->num_levels * field->level[0].C)) return e;
+  if (int e = validate_frames(frames)) return e;
+  MISO_REQUIRE(cfg && grad && workspace, "mapping_step_wgrad: null cfg/grad/workspace");
+  MISO_REQUIRE(N > 0 && x && gt_sdf && gt_valid && gt_sign, "mapping_step_wgrad: null inputs or N == 0");
+  MISO_REQUIRE(cfg->loss_type == 0 || cfg->loss_type == 1, "mapping_step_wgrad: loss_type must be 0 (L1) or 1 (L2)");
+  MISO_REQUIRE(cfg->eik_mode == 0 || cfg->eik_mode == 1, "mapping_step_wgrad: eik_mode must be 0 or 1");
+  MISO_REQUIRE(!cfg->n_device, "mapping_step_wgrad: device-side sample counts are not supported");
+  const bool eik_on = cfg->eik_mode != 0 && cfg->weight_eik != 0.f;
+  MISO_REQUIRE(!(eik_on && cfg->eik_trunc_dist >= 0.f) || eik_count, "mapping_step_wgrad: eik filter needs eik_count");
+  cudaStream_t s = (cudaStream_t)stream;
+  const miso_frames_t fr = frames_or_none(frames);
+  MapArgs m;
+  memset(&m, 0, sizeof(m));
+  m.x = x, m.N = N, m.gt_sdf = gt_sdf, m.gt_valid = gt_valid, m.gt_sign = gt_sign, m.weights = weights;
+  m.cfg = *cfg, m.eik_count = eik_count;
+  const int nblocks = (int)std::min<int64_t>(wgrad_blocks(), (N + wgrad::kT - 1) / wgrad::kT);
+  MISO_DISPATCH_LC(field->num_levels, field->level[0].C, {
+    constexpr size_t smem = sizeof(wgrad::Smem<L * C>);
+    auto k = mapping_wgrad_kernel<L, C>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<nblocks, kThreads, smem, s>>>(*field, *dec, fr, m, workspace);
+    if (int e = check_launch("mapping_step_wgrad")) return e;
+    constexpr int np = wgrad::param_count<L * C>();
+    mapping_wgrad_finalize_kernel<L * C><<<(np + kThreads - 1) / kThreads, kThreads, 0, s>>>(workspace, nblocks, *grad);
+  });
+  return check_launch("mapping_step_wgrad(finalize)");
 }
 
 extern "C" int miso_mapping_step_fd(const miso_field_t* field, const miso_decoder_t* dec, const miso_frames_t* frames,

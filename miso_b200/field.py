@@ -100,6 +100,12 @@ class DecoderSpec:
         return d
 
 
+def decoder_parameters(mlp) -> list:
+    """[W1, b1, W2, b2, W3, b3] of an MLPNet, the live parameters (order of miso_decoder_t / miso_decoder_grad_t)."""
+    linears = [m for m in mlp.network if isinstance(m, torch.nn.Linear)]
+    return [t for l in linears for t in (l.weight, l.bias)]
+
+
 class FramesSpec:
     """Per-sample keyframe ids + per-keyframe poses (loss.py:764-774), all on the device."""
 

@@ -87,6 +87,7 @@ class MappingWorkspace:
         self.partials = torch.zeros(int(lib.miso_mapping_workspace_floats()), dtype=torch.float32, device=device)
         self.eik_count = torch.zeros(1, dtype=torch.int32, device=device)
         self.fd = None   # (12 N) floats of the finite-difference step, grown on demand
+        self.wgrad = None   # per-CTA rows of the decoder-gradient pass, allocated on first use
 
     @classmethod
     def get(cls, device):
@@ -98,12 +99,14 @@ class MappingWorkspace:
 
 def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
                      weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None,
-                     n_total=0, count_allreduce=None, fd_eps=None, n_device=None, count_on=None):
+                     n_total=0, count_allreduce=None, fd_eps=None, n_device=None, count_on=None, dec_grads=None):
     """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
     terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped).
     `fd_eps` selects the finite-difference eikonal term (miso_mapping_step_fd) instead of the analytic one.
     `n_device` (device int32 tensor) limits the step to the first *n_device samples (batch compacted on the device,
-    miso_b200.sharded_fit); `count_on` is then the FULL batch's gt sdf for the |gt| < eik_trunc count."""
+    miso_b200.sharded_fit); `count_on` is then the FULL batch's gt sdf for the |gt| < eik_trunc count.
+    `dec_grads` (six float32 tensors shaped like W1, b1, W2, b2, W3, b3, or None entries): the trainable-decoder case --
+    d total / d decoder parameters is accumulated into them by a second pass (miso_mapping_step_wgrad)."""
     lib = _lib.load()
     dev = x.device
     N = x.shape[0]
@@ -147,6 +150,22 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
                 gt_sdf.data_ptr(), gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg),
                 ws.eik_count.data_ptr(), ws.partials.data_ptr(), loss_out.data_ptr(), _lib.ptr(sdf_out), stream),
                 "mapping_step")
+        if dec_grads is not None:
+            if fd_eps is not None and cfg.eik_mode == 1:
+                raise RuntimeError("decoder gradients are fused for the analytic eikonal term only")
+            if n_device is not None:
+                raise RuntimeError("decoder gradients are not available for device-compacted batches")
+            if ws.wgrad is None:
+                ws.wgrad = torch.empty(int(lib.miso_mapping_wgrad_workspace_floats()), dtype=torch.float32, device=dev)
+            dg = _lib.DecoderGrad()
+            for name, t, ref in zip(("W1", "b1", "W2", "b2", "W3", "b3"), dec_grads, spec.decoder.tensors):
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != ref.numel()):
+                    raise RuntimeError(f"decoder gradient {name}: expected a contiguous float32 tensor of {ref.numel()} elements")
+                setattr(dg, name, _lib.ptr(t))
+            _lib.check(lib.miso_mapping_step_wgrad(
+                C.byref(fld), C.byref(dec), C.byref(fr) if fr is not None else None, x.data_ptr(), N,
+                gt_sdf.data_ptr(), gt_valid.data_ptr(), gt_sign.data_ptr(), _lib.ptr(weights), C.byref(cfg),
+                ws.eik_count.data_ptr(), C.byref(dg), ws.wgrad.data_ptr(), stream), "mapping_step_wgrad")
         if profile:
             e1.record(torch.cuda.current_stream(dev))
             PROFILE_EVENTS.append((e0, e1))
@@ -174,11 +193,14 @@ class _FusedMappingLoss(torch.autograd.Function):
     with NaN instead of returning a silently wrong gradient (a single kernel cannot un-mix them)."""
 
     @staticmethod
-    def forward(ctx, x, gt_sdf, gt_valid, gt_sign, weights, spec, frames, cfg, *feats):
-        need = [f.requires_grad for f in feats]
-        grads = [torch.zeros_like(f) if n else None for f, n in zip(feats, need)]
-        out = mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, **cfg)
-        ctx.grads = grads
+    def forward(ctx, x, gt_sdf, gt_valid, gt_sign, weights, spec, frames, cfg, n_levels, *tensors):
+        # tensors = the level grids, then (trainable decoder only) W1, b1, W2, b2, W3, b3
+        feats, dec = tensors[:n_levels], tensors[n_levels:]
+        grads = [torch.zeros_like(f) if f.requires_grad else None for f in feats]
+        dgrads = [torch.zeros_like(p) if p.requires_grad else None for p in dec]
+        out = mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights,
+                               dec_grads=dgrads if any(g is not None for g in dgrads) else None, **cfg)
+        ctx.grads = grads + dgrads
         ctx.set_materialize_grads(False)  # terms the caller drops arrive as None, not as zeros
         w = out.new_tensor([cfg["weight_sdf"], cfg["weight_fs"], cfg["weight_eik"] if cfg["eik_on"] else 0.0])
         terms = out[:3] * w
@@ -191,14 +213,14 @@ class _FusedMappingLoss(torch.autograd.Function):
         ctx.grads = None
         gs = [g for g in (g0, g1, g2) if g is not None]
         if not gs:
-            return (None,) * (8 + len(grads))
+            return (None,) * (9 + len(grads))
         s = gs[0]
         for g in gs[1:]:
             s = torch.where(g == s, s, torch.full_like(s, float("nan")))
         outs = []
         for G in grads:
             outs.append(None if G is None else G.mul_(s))
-        return (None,) * 8 + tuple(outs)
+        return (None,) * 9 + tuple(outs)
 
 
 class MisoLossMappingBase:
@@ -234,16 +256,23 @@ class MisoLossMappingBase:
         raise NotImplementedError
 
     def _fused_ok(self, model):
-        if getattr(model, "fused_spec", None) is None or model.fused_spec() is None:
+        if getattr(model, "fused_spec", None) is None or model.fused_spec(trainable_decoder_ok=True) is None:
             return False
         if self.loss_type not in ("L1", "L2"):
             return False
         if self.weight_eik > 0 and self.grad_method != "autograd":
-            # finite differences run fused (miso_mapping_step_fd) where the two-threads-per-point kernel applies
-            if self.grad_method != "finitediff" or not self._fd_kernel_covers(model):
+            # finite differences run fused (miso_mapping_step_fd) where the two-threads-per-point kernel applies;
+            # the decoder-gradient pass (miso_mapping_step_wgrad) covers the analytic term only
+            if (self.grad_method != "finitediff" or not self._fd_kernel_covers(model)
+                    or self._trainable_decoder(model)):
                 return False
         R, t, _ = self.frame_table(model)
         return not (R.requires_grad or t.requires_grad)
+
+    @staticmethod
+    def _trainable_decoder(model):
+        dec = getattr(model, "decoder", None)
+        return dec is not None and any(p.requires_grad for p in dec.parameters())
 
     @staticmethod
     def _fd_kernel_covers(model) -> bool:
@@ -279,12 +308,14 @@ class MisoLossMappingBase:
         return _field.FramesSpec(ids, R, t)
 
     def _compute_fused(self, model, coords_frame, ids, weights, gt_sdf, gt_valid, gt_sign):
-        spec = model.fused_spec()
+        spec = model.fused_spec(trainable_decoder_ok=True)
         frames = self._frames(model, ids)
         x = _field._prep_x(coords_frame)
+        levels = model.level_tensors()
+        dec_params = _field.decoder_parameters(model.decoder) if self._trainable_decoder(model) else []
         t_sdf, t_fs, t_eik, raw = _FusedMappingLoss.apply(
             x, _flat_f32(gt_sdf), _flat_u8(gt_valid), _flat_f32(gt_sign), _flat_f32(weights), spec, frames,
-            self._step_cfg(), *model.level_tensors())
+            self._step_cfg(), len(levels), *levels, *dec_params)
         self.last_terms = raw
         loss_dict = {f"sdf_{self.loss_type}": t_sdf}
         if self.weight_eik > 0:
@@ -319,8 +350,8 @@ class MisoLossMappingBase:
         loss tensor [sdf, fs, eik, total].  `n_total` / `count_allreduce` are the point-sharded multi-GPU
         hooks (miso_b200.dist): means run over the global batch so per-rank results sum."""
         if not self._fused_ok(model):
-            raise RuntimeError("step_into_grads needs the fused path (fixed decoder, locked poses, "
-                               "grad_method='autograd' when weight_eik > 0)")
+            raise RuntimeError("step_into_grads needs the fused path (64-wide MLP decoder, locked poses; a trainable "
+                               "decoder needs grad_method='autograd' when weight_eik > 0)")
         coords_frame = model_input["coords_frame"][0]
         ids = model_input["sample_frame_ids"][0, :, 0]
         feats = model.level_tensors()
@@ -330,10 +361,18 @@ class MisoLossMappingBase:
             if active and f.grad is None:
                 f.grad = torch.zeros_like(f)
             grads.append(f.grad if active else None)
-        raw = mapping_step_raw(feats, grads, model.fused_spec(), self._frames(model, ids),
+        dec_grads = None
+        if self._trainable_decoder(model):
+            dec_grads = []
+            for p in _field.decoder_parameters(model.decoder):
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                dec_grads.append(p.grad if p.requires_grad else None)
+        raw = mapping_step_raw(feats, grads, model.fused_spec(trainable_decoder_ok=True), self._frames(model, ids),
                                _field._prep_x(coords_frame), _flat_f32(gt["sdf"][0]), _flat_u8(gt["sdf_valid"][0]),
                                _flat_f32(gt["sdf_signs"][0]), _flat_f32(model_input["weights"][0]),
-                               n_total=n_total, count_allreduce=count_allreduce, **self._step_cfg())
+                               n_total=n_total, count_allreduce=count_allreduce, dec_grads=dec_grads,
+                               **self._step_cfg())
         self.last_terms = raw
         return raw
 

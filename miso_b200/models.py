@@ -390,16 +390,19 @@ class GridNet(BaseNet):
         return torch.matmul(self.Rwk, geo.so3_exp_map(dr)), self.twk + dt
 
     # ---- queries: the hot path ------------------------------------------------------------------------
-    def fused_spec(self) -> Optional[_field.FieldSpec]:
+    def fused_spec(self, trainable_decoder_ok: bool = False) -> Optional[_field.FieldSpec]:
         """Descriptor for the fused kernels, or None when they do not apply (trainable / non-64-wide / positional
         decoder, unsupported (levels, channels), not on CUDA).  The cheap predicate is re-evaluated on every call
         -- un-freezing the decoder or swapping it takes effect immediately -- and only the packed decoder weights
-        are cached, keyed on the identity and storage of the weight tensors."""
+        are cached, keyed on the identity and storage of the weight tensors.  `trainable_decoder_ok`: the mapping
+        step also covers a trainable decoder (its parameter gradients come from miso_mapping_step_wgrad); the
+        forward-only users keep the autograd route for it."""
         dec = self.decoder
         if (dec is None or self.decoder_type != "mlp" or not self.pos_invariant or self.decoder_hidden_dim != 64
                 or self.decoder_hidden_layers != 1 or self.decoder_out_dim != 1
                 or (self.num_levels, self.fdim) not in FUSED_LEVEL_CHANNEL_SHAPES
-                or not self.features[0].feature.is_cuda or any(p.requires_grad for p in dec.parameters())):
+                or not self.features[0].feature.is_cuda
+                or (not trainable_decoder_ok and any(p.requires_grad for p in dec.parameters()))):
             return None
         key = tuple((id(p), p.data_ptr(), p._version) for p in dec.parameters())
         if self._decoder_spec is None or self._decoder_spec[0] != key:

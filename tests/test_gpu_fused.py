@@ -148,6 +148,80 @@ def test_mapping_generic_path_matches_fused_and_oracle():
         assert rel_err(a, b) < TOL_G
 
 
+@pytest.mark.parametrize("loss_type,w_eik,eik_trunc,w_fs,shape,n", [
+    ("L1", 0.5, None, 0.1, (2, 4), 6000), ("L2", 0.5, 0.1, 0.5, (2, 4), 4133), ("L1", 0.0, None, 0.1, (2, 4), 3000),
+    ("L1", 0.5, None, 0.1, (1, 16), 3000), ("L2", 0.3, None, 0.0, (3, 4), 2500), ("L1", 0.5, None, 0.1, (1, 4), 64)])
+def test_mapping_trainable_decoder_fused(loss_type, w_eik, eik_trunc, w_fs, shape, n):
+    """decoder.fix: False (grid_net.py:110,126,346-348) stays on the fused step: the grid gradients and loss terms come
+    from miso_mapping_step, d total / d {W1,b1,W2,b2,W3,b3} -- including the eikonal term's second-order path through
+    the weights -- from miso_mapping_step_wgrad; both against the oracle's autograd on a kink-free batch."""
+    from helpers import drop_fragile_points
+    from miso_b200.loss import MisoLossMapping
+    net, _, o2 = make_pair(n_levels=shape[0], fdim=shape[1], fix=False, scale=3 if shape[0] > 2 else 5)
+    mi, gt, (R, t) = _batch(n + 400, seed=7)
+    mi, gt, _ = drop_fragile_points(o2, mi, gt, (R, t), n, 0.15)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type=loss_type, weight_sdf=1.0, weight_eik=w_eik, weight_fs=w_fs, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=eik_trunc)
+    assert any(p.requires_grad for p in net.decoder.parameters()) and net.fused_spec() is None
+    assert L._fused_ok(net)
+    ld = L.compute(net, _to_cuda(mi), _to_cuda(gt))
+    sum(v.mean() for v in ld.values()).backward()
+    lo = O.mapping_loss(o2, mi, gt, {k: (R[k], t[k]) for k in range(R.shape[0])}, loss_type, 1.0, w_eik, w_fs, 0.15,
+                        grad_method="autograd", eik_trunc_dist=eik_trunc)
+    sum(lo.values()).backward()
+    for k in lo:
+        assert rel_err(ld[k], lo[k]) < TOL_G, k
+    for l in range(shape[0]):
+        assert rel_err(net.features[l].feature.grad, o2.features[l].grad) < TOL_G
+    names = ["W1", "b1", "W2", "b2", "W3", "b3"]
+    got = [p.grad.clone() for p in net.decoder.parameters()]
+    for name, a, b in zip(names, got, [p.grad for p in o2.decoder.parameters()]):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < TOL_G, name
+    # the trainer's entry point accumulates the same gradients into .grad (twice the value after a second pass)
+    L.step_into_grads(net, _to_cuda(mi), _to_cuda(gt))
+    for name, a, p in zip(names, got, net.decoder.parameters()):
+        assert rel_err(p.grad, 2 * a) < 1e-6, name
+
+
+def test_trainer_with_trainable_decoder_matches_oracle_adam():
+    """Three fused train steps with decoder.fix: False vs oracle loss + torch.optim.Adam over grids AND decoder."""
+    from helpers import drop_fragile_points
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    net, _, o2 = make_pair(fix=False)
+    mi, gt, (R, t) = _batch(4400, seed=9)
+    mi, gt, _ = drop_fragile_points(o2, mi, gt, (R, t), 4000, 0.15)
+    for k in range(R.shape[0]):
+        net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+    net.unlock_feature()
+    net.lock_pose()
+    L = MisoLossMapping(loss_type="L1", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                        grad_method="autograd", eik_trunc_dist=None)
+    tr = GridTrainer({"grid_training_mode": "joint", "learning_rate": 1e-3}, net, L, lambda e: (mi, gt))
+    opt = torch.optim.Adam(list(o2.features.parameters()) + list(o2.decoder.parameters()), lr=1e-3)
+    poses = {k: (R[k], t[k]) for k in range(R.shape[0])}
+    for _ in range(3):
+        terms = tr.train_step(_to_cuda(mi), _to_cuda(gt))
+        opt.zero_grad()
+        lo = O.mapping_loss(o2, mi, gt, poses, "L1", 1.0, 0.5, 0.1, 0.15, grad_method="autograd", eik_trunc_dist=None)
+        tot = sum(lo.values())
+        tot.backward()
+        opt.step()
+        assert rel_err(terms[3], tot) < TOL_G
+    # Adam's first steps are sign-like (|update| ~ lr regardless of the gradient's size): compare the parameters
+    for a, b, b0 in zip(net.decoder.parameters(), o2.decoder.parameters(), synth.decoder_weights(8, seed=0).values()):
+        assert rel_err(a, b) < 2e-4
+        if b0.numel() > 1:
+            assert rel_err(b, b0) > 1e-3     # the decoder did move
+    for l in range(2):
+        assert rel_err(net.features[l].feature, o2.features[l]) < 1e-3
+
+
 def test_trainer_steps_match_oracle_adam():
     """k fused train steps (count + mapping step + fused Adam/zero) vs oracle loss + torch.optim.Adam."""
     from miso_b200.loss import MisoLossMapping
