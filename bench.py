@@ -304,7 +304,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None   # sampled across all timed regions (value + e2e + e2e_compact)
     assert torch.isfinite(loss_host[wu:]).all(), "non-finite loss in the compact e2e run"
 
-    align, ncd, torch_gpu, fd = None, None, None, None
+    align, ncd, torch_gpu, fd, wdec = None, None, None, None, None
     if not args.no_extras:
         del dev_batches
         torch.cuda.empty_cache()
@@ -312,6 +312,7 @@ def run_ours(args):
         if world == 1:
             torch_gpu = torch_gpu_arm(device)
             fd = bench_fd(device)
+            wdec = bench_trainable_decoder(device)
         align = bench_align(device, iters=10, warmup=2, world=world, rank=rank)
         if world > 1:
             # pair-sharded: an iteration ends when the slowest rank is done
@@ -362,7 +363,7 @@ def run_ours(args):
                      "floors_ms": {"red_v4_scatter_only": 0.121, "gather_only": 0.041,
                                    "source": "profiles/r01_scatter_probe.json (benchmarks/scatter_probe.py, same batch)"}},
         "final_loss_terms": final_loss,
-        "extra": {"ncd": ncd, "torch_gpu_baseline": torch_gpu, "finite_difference_step": fd, "align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
+        "extra": {"ncd": ncd, "torch_gpu_baseline": torch_gpu, "finite_difference_step": fd, "trainable_decoder_step": wdec, "align": align, "align_workload": "16 ScanNet-shaped submaps (4x4 floor plan, 40 % overlap), 120 pairs "
                   "(sharded round-robin over ranks, pose-gradient all_reduce), latent L2 loss, Adam lr 1e-2; level 0: "
                   "<= 32 k samples/pair, level 1: <= 4 M samples/pair"},
     }
@@ -690,7 +691,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
     return out
 
 
-def torch_gpu_arm(device, steps=5, warmup=2):
+def torch_gpu_arm(device, steps=5, warmup=2, trainable_decoder=False):
     """The reference's GPU op sequence for the same headline step on this B200, as the kernel-for-kernel bar (SURVEY.md
     section 2a / 8d): ATen grid_sampler_3d (+ its backward) per level, the reference's own double-backward extension
     (oracle/_ref/gridsample_grad2.so, built unmodified by oracle/build_ref.py) for the eikonal term, cuBLAS Linear
@@ -708,7 +709,12 @@ def torch_gpu_arm(device, steps=5, warmup=2):
     mi = {k: v.to(device) for k, v in mi.items()}
     gt = {k: v.to(device) for k, v in gt.items()}
     poses = {k: (R[k].to(device), t[k].to(device)) for k in range(R.shape[0])}
-    opt = torch.optim.Adam(list(model.features.parameters()), lr=1e-3)
+    params = list(model.features.parameters())
+    if trainable_decoder:     # decoder.fix: False -- autograd also differentiates the MLP weights (second order included)
+        for p in model.decoder.parameters():
+            p.requires_grad_(True)
+        params += list(model.decoder.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
     first = None
 
     def step():
@@ -723,7 +729,7 @@ def torch_gpu_arm(device, steps=5, warmup=2):
     for i in range(warmup):
         tot = step()
         if i == 0:
-            first = float(tot)
+            first = float(tot.detach())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -800,6 +806,44 @@ def bench_fd(device, steps=20, warmup=3):
             "ms_per_step": ms, "points_per_s": N_POINTS / (ms * 1e-3), "reference_gpu_ms_per_step": ms_ref,
             "speedup_vs_reference_gpu": ms_ref / ms, "first_step_total": ours_total, "reference_first_step_total": ref_total,
             "first_step_rel_err": abs(ours_total - ref_total) / abs(ref_total)}
+
+
+def bench_trainable_decoder(device, steps=20, warmup=3):
+    """The headline step with `decoder.fix: False` (grid_net.py:110,126,346-348): miso_mapping_step (loss terms + grid
+    gradients) + miso_mapping_step_wgrad (decoder-parameter gradients incl. the eikonal term's second-order path) + fused
+    Adam over grids and decoder, against the reference's GPU op sequence training the same parameters."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    mi, gt, poses = host_batch(0, 0)
+    dmi = {k: v.to(device) for k, v in mi.items()}
+    dgt = {k: v.to(device) for k, v in gt.items()}
+    net = build_model(device, poses, seed=0)
+    for p in net.decoder.parameters():
+        p.requires_grad_(True)
+    tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net, MisoLossMapping(**LOSS_CFG), None,
+                     device=device)
+    first = None
+    for _ in range(warmup):
+        out = tr.train_step(dmi, dgt)
+        first = out if first is None else first
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.train_step(dmi, dgt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ours_total = float(first[3])
+    del tr, net
+    torch.cuda.empty_cache()
+    ref = torch_gpu_arm(device, steps=5, warmup=2, trainable_decoder=True)
+    return {"what": "headline step with a TRAINABLE decoder (decoder.fix: False): fused step + decoder-gradient pass + Adam "
+                    "vs the reference's GPU op sequence, same batch and parameters",
+            "ms_per_step": ms, "points_per_s": N_POINTS / (ms * 1e-3), "reference_gpu_ms_per_step": ref["ms_per_step"],
+            "speedup_vs_reference_gpu": ref["ms_per_step"] / ms, "first_step_total": ours_total,
+            "reference_first_step_total": ref["first_step_total"],
+            "first_step_rel_err": abs(ours_total - ref["first_step_total"]) / abs(ref["first_step_total"])}
 
 
 def run_torch_gpu(args):

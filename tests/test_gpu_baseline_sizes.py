@@ -129,6 +129,29 @@ def test_mapping_step_scannet_grid_kink_free(log2n):
     RESULTS[f"scannet_2p{log2n}_kink_free"]["samples_dropped_from_pool"] = dropped
 
 
+def test_mapping_step_trainable_decoder_scannet_2p20_kink_free():
+    """decoder.fix: False at BASELINE configs[1] size: every CTA of miso_mapping_step_wgrad walks ~55 tiles, the
+    per-CTA rows are summed by the finalize kernel.  Decoder-parameter gradients vs the oracle's autograd."""
+    bound = synth.SCANNET_SUBMAP_BOUND
+    N = 1 << 20
+    net, _, o2 = make_pair(bound=bound, base_cell=0.5, scale=5, std=1e-2, seed=3, num_poses=49, fix=False)
+    mi, gt, poses = synth.rgbd_batch(N + N // 16, num_kf=49, bound=bound, seed=57)
+    mi, gt, dropped = drop_fragile_points(o2, mi, gt, poses, N, 0.15)
+    for p in net.decoder.parameters():
+        p.grad = None
+    got = _run_fused(net, mi, gt, poses, "L1", 0.5, 0.1, 0.15, None)
+    want = oracle_mapping_chunked(o2, mi, gt, poses, "L1", 1.0, 0.5, 0.1, 0.15, None)
+    _check(net, o2, got, want, "scannet_2p20_trainable_decoder_kink_free")
+    errs = {}
+    for name, a, b in zip(["W1", "b1", "W2", "b2", "W3", "b3"], net.decoder.parameters(), o2.decoder.parameters()):
+        errs[name] = rel_err(a.grad, b.grad)
+    RESULTS["scannet_2p20_trainable_decoder_kink_free"]["decoder_grad_rel_err_vs_fp32_oracle"] = errs
+    RESULTS["scannet_2p20_trainable_decoder_kink_free"]["samples_dropped_from_pool"] = dropped
+    _record("scannet_2p20_trainable_decoder_kink_free", **RESULTS["scannet_2p20_trainable_decoder_kink_free"])
+    for name, e in errs.items():
+        assert e < TOL_GRAD, (name, e)
+
+
 def test_mapping_step_ncd_quad_grid_2p22_lidar_kink_free():
     bound = synth.NCD_QUAD_BOUND
     N = 1 << 22
