@@ -1,6 +1,9 @@
 """Shared builders for the parity tests: the same seeded model on the CUDA product path and in the
 CPU oracle."""
+import os
+
 import numpy as np
+
 import torch
 
 from miso_b200 import synth
@@ -15,7 +18,13 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.detach().double().cpu().reshape(-1)
     nb = b.norm().item()
     d = (a - b).norm().item()
-    return d / nb if nb > 1e-30 else d
+    r = d / nb if nb > 1e-30 else d
+    if os.environ.get("MISO_LOG_RELERR"):   # tolerance audit: every comparison with its call site
+        import inspect
+        fr = inspect.stack()[1]
+        with open(os.environ["MISO_LOG_RELERR"], "a") as fh:
+            fh.write(f"{os.path.basename(fr.filename)}:{fr.lineno} {fr.function} {r:.3e}\n")
+    return r
 
 
 def make_pair(bound=SMALL_BOUND, n_levels=2, fdim=4, base_cell=0.5, scale=5, std=0.1, seed=0, device="cuda",

@@ -330,12 +330,12 @@ def test_tracker_lm_normal_equations_and_step():
         H, b, fov = tr.normal_equations(xf.cuda(), gt_sdf.cuda(), Rwf.cuda(), twf.cuda())
         Ho, bo, do = O.lm_normal_equations(o2, xf, gt_sdf, Rwf, twf, loss_type=loss_type, gm_scale=0.1, lm_lambda=1e-4)
         assert rel_err(H, Ho) < TOL_G and rel_err(b, bo) < TOL_G
-        assert rel_err(torch.linalg.solve(H, -b), do) < 1e-3   # 6x6 solve amplifies by cond(H)
+        assert rel_err(torch.linalg.solve(H, -b), do) < TOL_G   # measured 3.6e-7
     mi = {"coords_frame": xf[None].cuda(), "sample_frame_ids": torch.zeros(1, 4000, 1, dtype=torch.long).cuda()}
     gt = {"sdf": gt_sdf[None].cuda(), "sdf_valid": torch.ones(1, 4000, 1, dtype=torch.bool).cuda()}
     info = tr.lm_step(0, mi, gt)
-    assert rel_err(net.rotation_corrections[0], do[:3, 0]) < 1e-3
-    assert rel_err(net.translation_corrections[0], do[3:]) < 1e-3
+    assert rel_err(net.rotation_corrections[0], do[:3, 0]) < TOL_G
+    assert rel_err(net.translation_corrections[0], do[3:]) < TOL_G
     assert 0.0 <= info["fov_overlap"] <= 1.0
     # one-launch normal equations vs the torch formulation on the same fused sdf+gradient, incl. the in-kernel
     # |gt| < trunc filter against an explicit nonzero()/gather selection (tracker.py:158-164), and fov_overlap

@@ -151,8 +151,8 @@ def test_alignment_sdf_against_reference_outputs(loss):
     (key, val), = pairwise_loss_sdf(atlas, loader, 0, 1, align_loss=loss, device="cuda").items()
     assert key == str(z[f"{loss}.key"])
     val.backward()
-    # the residual is a DIFFERENCE of two forward values that are each within 1e-5: allow 5e-5 on the loss
-    assert rel_err(val, T(z[f"{loss}.loss"])) < 5e-5
+    # the residual is a DIFFERENCE of two forward values that are each within 1e-5: allow 2e-5 on the loss (measured 1.1e-5)
+    assert rel_err(val, T(z[f"{loss}.loss"])) < 2e-5
     for i in range(2):
         assert rel_err(atlas.rotation_corrections[i].grad, T(z[f"{loss}.grad_rot{i}"])) < 1e-4
         assert rel_err(atlas.translation_corrections[i].grad, T(z[f"{loss}.grad_tra{i}"])) < 1e-4
@@ -191,7 +191,7 @@ def test_loss_variants_and_dense_queries_against_reference_outputs():
     ld = L.compute(net, {"coords": coords[None]}, {"sdf": gts[None], "sdf_valid": valid[None], "sdf_sign": sign[None]})
     sum(ld.values()).backward()
     for k in ("sdf", "pos_space", "neg_space", "eik"):
-        assert rel_err(ld[k], T(z[f"tsdf.{k}"])) < 2e-5, k
+        assert rel_err(ld[k], T(z[f"tsdf.{k}"])) < 1e-5, k
     for l in range(2):
         assert rel_err(net.features[l].feature.grad, T(z[f"tsdf.grad_feat{l}"])) < 1e-4
         net.features[l].feature.grad = None
@@ -224,7 +224,7 @@ def test_loss_variants_and_dense_queries_against_reference_outputs():
 @pytest.mark.parametrize("loss_type", ["L2", "GM"])
 def test_tracker_lm_step_against_reference_outputs(loss_type):
     """Tracker.lm_step through the one-launch normal equations (miso_track_normal_equations) vs the pose update the
-    reference's own lm_step produced (tests/golden/tracker.npz).  The 6x6 solve amplifies by cond(H): 1e-3."""
+    reference's own lm_step produced (tests/golden/tracker.npz): north-star pose tolerance 1e-4 (measured 1.2e-6)."""
     from miso_b200.tracker import Tracker
     z = load("tracker.npz")
     N = z["coords_frame"].shape[0]
@@ -235,8 +235,8 @@ def test_tracker_lm_step_against_reference_outputs(loss_type):
         net.set_initial_kf_pose(0, T(z["Rwf"]), T(z["twf"]), kf_key="KF0")
         tr = Tracker(net, loss_type=loss_type, gm_scale_sdf=0.1, lm_lambda=1e-4, trunc_dist=trunc)
         info = tr.lm_step(0, mi, gt)
-        assert rel_err(net.rotation_corrections[0], T(z[f"{loss_type}.{tag}.delta_R"])) < 1e-3
-        assert rel_err(net.translation_corrections[0], T(z[f"{loss_type}.{tag}.delta_t"])) < 1e-3
+        assert rel_err(net.rotation_corrections[0], T(z[f"{loss_type}.{tag}.delta_R"])) < 1e-4
+        assert rel_err(net.translation_corrections[0], T(z[f"{loss_type}.{tag}.delta_t"])) < 1e-4
         ref = z[f"{loss_type}.{tag}.info"]
         assert abs(info["grad_norm"] - ref[2]) < 1e-4 * ref[2] and abs(info["fov_overlap"] - ref[3]) < 1e-6
 
@@ -274,8 +274,8 @@ def test_alignment_loop_against_reference_outputs(fused_glue):
         A.generic_align_multiple_submaps(atlas, None, ("latent", None), num_iters=4, lr=1e-2, level=level,
                                          fused_pose_glue=fused_glue)
     for i in range(3):
-        assert rel_err(atlas.rotation_corrections[i], T(z[f"final.rot{i}"])) < 1e-3, i
-        assert rel_err(atlas.translation_corrections[i], T(z[f"final.tra{i}"])) < 1e-3, i
+        assert rel_err(atlas.rotation_corrections[i], T(z[f"final.rot{i}"])) < 1e-4, i      # measured 2.2e-6
+        assert rel_err(atlas.translation_corrections[i], T(z[f"final.tra{i}"])) < 1e-4, i
 
 
 def _variants_atlas(z):
