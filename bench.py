@@ -575,7 +575,7 @@ def build_ncd_model(device, poses):
     return net
 
 
-def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
+def bench_ncd(device, steps=100, warmup=5, world=1, rank=0, modes=("allreduce", "slab"), halo="auto"):
     """Fused step + Adam on the NCD quad grid (levels 20x90x90 + 100x450x450 x C4: the 324 MB fine level, its gradient
     and the Adam moments are NOT L2-resident, so dram traffic is meaningful here), 2^22 LiDAR-sampled points per step.
     One GPU: the whole batch.  N GPUs (strong scaling, same global batch): (a) the north star's split -- contiguous
@@ -638,25 +638,27 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
         del tr1, net1
         torch.cuda.empty_cache()
         total_steps = warmup + steps
+        rel_a = [0.0]
         # ---- (a) point chunks + dense-gradient all_reduce + replicated Adam ----
-        b0, b1 = mdist.shard_points(NCD_POINTS, rank, world)
-        smi = {k: v[:, b0:b1].contiguous() for k, v in dmi.items()}
-        sgt = {k: v[:, b0:b1].contiguous() for k, v in dgt.items()}
-        net_a = build_ncd_model(device, poses)
-        tr_a = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net_a, MisoLossMapping(**NCD_LOSS), None,
-                           device=device)
-        ms_a, terms_a = timed(lambda: tr_a.train_step(smi, sgt, n_total=NCD_POINTS, allreduce=mdist.allreduce_sum_), steps)
-        rel_a = [float((a - b).norm() / b.norm()) for a, b in zip(net_a.level_tensors(), ref_params)]
-        out["point_sharded_allreduce"] = {
-            "ms_per_step": ms_a, "points_per_s": NCD_POINTS / (ms_a * 1e-3), "speedup_vs_1gpu": ms1 / ms_a,
-            "collective": "ncclAllReduce(sum, f32) of both grid levels' dense gradients",
-            "collective_bytes_per_step": sum(p.numel() * 4 for p in net_a.level_tensors()),
-            "param_rel_err_vs_1gpu": rel_a, "loss_rel_err_vs_1gpu": abs(float(terms_a[3]) - float(terms1[3])) / abs(float(terms1[3]))}
-        del tr_a, net_a, smi, sgt
-        torch.cuda.empty_cache()
+        if "allreduce" in modes:
+            b0, b1 = mdist.shard_points(NCD_POINTS, rank, world)
+            smi = {k: v[:, b0:b1].contiguous() for k, v in dmi.items()}
+            sgt = {k: v[:, b0:b1].contiguous() for k, v in dgt.items()}
+            net_a = build_ncd_model(device, poses)
+            tr_a = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint"}, net_a, MisoLossMapping(**NCD_LOSS), None,
+                               device=device)
+            ms_a, terms_a = timed(lambda: tr_a.train_step(smi, sgt, n_total=NCD_POINTS, allreduce=mdist.allreduce_sum_), steps)
+            rel_a = [float((a - b).norm() / b.norm()) for a, b in zip(net_a.level_tensors(), ref_params)]
+            out["point_sharded_allreduce"] = {
+                "ms_per_step": ms_a, "points_per_s": NCD_POINTS / (ms_a * 1e-3), "speedup_vs_1gpu": ms1 / ms_a,
+                "collective": "ncclAllReduce(sum, f32) of both grid levels' dense gradients",
+                "collective_bytes_per_step": sum(p.numel() * 4 for p in net_a.level_tensors()),
+                "param_rel_err_vs_1gpu": rel_a, "loss_rel_err_vs_1gpu": abs(float(terms_a[3]) - float(terms1[3])) / abs(float(terms1[3]))}
+            del tr_a, net_a, smi, sgt
+            torch.cuda.empty_cache()
         # ---- (b) z-slabs of the fine level, one-plane halos ----
         net_b = build_ncd_model(device, poses)
-        fit = SlabShardedFit(net_b, MisoLossMapping(**NCD_LOSS), lr=1e-3)
+        fit = SlabShardedFit(net_b, MisoLossMapping(**NCD_LOSS), lr=1e-3, halo=halo)
         bounds = fit.calibrate(dmi)
         ms_b_eager, _ = timed(lambda: fit.step(dmi, dgt), 0)        # warm-up steps only, eager
         replay = fit.graphed_step(dmi, dgt)                            # + 1 eager step (the capture itself runs nothing)
@@ -681,8 +683,11 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0):
             "ms_per_step": ms_b, "points_per_s": NCD_POINTS / (ms_b * 1e-3), "speedup_vs_1gpu": ms1 / ms_b,
             "cuda_graph": True, "slab_axis": slab_axis, "slab_bounds_planes": bounds, "max_samples_per_rank": int(cnt.item()),
             "load_imbalance": float(cnt.item()) * world / NCD_POINTS,
-            "collective": "P2P halo: one z-plane of fine-level gradients up + one plane of parameters down per neighbour, "
-                          "ncclAllReduce of the coarse level's gradient and the 4 loss terms",
+            "halo": "p2p" if fit.p2p else "nccl",
+            "collective": ("boundary-plane Adam over NVLink peer memory (miso_adam_step_halo: peer loads of the neighbour's "
+                           "gradient plane, peer stores of the new parameter plane), interior Adam on a second stream, "
+                           if fit.p2p else "NCCL P2P halo: one plane of fine-level gradients up + one plane of parameters down "
+                           "per neighbour, ") + "ncclAllReduce of the coarse level's gradient and of the 4 loss terms",
             "collective_bytes_per_step": 2 * fit.plane_elems * 4 + net_b.level_tensors()[0].numel() * 4 + 16,
             "param_rel_err_vs_1gpu": rel_b, "loss_rel_err_vs_1gpu": abs(float(terms_b[3]) - float(terms1[3])) / abs(float(terms1[3]))}
         assert max(rel_a) < 1e-4 and max(rel_b) < 1e-4, (rel_a, rel_b)

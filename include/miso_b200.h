@@ -350,6 +350,21 @@ int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched
                        float beta2, float eps, int32_t* step_counter, float* scalars, const float* gate,
                        int32_t zero_grad, miso_stream_t stream);
 
+/* Adam on one boundary plane of a slab-sharded level, fused with both halo exchanges over NVLink peer memory
+ * (miso_b200/sharded_fit.py; the multi-GPU form of trainer.py:209-217 + 422-437 for one large grid): gradient =
+ * g + g_peer (the same plane of the lower neighbour's gradient buffer, read with peer loads and cleared in place), the
+ * new parameters are written to p and to p_peer (the neighbour's copy of the plane, read by its next step).  g_peer /
+ * p_peer: pointers obtained from miso_ipc_import (or NULL at the ends of the chain).  Device-side step counter as in
+ * miso_adam_step_dev.  The caller orders the ranks with the collectives around the call. */
+int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64_t n, float* g_peer, float* p_peer, float lr,
+                        float beta1, float beta2, float eps, int32_t* step_counter, float* scalars, miso_stream_t stream);
+
+/* Same-node peer mapping of a device allocation (CUDA IPC).  export: handle (64 bytes) of the allocation `ptr` lives
+ * in + ptr's offset from its base, to be sent to the neighbour's process; import: maps it for the CURRENT device
+ * (peer access enabled lazily) and returns the pointer; mappings are cached per (device, handle). */
+int miso_ipc_export(const void* ptr, unsigned char handle[64], int64_t* offset);
+int miso_ipc_import(const unsigned char handle[64], int64_t offset, void** ptr);
+
 /* ------------------------------------------------------------------------------------------
  * 5. Self-test of the tensor-core building block of the fused decoder (tcgen05.mma kind::tf32 with the
  *    3xTF32 split, activations in TMEM, weights in shared memory): D (M,64) = A (M,64) * W^T

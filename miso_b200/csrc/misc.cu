@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace miso {
@@ -278,6 +281,18 @@ __global__ void __launch_bounds__(kThreads)
       const int plane = (int)fz;
       keep |= (plane >= z_begin && plane < z_end) ? (1u << k) : 0u;
     }
+    // the kept samples' targets are fetched now, so that their latency overlaps the prefix sum and the chunk's atomic
+    float g_sdf[kSelPer], g_sign[kSelPer], g_w[kSelPer];
+    uint8_t g_valid[kSelPer];
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+      g_sdf[k] = g_sign[k] = 0.f, g_w[k] = 1.f, g_valid[k] = 0;
+      if ((keep >> k) & 1u) {
+        const int64_t n = n0 + k;
+        g_sdf[k] = sdf[n], g_valid[k] = valid[n], g_sign[k] = sign[n];
+        if (weights) g_w[k] = weights[n];
+      }
+    }
     // exclusive prefix of the per-thread keep counts: inside the warp by shuffles, across warps through shared memory
     const int mine = __popc(keep);
     int incl = mine;
@@ -303,13 +318,12 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int k = 0; k < kSelPer; ++k) {
       if (!((keep >> k) & 1u)) continue;
-      const int64_t n = n0 + k;
       x_out[3 * o] = px[k][0], x_out[3 * o + 1] = px[k][1], x_out[3 * o + 2] = px[k][2];
       if (ids_out) ids_out[o] = id[k];
-      sdf_out[o] = sdf[n];
-      valid_out[o] = valid[n];
-      sign_out[o] = sign[n];
-      if (weights_out) weights_out[o] = weights ? weights[n] : 1.f;
+      sdf_out[o] = g_sdf[k];
+      valid_out[o] = g_valid[k];
+      sign_out[o] = g_sign[k];
+      if (weights_out) weights_out[o] = g_w[k];
       ++o;
     }
     __syncthreads();
@@ -394,6 +408,119 @@ extern "C" int miso_adam_step(float* p, float* g, float* m, float* v, int64_t n,
   return check_launch("adam_step");
 }
 
+// Adam on ONE boundary plane of a slab-sharded level (miso_b200/sharded_fit.py), fused with both halo exchanges over
+// NVLink peer memory: the plane's gradient is g + g_peer, where g_peer is the SAME plane in the lower neighbour's
+// gradient buffer (its samples' upper corners land there) read with peer loads and cleared in place; the updated
+// parameters are stored locally and into the neighbour's copy of the plane (p_peer, peer stores), which its next step
+// reads.  Replaces isend/irecv of the gradient plane + add + Adam + isend/irecv of the parameter plane.  Ordering
+// between the ranks comes from the collectives around it (see SlabShardedFit._exchange_and_update).
+__global__ void __launch_bounds__(kThreads)
+    adam_halo_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     float* __restrict__ g_peer, float* __restrict__ p_peer, int64_t n4, float lr, float b1, float b2,
+                     float eps, AdamDev dev) {
+  __shared__ float sh_dev[3];
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  adam_dev_begin(dev, lr, b1, b2, step_size, bc2_sqrt, sh_dev);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    if (g_peer) {
+      const float4 gp = reinterpret_cast<const float4*>(g_peer)[i];
+      gv.x += gp.x, gv.y += gp.y, gv.z += gp.z, gv.w += gp.w;
+      if (gp.x != 0.f || gp.y != 0.f || gp.z != 0.f || gp.w != 0.f) reinterpret_cast<float4*>(g_peer)[i] = zero4;
+    }
+    const float4 mv = reinterpret_cast<float4*>(m)[i];
+    const float4 vv = reinterpret_cast<float4*>(v)[i];
+    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f && mv.x == 0.f && mv.y == 0.f && mv.z == 0.f &&
+        mv.w == 0.f && vv.x == 0.f && vv.y == 0.f && vv.z == 0.f && vv.w == 0.f)
+      continue;   // never touched: exactly-zero update, the neighbour's copy is already equal
+    const float4 pv = reinterpret_cast<float4*>(p)[i];
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w},
+          va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ma[e] = ma[e] + (ga[e] - ma[e]) * (1.f - b1);
+      va[e] = va[e] * b2 + (1.f - b2) * ga[e] * ga[e];
+      const float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] = pa[e] - step_size * (ma[e] / denom);
+    }
+    const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(p)[i] = pn;
+    if (p_peer) reinterpret_cast<float4*>(p_peer)[i] = pn;
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    reinterpret_cast<float4*>(g)[i] = zero4;
+  }
+  adam_dev_end(dev, false);
+}
+
+extern "C" int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64_t n, float* g_peer, float* p_peer,
+                                   float lr, float beta1, float beta2, float eps, int32_t* step_counter, float* scalars,
+                                   miso_stream_t stream) {
+  MISO_REQUIRE(p && g && m && v && step_counter && scalars, "adam_step_halo: null tensor");
+  MISO_REQUIRE(n > 0 && n % 4 == 0, "adam_step_halo: n must be a positive multiple of 4");
+  MISO_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g_peer | (uintptr_t)p_peer) % 16) == 0,
+               "adam_step_halo: tensors not 16-byte aligned");
+  const AdamDev dev{step_counter, nullptr, reinterpret_cast<unsigned*>(scalars)};
+  adam_halo_kernel<<<grid_for(n / 4, kThreads, sm_count() * 4), kThreads, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, g_peer, p_peer, n / 4, lr, beta1, beta2, eps, dev);
+  return check_launch("adam_step_halo");
+}
+
+// Same-node peer mapping of a device allocation (CUDA IPC): export on the owner, import in the neighbour's process.
+// The handle names the whole cudaMalloc allocation `ptr` lives in; `offset` is ptr's distance from its base.
+extern "C" int miso_ipc_export(const void* ptr, unsigned char handle[64], int64_t* offset) {
+  MISO_REQUIRE(ptr && handle && offset, "ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (range_fn)f;
+  }();
+  MISO_REQUIRE(get_range, "ipc_export: cuMemGetAddressRange not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  MISO_REQUIRE(get_range(&base, &size, (unsigned long long)(uintptr_t)ptr) == 0, "ipc_export: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+  MISO_REQUIRE(e == cudaSuccess, "ipc_export: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  memcpy(handle, &h, 64);
+  *offset = (int64_t)((unsigned long long)(uintptr_t)ptr - base);
+  return MISO_OK;
+}
+
+extern "C" int miso_ipc_import(const unsigned char handle[64], int64_t offset, void** ptr) {
+  MISO_REQUIRE(handle && ptr && offset >= 0, "ipc_import: bad argument");
+  // an allocation can be opened once per process and device: cache the mappings
+  struct Entry { unsigned char h[64]; int dev; void* base; };
+  static std::vector<Entry> cache;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& en : cache)
+    if (en.dev == dev && !memcmp(en.h, handle, 64)) {
+      *ptr = (char*)en.base + offset;
+      return MISO_OK;
+    }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* base = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  MISO_REQUIRE(e == cudaSuccess, "ipc_import: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  Entry en;
+  memcpy(en.h, handle, 64);
+  en.dev = dev, en.base = base;
+  cache.push_back(en);
+  *ptr = (char*)base + offset;
+  return MISO_OK;
+}
+
 // step = ++(*counter); scalars = {lr / (1 - b1^step), sqrt(1 - b2^step)} in float64, exactly the host formula above
 extern "C" int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched, int64_t n, float lr,
                                   float beta1, float beta2, float eps, int32_t* step_counter, float* scalars,
@@ -457,7 +584,13 @@ extern "C" int miso_slab_select(const miso_frames_t* frames, const float* x, int
   cudaMemsetAsync(count, 0, sizeof(int32_t), s);
   if (N == 0) return check_launch("slab_select(memset)");
   MISO_REQUIRE(N < ((int64_t)1 << 31), "slab_select: N must fit int32");
-  const int blocks = grid_for((N + kThreads * kSelPer - 1) / (kThreads * kSelPer), 1, sm_count() * 8);
+  // one full wave of resident blocks (the kernel is latency-bound: a partial second wave costs a whole extra trip)
+  static int per_sm = 0;
+  if (!per_sm) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slab_select_kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int blocks = grid_for((N + kThreads * kSelPer - 1) / (kThreads * kSelPer), 1, sm_count() * per_sm);
   slab_select_kernel<<<blocks, kThreads, 0, s>>>(x, have_frames ? frames->ids : nullptr, have_frames ? frames->R : nullptr,
                                                  have_frames ? frames->t : nullptr, have_frames ? frames->num_frames : 0, N,
                                                  zmin, zmax, Z, axis, z_begin, z_end, gt_sdf, gt_valid, gt_sign, weights, x_out,

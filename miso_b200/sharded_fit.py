@@ -99,7 +99,12 @@ class SlabShardedFit:
     """Adam fit of one GridNet on a replicated batch, the largest level cut into z-slabs over the ranks."""
 
     def __init__(self, model, loss: MisoLossMapping, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 rank: Optional[int] = None, world: Optional[int] = None, bounds: Optional[Sequence[int]] = None):
+                 rank: Optional[int] = None, world: Optional[int] = None, bounds: Optional[Sequence[int]] = None,
+                 halo: str = "auto"):
+        """`halo`: "p2p" -- the boundary plane's Adam reads the neighbour's gradient plane and writes the neighbour's
+        parameter plane directly over NVLink peer memory (one node, CUDA IPC; miso_adam_step_halo), the interior
+        planes' Adam overlaps it on a second stream; "nccl" -- batched isend/irecv of the two planes (any topology);
+        "auto" -- p2p when a NCCL process group spans more than one rank."""
         r, w = mdist.world()
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
@@ -109,6 +114,13 @@ class SlabShardedFit:
         f = feats[self.slab_level]
         if f.stride(1) != 1:
             raise RuntimeError("SlabShardedFit needs channels innermost (channels_last_3d or a permutation of it)")
+        if halo not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"halo must be 'auto', 'p2p' or 'nccl', not {halo!r}")
+        live = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.p2p = halo == "p2p" or (halo == "auto" and live and f.is_cuda and dist.get_backend() == "nccl")
+        if self.p2p and not (live and self.world == dist.get_world_size() and self.rank == dist.get_rank()):
+            raise RuntimeError("halo='p2p' needs an initialised process group whose ranks are the slab owners")
+        self._peer, self._side = None, None
         self.axis = 2                        # slab axis in (x, y, z) numbering; z is slowest in channels_last_3d
         self._configure_axis(2 if f.stride(2) > f.stride(3) else 1)
         self.bounds = list(bounds) if bounds is not None else [round(self.Z * k / self.world) for k in range(self.world + 1)]
@@ -145,8 +157,16 @@ class SlabShardedFit:
 
     def _set_slab(self):
         self.zb, self.ze = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        n = (self.ze - self.zb) * self.plane_elems
         dev = self.model.level_tensors()[self.slab_level].device
+        self._peer = None
+        # p2p halos: the first owned plane (it also receives the lower neighbour's gradient) has its own Adam launch
+        self.zi = self.zb + 1 if (self.p2p and self.rank > 0) else self.zb
+        if self.zi != self.zb:
+            self.b_exp_avg = torch.zeros(self.plane_elems, dtype=torch.float32, device=dev)
+            self.b_exp_avg_sq = torch.zeros(self.plane_elems, dtype=torch.float32, device=dev)
+            self.b_step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.b_scalars = torch.zeros(3, dtype=torch.float32, device=dev)
+        n = (self.ze - self.zi) * self.plane_elems
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         # "ever touched" bitmap of the slab (one bit per 4-float voxel): never-touched voxels cost one gradient read
@@ -240,12 +260,79 @@ class SlabShardedFit:
         self._exchange_and_update(feats, grads, terms, b)
         return terms
 
+    def _adam_interior(self, feats, grads):
+        sl = self.slab_level
+        n = (self.ze - self.zi) * self.plane_elems
+        if n <= 0:
+            return
+        off = self.zi * self.plane_elems * 4
+        dev = feats[sl].device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().miso_adam_step_dev(
+                feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), self.touched.data_ptr(), n, self.lr, float(self.betas[0]),
+                float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), None, 1,
+                _lib.stream_ptr(dev)), "adam_step")
+
+    def _open_peers(self, feats, grads):
+        """Map the lower neighbour's gradient and parameter buffers of the slab level into this process (CUDA IPC).
+        Collective (all_gather_object): every rank calls it at the same point, outside any graph capture."""
+        lib, sl = _lib.load(), self.slab_level
+        mine = []
+        for t in (grads[sl], feats[sl]):
+            h, off = (C.c_ubyte * 64)(), C.c_int64(0)
+            _lib.check(lib.miso_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
+            mine.append((bytes(h), int(off.value)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        self._peer = {"key": (grads[sl].data_ptr(), feats[sl].data_ptr()), "g": None, "p": None}
+        if self.rank > 0:
+            ptrs = []
+            with torch.cuda.device(feats[sl].device):
+                for hb, off in everyone[self.rank - 1]:
+                    out = C.c_void_p()
+                    _lib.check(lib.miso_ipc_import((C.c_ubyte * 64).from_buffer_copy(hb), off, C.byref(out)), "ipc_import")
+                    ptrs.append(int(out.value))
+            plane = self.zb * self.plane_elems * 4        # my first plane == the neighbour's halo plane `ze`
+            self._peer["g"], self._peer["p"] = ptrs[0] + plane, ptrs[1] + plane
+        dist.barrier()
+
     def _exchange_and_update(self, feats, grads, terms, b):
         lib = _lib.load()
         sl, r, W = self.slab_level, self.rank, self.world
+        coarse = [gr for l, gr in enumerate(grads) if l != sl and gr is not None]
+        if W > 1 and self.p2p:
+            dev = feats[sl].device
+            if self._peer is None or self._peer["key"] != (grads[sl].data_ptr(), feats[sl].data_ptr()):
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("SlabShardedFit: run one eager step before capturing (peer buffers are mapped then)")
+                self._open_peers(feats, grads)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            # (1) every rank's step kernel is complete once this all_reduce returns: the neighbour's halo plane is final
+            mdist.allreduce_sum_(coarse)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._adam_interior(feats, grads)          # touches planes [zi, ze) only: overlaps the halo work
+            self.other.step()
+            if r > 0:
+                off = self.zb * self.plane_elems * 4
+                with torch.cuda.device(dev):
+                    _lib.check(lib.miso_adam_step_halo(
+                        feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.b_exp_avg.data_ptr(),
+                        self.b_exp_avg_sq.data_ptr(), self.plane_elems, self._peer["g"], self._peer["p"], self.lr,
+                        float(self.betas[0]), float(self.betas[1]), self.eps, self.b_step_dev.data_ptr(),
+                        self.b_scalars.data_ptr(), _lib.stream_ptr(dev)), "adam_step_halo")
+            main.wait_stream(self._side)
+            # (2) ... and every rank's Adam is complete once this one returns: my halo plane `ze` holds the upper
+            # neighbour's new parameters and my gradient plane `ze` has been consumed (and cleared) by it
+            mdist.allreduce_sum_([terms])
+            self.step_count += 1
+            return
         g, p = self._flat(grads[sl]), self._flat(feats[sl])
         if W > 1:
-            mdist.allreduce_sum_([gr for l, gr in enumerate(grads) if l != sl and gr is not None] + [terms])
+            mdist.allreduce_sum_(coarse + [terms])
             # gradient halo: my samples also wrote plane `ze`, which rank r+1 owns
             exchange_halo_planes(g[self.ze] if self.ze < self.Z else None, b["halo"] if r > 0 else None, r, W)
             if r > 0:
@@ -254,22 +341,14 @@ class SlabShardedFit:
                 g[self.ze].zero_()
         self.other.step()
         self.step_count += 1
-        n = (self.ze - self.zb) * self.plane_elems
-        off = self.zb * self.plane_elems * 4
-        dev = feats[sl].device
-        with torch.cuda.device(dev):
-            _lib.check(lib.miso_adam_step_dev(
-                feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, self.exp_avg.data_ptr(),
-                self.exp_avg_sq.data_ptr(), self.touched.data_ptr(), n, self.lr, float(self.betas[0]),
-                float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), None, 1,
-                _lib.stream_ptr(dev)), "adam_step")
+        self._adam_interior(feats, grads)
         if W > 1:
             # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)
             exchange_halo_planes_down(p[self.zb] if r > 0 else None, p[self.ze] if self.ze < self.Z else None, r, W)
 
     def graphed_step(self, model_input: dict, gt: dict):
         """Capture `step` on these (device-resident, fixed-address) batch tensors into a CUDA graph -- slab selection,
-        fused step, the NCCL halo exchanges / all_reduce and both Adam sweeps -- after one eager step on a side stream
+        fused step, the all_reduces, the halo exchange (peer-memory Adam or NCCL P2P) and the Adam sweeps -- after one eager step on a side stream
         (module loading, NCCL channel setup; it counts as a training step).  Returns `replay() -> loss terms`: one
         graph launch per step, which matters here because a step is ~15 short launches and collectives."""
         cur = torch.cuda.current_stream()
