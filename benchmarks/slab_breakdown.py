@@ -35,42 +35,8 @@ def main():
         e.record()
         marks.append((name, e))
 
-    # wrap the phases
+    fit.mark = mark      # SlabShardedFit reports its phase boundaries
     lib = _lib.load()
-    orig_select, orig_step_raw = lib.miso_slab_select, sf.mapping_step_raw
-    orig_xchg = fit._exchange_and_update
-
-    def step_raw(*a, **k):
-        mark("select_done")
-        out = orig_step_raw(*a, **k)
-        mark("kernel_done")
-        return out
-    sf.mapping_step_raw = step_raw
-
-    def xchg(feats, grads, terms, b):
-        sl, r, W = fit.slab_level, fit.rank, fit.world
-        g, p = fit._flat(grads[sl]), fit._flat(feats[sl])
-        if W > 1:
-            mdist.allreduce_sum_([gr for l, gr in enumerate(grads) if l != sl and gr is not None] + [terms])
-            mark("allreduce_done")
-            sf.exchange_halo_planes(g[fit.ze] if fit.ze < fit.Z else None, b["halo"] if r > 0 else None, r, W)
-            if r > 0:
-                g[fit.zb].add_(b["halo"])
-            if fit.ze < fit.Z:
-                g[fit.ze].zero_()
-            mark("grad_halo_done")
-        fit.other.step()
-        mark("adam_other_done")
-        n = (fit.ze - fit.zb) * fit.plane_elems
-        off = fit.zb * fit.plane_elems * 4
-        _lib.check(lib.miso_adam_step_dev(feats[sl].data_ptr() + off, grads[sl].data_ptr() + off, fit.exp_avg.data_ptr(),
-                                          fit.exp_avg_sq.data_ptr(), fit.touched.data_ptr(), n, fit.lr, 0.9, 0.999, fit.eps,
-                                          fit.step_dev.data_ptr(), fit.scalars.data_ptr(), None, 1, _lib.stream_ptr(dev)), "adam_step")
-        mark("adam_slab_done")
-        if W > 1:
-            sf.exchange_halo_planes_down(p[fit.zb] if r > 0 else None, p[fit.ze] if fit.ze < fit.Z else None, r, W)
-            mark("param_halo_done")
-    fit._exchange_and_update = xchg
     acc = {}
     for it in range(12):
         marks.clear()
@@ -109,8 +75,8 @@ def main():
         b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(), b["count"].data_ptr(),
         _lib.stream_ptr(dev)))
     feats = net.level_tensors()
-    n_sl = (fit.ze - fit.zb) * fit.plane_elems
-    off = fit.zb * fit.plane_elems * 4
+    n_sl = (fit.ze - fit.zi) * fit.plane_elems
+    off = fit.zi * fit.plane_elems * 4
     acc["adam_slab_only_zero_grad"] = t_loop(lambda: lib.miso_adam_step_dev(
         feats[1].data_ptr() + off, feats[1].grad.data_ptr() + off, fit.exp_avg.data_ptr(), fit.exp_avg_sq.data_ptr(),
         fit.touched.data_ptr(), n_sl, fit.lr, 0.9, 0.999, fit.eps, fit.step_dev.data_ptr(), fit.scalars.data_ptr(), None, 1,

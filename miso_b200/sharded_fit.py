@@ -121,6 +121,7 @@ class SlabShardedFit:
         if self.p2p and not (live and self.world == dist.get_world_size() and self.rank == dist.get_rank()):
             raise RuntimeError("halo='p2p' needs an initialised process group whose ranks are the slab owners")
         self._peer, self._side = None, None
+        self.mark = None     # optional callable(name): phase boundaries of a step (benchmarks/slab_breakdown.py)
         self.axis = 2                        # slab axis in (x, y, z) numbering; z is slowest in channels_last_3d
         self._configure_axis(2 if f.stride(2) > f.stride(3) else 1)
         self.bounds = list(bounds) if bounds is not None else [round(self.Z * k / self.world) for k in range(self.world + 1)]
@@ -182,11 +183,13 @@ class SlabShardedFit:
 
     def calibrate(self, model_input: dict, voxel_cost: float = 1.0 / 56.0, axes=None):
         """Choose slab boundaries that balance the per-step work of this batch over the ranks (identical on every rank:
-        the batch is replicated): a plane costs its sample count (fused step, ~0.19 ns per sample on B200) plus
-        `voxel_cost` sample-equivalents per parameter it holds (the Adam sweep streams the slab's gradient and, for
-        touched voxels, p / m / v: ~0.0034 ns per float measured on the NCD quad grid).  Both candidate slab axes
-        (z, y) are tried and the one whose heaviest slab is lightest wins; the level is re-laid with that axis slowest.
-        Resets the slab's Adam moments; call before the first step."""
+        the batch is replicated).  A step is two phases separated by a collective -- the fused step kernel (cost ~ the
+        rank's sample count, ~0.2 ns per sample on B200) and the Adam sweep of the slab (`voxel_cost` sample-equivalents
+        per parameter: it streams the slab's gradient and, for touched voxels, p / m / v, ~0.0034 ns per float on the NCD
+        quad grid) -- so the step costs  max_r samples_r + voxel_cost * max_r params_r.  Candidates: both slab axes
+        (z, y) x cuts that equalise `samples + w * voxel_cost * params` per slab for a few weights w; the candidate with
+        the smallest modelled step wins, the level is re-laid with that axis slowest.  Resets the slab's Adam moments;
+        call before the first step."""
         coords = model_input["coords_frame"][0]
         ids = model_input["sample_frame_ids"][0, :, 0]
         R, t, _ = self.loss.frame_table(self.model)
@@ -198,13 +201,15 @@ class SlabShardedFit:
                 continue
             lo, hi = self.model._bound_host[2 * axis], self.model._bound_host[2 * axis + 1]
             w = torch.einsum("nj,nj->n", R[ids][:, axis, :], coords) + t[ids][:, axis, 0]
-            cost = torch.bincount(plane_of_points(w, lo, hi, n_planes), minlength=n_planes).double() \
-                + voxel_cost * (f.numel() // n_planes)
-            bounds = slab_bounds_from_histogram(cost, self.world)
-            cum = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(cost.cpu(), 0)])
-            worst = max(float(cum[b1] - cum[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:]))
-            if best is None or worst < 0.98 * best[0]:     # z (the native layout) unless y is clearly better
-                best = (worst, axis, bounds)
+            samples = torch.bincount(plane_of_points(w, lo, hi, n_planes), minlength=n_planes).double().cpu()
+            per_plane = f.numel() // n_planes
+            cum = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(samples, 0)])
+            for weight in (1.0, 0.5, 0.25, 0.0):
+                bounds = slab_bounds_from_histogram(samples + weight * voxel_cost * per_plane, self.world)
+                step = max(float(cum[b1] - cum[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:])) \
+                    + voxel_cost * per_plane * max(b1 - b0 for b0, b1 in zip(bounds[:-1], bounds[1:]))
+                if best is None or step < 0.98 * best[0]:     # z (the native layout) unless y is clearly better
+                    best = (step, axis, bounds)
         _, axis, self.bounds = best
         if axis != self.axis:
             self._relayout(axis)
@@ -245,6 +250,7 @@ class SlabShardedFit:
                 sdf.data_ptr(), valid.data_ptr(), sign.data_ptr(), w.data_ptr(), b["x"].data_ptr(), b["ids"].data_ptr(),
                 b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(),
                 b["count"].data_ptr(), stream), "slab_select")
+        self._m("select")
         feats = m.level_tensors()
         grads = []
         for f in feats:
@@ -257,8 +263,13 @@ class SlabShardedFit:
         # the |gt| < eik_trunc count runs over the FULL batch inside mapping_step_raw when gt_sdf_count is given
         terms = mapping_step_raw(feats, grads, m.fused_spec(), own_frames, b["x"], b["sdf"], b["valid"], b["sign"], b["w"],
                                  n_total=N, n_device=b["count"], count_on=sdf, **cfg)
+        self._m("step_kernel")
         self._exchange_and_update(feats, grads, terms, b)
         return terms
+
+    def _m(self, name):
+        if self.mark is not None:
+            self.mark(name)
 
     def _adam_interior(self, feats, grads):
         sl = self.slab_level
@@ -312,6 +323,7 @@ class SlabShardedFit:
             main = torch.cuda.current_stream(dev)
             # (1) every rank's step kernel is complete once this all_reduce returns: the neighbour's halo plane is final
             mdist.allreduce_sum_(coarse)
+            self._m("allreduce_coarse")
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._adam_interior(feats, grads)          # touches planes [zi, ze) only: overlaps the halo work
@@ -325,9 +337,11 @@ class SlabShardedFit:
                         float(self.betas[0]), float(self.betas[1]), self.eps, self.b_step_dev.data_ptr(),
                         self.b_scalars.data_ptr(), _lib.stream_ptr(dev)), "adam_step_halo")
             main.wait_stream(self._side)
+            self._m("adam_interior|coarse+halo")
             # (2) ... and every rank's Adam is complete once this one returns: my halo plane `ze` holds the upper
             # neighbour's new parameters and my gradient plane `ze` has been consumed (and cleared) by it
             mdist.allreduce_sum_([terms])
+            self._m("allreduce_terms")
             self.step_count += 1
             return
         g, p = self._flat(grads[sl]), self._flat(feats[sl])
