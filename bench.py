@@ -661,7 +661,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0, modes=("allreduce", 
         fit = SlabShardedFit(net_b, MisoLossMapping(**NCD_LOSS), lr=1e-3, halo=halo)
         bounds = fit.calibrate(dmi)
         ms_b_eager, _ = timed(lambda: fit.step(dmi, dgt), 0)        # warm-up steps only, eager
-        replay = fit.graphed_step(dmi, dgt)                            # + 1 eager step (the capture itself runs nothing)
+        replay = fit.graphed_step(dmi, dgt, prefetch_same=True)       # + 1 eager step (the captures themselves run nothing)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_b = steps - 1
         torch.cuda.synchronize()
@@ -684,6 +684,7 @@ def bench_ncd(device, steps=100, warmup=5, world=1, rank=0, modes=("allreduce", 
             "cuda_graph": True, "slab_axis": slab_axis, "slab_bounds_planes": bounds, "max_samples_per_rank": int(cnt.item()),
             "load_imbalance": float(cnt.item()) * world / NCD_POINTS,
             "halo": "p2p" if fit.p2p else "nccl",
+            "selection": "the next step's slab selection runs on a second stream behind the step kernel (two compaction buffer sets)",
             "collective": ("boundary-plane Adam over NVLink peer memory (miso_adam_step_halo: peer loads of the neighbour's "
                            "gradient plane, peer stores of the new parameter plane), interior Adam on a second stream, "
                            if fit.p2p else "NCCL P2P halo: one plane of fine-level gradients up + one plane of parameters down "

@@ -359,6 +359,14 @@ int miso_adam_step_dev(float* p, float* g, float* m, float* v, uint32_t* touched
 int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64_t n, float* g_peer, float* p_peer, float lr,
                         float beta1, float beta2, float eps, int32_t* step_counter, float* scalars, miso_stream_t stream);
 
+/* Neighbour-to-neighbour ordering over peer memory, no collective: miso_peer_signal adds 1 to a counter that lives in
+ * the neighbour's memory (pointer from miso_ipc_import) once everything enqueued before it on `stream` is complete;
+ * miso_peer_wait(sync) holds `stream` until sync[0] (the counter the peer bumps) has reached sync[1], then increments
+ * sync[1] (the number of waits so far).  sync: 4 device uint32 {counter, waits, error, -}, zero-initialised; the wait
+ * gives up after ~4 s and sets sync[2] instead of hanging the device. */
+int miso_peer_signal(uint32_t* flag_peer, miso_stream_t stream);
+int miso_peer_wait(uint32_t* sync, miso_stream_t stream);
+
 /* Same-node peer mapping of a device allocation (CUDA IPC).  export: handle (64 bytes) of the allocation `ptr` lives
  * in + ptr's offset from its base, to be sent to the neighbour's process; import: maps it for the CURRENT device
  * (peer access enabled lazily) and returns the pointer; mappings are cached per (device, handle). */

@@ -112,6 +112,8 @@ _SIGNATURES = {
                                          C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "miso_adam_step_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "miso_peer_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "miso_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "miso_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "miso_ipc_import": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "miso_adam_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,

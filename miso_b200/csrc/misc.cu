@@ -468,6 +468,38 @@ extern "C" int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64
   return check_launch("adam_step_halo");
 }
 
+// Neighbour-to-neighbour ordering without a collective (slab-sharded fit): after its boundary-plane Adam a rank bumps a
+// counter in the LOWER neighbour's memory; before its next step kernel that neighbour waits until the counter has reached
+// the number of steps it has taken.  sync = {flag (written by the peer), expected, error, -}.  The wait gives up after
+// ~4 s (error word set, checked by the host) instead of hanging the GPU.
+__global__ void peer_signal_kernel(unsigned* flag_peer) {
+  __threadfence_system();
+  atomicAdd_system(flag_peer, 1u);
+}
+__global__ void peer_wait_kernel(unsigned* sync) {
+  const unsigned want = sync[1];
+  sync[1] = want + 1u;
+  const long long t0 = clock64();
+  while (*reinterpret_cast<volatile unsigned*>(sync) < want) {
+    if (clock64() - t0 > 8000000000LL) {
+      sync[2] = 1u;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+extern "C" int miso_peer_signal(uint32_t* flag_peer, miso_stream_t stream) {
+  MISO_REQUIRE(flag_peer, "peer_signal: null flag");
+  peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag_peer);
+  return check_launch("peer_signal");
+}
+extern "C" int miso_peer_wait(uint32_t* sync, miso_stream_t stream) {
+  MISO_REQUIRE(sync, "peer_wait: null sync words");
+  peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sync);
+  return check_launch("peer_wait");
+}
+
 // Same-node peer mapping of a device allocation (CUDA IPC): export on the owner, import in the neighbour's process.
 // The handle names the whole cudaMalloc allocation `ptr` lives in; `offset` is ptr's distance from its base.
 extern "C" int miso_ipc_export(const void* ptr, unsigned char handle[64], int64_t* offset) {

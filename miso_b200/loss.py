@@ -99,7 +99,8 @@ class MappingWorkspace:
 
 def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, weights, *, loss_type, weight_sdf,
                      weight_fs, weight_eik, trunc_dist, eik_trunc_dist, eik_on, grad_scale=1.0, sdf_out=None,
-                     n_total=0, count_allreduce=None, fd_eps=None, n_device=None, count_on=None, dec_grads=None):
+                     n_total=0, count_allreduce=None, fd_eps=None, n_device=None, count_on=None, dec_grads=None,
+                     loss_out=None):
     """Launch the fused mapping step.  Returns a (4,) float tensor [sdf, fs, eik, total] (unweighted
     terms, weighted total).  Gradients are ACCUMULATED into `grads` (None entries are skipped).
     `fd_eps` selects the finite-difference eikonal term (miso_mapping_step_fd) instead of the analytic one.
@@ -123,7 +124,8 @@ def mapping_step_raw(feats, grads, spec, frames, x, gt_sdf, gt_valid, gt_sign, w
     fld = _field.make_field(feats, spec.bound, grads, spec.ignore_mask)
     dec = spec.decoder.struct()
     fr = frames.struct() if frames is not None else None
-    loss_out = torch.empty(4, dtype=torch.float32, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(4, dtype=torch.float32, device=dev)
     stream = _lib.stream_ptr(dev)
     with torch.cuda.device(dev):
         if cfg.eik_mode == 1 and eik_trunc_dist is not None:

@@ -120,7 +120,9 @@ class SlabShardedFit:
         self.p2p = halo == "p2p" or (halo == "auto" and live and f.is_cuda and dist.get_backend() == "nccl")
         if self.p2p and not (live and self.world == dist.get_world_size() and self.rank == dist.get_rank()):
             raise RuntimeError("halo='p2p' needs an initialised process group whose ranks are the slab owners")
-        self._peer, self._side = None, None
+        self._peer, self._side, self._side2, self._flat_buf = None, None, None, None
+        self._sets, self._presel = None, None
+        self.sync = torch.zeros(4, dtype=torch.int32, device=f.device) if self.p2p else None
         self.mark = None     # optional callable(name): phase boundaries of a step (benchmarks/slab_breakdown.py)
         self.axis = 2                        # slab axis in (x, y, z) numbering; z is slowest in channels_last_3d
         self._configure_axis(2 if f.stride(2) > f.stride(3) else 1)
@@ -217,41 +219,78 @@ class SlabShardedFit:
         return self.bounds
 
     # ---- one step --------------------------------------------------------------------------------------
-    def _buffers(self, N, dev, need_w):
-        if self._bufs is None or self._bufs["N"] != N:
-            self._bufs = {"N": N, "x": torch.empty((N, 3), dtype=torch.float32, device=dev),
-                          "ids": torch.empty(N, dtype=torch.int64, device=dev),
-                          "sdf": torch.empty(N, dtype=torch.float32, device=dev),
-                          "valid": torch.empty(N, dtype=torch.uint8, device=dev),
-                          "sign": torch.empty(N, dtype=torch.float32, device=dev),
-                          "w": torch.empty(N, dtype=torch.float32, device=dev),
-                          "count": torch.zeros(1, dtype=torch.int32, device=dev),
-                          "halo": torch.empty(self.plane_elems, dtype=torch.float32, device=dev)}
-        return self._bufs
+    def _buffers(self, N, dev, need_w=True, which=0):
+        """Compaction targets of the slab selection; two sets, so the next batch can be selected while this one trains."""
+        if self._sets is None or self._sets[0]["N"] != N:
+            def make():
+                return {"N": N, "x": torch.empty((N, 3), dtype=torch.float32, device=dev),
+                        "ids": torch.empty(N, dtype=torch.int64, device=dev),
+                        "sdf": torch.empty(N, dtype=torch.float32, device=dev),
+                        "valid": torch.empty(N, dtype=torch.uint8, device=dev),
+                        "sign": torch.empty(N, dtype=torch.float32, device=dev),
+                        "w": torch.empty(N, dtype=torch.float32, device=dev),
+                        "count": torch.zeros(1, dtype=torch.int32, device=dev)}
+            self._sets = [make(), make()]
+            self._halo = torch.empty(self.plane_elems, dtype=torch.float32, device=dev)
+            self._presel = None
+        out = self._sets[which]
+        out["halo"] = self._halo
+        return out
 
-    def step(self, model_input: dict, gt: dict) -> torch.Tensor:
-        """One fit step on the (replicated, device-resident) batch.  Returns the GLOBAL (4,) loss terms
-        [sdf, fs, eik, total]; nothing is synchronised with the host."""
+    @staticmethod
+    def _batch_key(model_input, gt):
+        return tuple(v.data_ptr() for v in model_input.values()) + tuple(v.data_ptr() for v in gt.values())
+
+    def _select(self, model_input: dict, gt: dict, which: int):
+        """Enqueue the slab selection of a batch into buffer set `which` on the current stream."""
         lib, m, L = _lib.load(), self.model, self.loss
-        if not L._fused_ok(m) or (L.weight_eik > 0 and L.grad_method != "autograd"):
-            raise RuntimeError("SlabShardedFit runs the fused analytic step (fixed decoder, locked poses)")
         coords = _field._prep_x(model_input["coords_frame"][0])
         ids = model_input["sample_frame_ids"][0, :, 0]
         sdf, valid, sign = _flat_f32(gt["sdf"][0]), _flat_u8(gt["sdf_valid"][0]), _flat_f32(gt["sdf_signs"][0])
         w = _flat_f32(model_input["weights"][0])
         N, dev = coords.shape[0], coords.device
-        b = self._buffers(N, dev, True)
-        frames = L._frames(m, ids)
-        fr = frames.struct()
-        stream = _lib.stream_ptr(dev)
+        b = self._buffers(N, dev, True, which)
+        fr = L._frames(m, ids).struct()
         with torch.cuda.device(dev):
             _lib.check(lib.miso_slab_select(
                 C.byref(fr), coords.data_ptr(), N, float(self.zmin), float(self.zmax), self.Z, self.axis, self.zb, self.ze,
                 sdf.data_ptr(), valid.data_ptr(), sign.data_ptr(), w.data_ptr(), b["x"].data_ptr(), b["ids"].data_ptr(),
                 b["sdf"].data_ptr(), b["valid"].data_ptr(), b["sign"].data_ptr(), b["w"].data_ptr(),
-                b["count"].data_ptr(), stream), "slab_select")
+                b["count"].data_ptr(), _lib.stream_ptr(dev)), "slab_select")
+        return b
+
+    def step(self, model_input: dict, gt: dict, prefetch=None) -> torch.Tensor:
+        """One fit step on the (replicated, device-resident) batch.  Returns the GLOBAL (4,) loss terms
+        [sdf, fs, eik, total]; nothing is synchronised with the host.  `prefetch = (model_input, gt)` of the NEXT step:
+        its slab selection is enqueued on a second stream behind this step's kernel, where it overlaps the collectives
+        and the Adam sweeps; the next `step` call on those tensors then starts with the fused kernel."""
+        lib, m, L = _lib.load(), self.model, self.loss
+        if not L._fused_ok(m) or (L.weight_eik > 0 and L.grad_method != "autograd"):
+            raise RuntimeError("SlabShardedFit runs the fused analytic step (fixed decoder, locked poses)")
+        ids = model_input["sample_frame_ids"][0, :, 0]
+        sdf = _flat_f32(gt["sdf"][0])
+        N, dev = model_input["coords_frame"].shape[1], model_input["coords_frame"].device
+        self._buffers(N, dev)
+        R, t, _ = L.frame_table(m)
+        stream = _lib.stream_ptr(dev)
+        key = self._batch_key(model_input, gt)
+        if self._presel is not None and self._presel[0] == key:
+            cur = self._presel[1]
+            b = self._buffers(N, dev, True, cur)
+        else:
+            cur = 0
+            b = self._select(model_input, gt, 0)
+        self._bufs = b
         self._m("select")
         feats = m.level_tensors()
+        loss_out = None
+        if self.p2p and self.world > 1:
+            loss_out = self._pack_replicated_grads(feats)
+            if self.rank + 1 < self.world:
+                # the upper neighbour's boundary-plane Adam of the previous step wrote my halo plane of parameters and
+                # consumed my halo plane of gradients: hold the step kernel until it has signalled
+                with torch.cuda.device(dev):
+                    _lib.check(lib.miso_peer_wait(self.sync.data_ptr(), stream), "peer_wait")
         grads = []
         for f in feats:
             if f.requires_grad and f.grad is None:
@@ -259,12 +298,23 @@ class SlabShardedFit:
             grads.append(f.grad if f.requires_grad else None)
         cfg = L._step_cfg()
         cfg.pop("fd_eps", None)
-        own_frames = _field.FramesSpec(b["ids"], frames.R, frames.t)
+        own_frames = _field.FramesSpec(b["ids"], R, t)      # the selection already mapped keyframe ids to table rows
         # the |gt| < eik_trunc count runs over the FULL batch inside mapping_step_raw when gt_sdf_count is given
         terms = mapping_step_raw(feats, grads, m.fused_spec(), own_frames, b["x"], b["sdf"], b["valid"], b["sign"], b["w"],
-                                 n_total=N, n_device=b["count"], count_on=sdf, **cfg)
+                                 n_total=N, n_device=b["count"], count_on=sdf, loss_out=loss_out, **cfg)
         self._m("step_kernel")
+        self._presel = None
+        if prefetch is not None:
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            self._side2.wait_stream(main)       # behind the step kernel (it fills the GPU; buffer set 1 - cur is free by then)
+            with torch.cuda.stream(self._side2):
+                self._select(prefetch[0], prefetch[1], 1 - cur)
+            self._presel = (self._batch_key(*prefetch), 1 - cur)
         self._exchange_and_update(feats, grads, terms, b)
+        if prefetch is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._side2)
         return terms
 
     def _m(self, name):
@@ -285,18 +335,43 @@ class SlabShardedFit:
                 float(self.betas[1]), self.eps, self.step_dev.data_ptr(), self.scalars.data_ptr(), None, 1,
                 _lib.stream_ptr(dev)), "adam_step")
 
+    def _pack_replicated_grads(self, feats):
+        """p2p mode: the gradients of the replicated (non-slab) levels and the step's 4 loss terms live in ONE flat
+        buffer, so a single all_reduce sums them all (and orders the ranks).  Returns the loss-term view."""
+        sl = self.slab_level
+        rep = [f for l, f in enumerate(feats) if l != sl and f.requires_grad]
+        key = tuple(f.data_ptr() for f in rep)
+        if self._flat_buf is None or self._flat_buf[0] != key:
+            total = sum(f.numel() for f in rep)
+            flat = torch.zeros(total + 4, dtype=torch.float32, device=feats[sl].device)
+            off = 0
+            for f in rep:
+                view = flat[off:off + f.numel()].as_strided(f.shape, f.stride())
+                if f.grad is not None:
+                    view.copy_(f.grad)
+                f.grad = view
+                off += f.numel()
+            self._flat_buf = (key, flat, total)
+        _, flat, total = self._flat_buf
+        return flat[total:]
+
+    def check_sync(self):
+        """Raises if a neighbour wait timed out (a rank died or fell out of step).  Synchronises with the host."""
+        if self.p2p and int(self.sync[2].item()) != 0:
+            raise RuntimeError("SlabShardedFit: timed out waiting for the upper neighbour's boundary-plane update")
+
     def _open_peers(self, feats, grads):
         """Map the lower neighbour's gradient and parameter buffers of the slab level into this process (CUDA IPC).
         Collective (all_gather_object): every rank calls it at the same point, outside any graph capture."""
         lib, sl = _lib.load(), self.slab_level
         mine = []
-        for t in (grads[sl], feats[sl]):
+        for t in (grads[sl], feats[sl], self.sync):
             h, off = (C.c_ubyte * 64)(), C.c_int64(0)
             _lib.check(lib.miso_ipc_export(t.data_ptr(), h, C.byref(off)), "ipc_export")
             mine.append((bytes(h), int(off.value)))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
-        self._peer = {"key": (grads[sl].data_ptr(), feats[sl].data_ptr()), "g": None, "p": None}
+        self._peer = {"key": (grads[sl].data_ptr(), feats[sl].data_ptr()), "g": None, "p": None, "flag": None}
         if self.rank > 0:
             ptrs = []
             with torch.cuda.device(feats[sl].device):
@@ -305,7 +380,7 @@ class SlabShardedFit:
                     _lib.check(lib.miso_ipc_import((C.c_ubyte * 64).from_buffer_copy(hb), off, C.byref(out)), "ipc_import")
                     ptrs.append(int(out.value))
             plane = self.zb * self.plane_elems * 4        # my first plane == the neighbour's halo plane `ze`
-            self._peer["g"], self._peer["p"] = ptrs[0] + plane, ptrs[1] + plane
+            self._peer["g"], self._peer["p"], self._peer["flag"] = ptrs[0] + plane, ptrs[1] + plane, ptrs[2]
         dist.barrier()
 
     def _exchange_and_update(self, feats, grads, terms, b):
@@ -321,8 +396,9 @@ class SlabShardedFit:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream(dev)
-            # (1) every rank's step kernel is complete once this all_reduce returns: the neighbour's halo plane is final
-            mdist.allreduce_sum_(coarse)
+            # (1) every rank's step kernel is complete once this all_reduce returns: the neighbour's halo plane is final.
+            # One buffer: the replicated levels' gradients and the loss terms (`terms` is its tail view)
+            mdist.allreduce_sum_([self._flat_buf[1]])
             self._m("allreduce_coarse")
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
@@ -336,12 +412,11 @@ class SlabShardedFit:
                         self.b_exp_avg_sq.data_ptr(), self.plane_elems, self._peer["g"], self._peer["p"], self.lr,
                         float(self.betas[0]), float(self.betas[1]), self.eps, self.b_step_dev.data_ptr(),
                         self.b_scalars.data_ptr(), _lib.stream_ptr(dev)), "adam_step_halo")
+                    # (2) tell the lower neighbour: its halo plane of parameters is written, its halo plane of gradients
+                    # consumed and cleared -- it waits for this before its next step kernel (miso_peer_wait in step())
+                    _lib.check(lib.miso_peer_signal(self._peer["flag"], _lib.stream_ptr(dev)), "peer_signal")
             main.wait_stream(self._side)
-            self._m("adam_interior|coarse+halo")
-            # (2) ... and every rank's Adam is complete once this one returns: my halo plane `ze` holds the upper
-            # neighbour's new parameters and my gradient plane `ze` has been consumed (and cleared) by it
-            mdist.allreduce_sum_([terms])
-            self._m("allreduce_terms")
+            self._m("adam_interior|coarse+halo+signal")
             self.step_count += 1
             return
         g, p = self._flat(grads[sl]), self._flat(feats[sl])
@@ -360,24 +435,34 @@ class SlabShardedFit:
             # parameter halo: the next step reads plane `ze` (owned and just updated by rank r+1)
             exchange_halo_planes_down(p[self.zb] if r > 0 else None, p[self.ze] if self.ze < self.Z else None, r, W)
 
-    def graphed_step(self, model_input: dict, gt: dict):
+    def graphed_step(self, model_input: dict, gt: dict, prefetch_same: bool = False):
         """Capture `step` on these (device-resident, fixed-address) batch tensors into a CUDA graph -- slab selection,
-        fused step, the all_reduces, the halo exchange (peer-memory Adam or NCCL P2P) and the Adam sweeps -- after one eager step on a side stream
-        (module loading, NCCL channel setup; it counts as a training step).  Returns `replay() -> loss terms`: one
-        graph launch per step, which matters here because a step is ~15 short launches and collectives."""
+        fused step, the all_reduce, the halo exchange (peer-memory Adam or NCCL P2P) and the Adam sweeps -- after one eager
+        step on a side stream (module loading, NCCL channel setup, peer mappings; it counts as a training step).  Returns
+        `replay() -> loss terms`: one graph launch per step, which matters here because a step is ~15 short launches.
+        `prefetch_same`: the tensors are a staging slot that holds the NEXT batch by the time a step's kernel has run
+        (or a resident batch): every step also selects the slot's samples for the following step (two graphs, alternating
+        between the two compaction buffer sets)."""
+        pf = (model_input, gt) if prefetch_same else None
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            self.step(model_input, gt)
+            self.step(model_input, gt, prefetch=pf)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            terms = self.step(model_input, gt)
-        self._graph = graph   # keep alive
+        graphs = []
+        for _ in range(2 if prefetch_same else 1):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                terms = self.step(model_input, gt, prefetch=pf)
+            graphs.append((graph, terms))
+        self._graphs = graphs   # keep alive
+        turn = [0]
 
         def replay():
+            graph, terms = graphs[turn[0] % len(graphs)]
+            turn[0] += 1
             graph.replay()
             return terms
         return replay
@@ -387,6 +472,7 @@ class SlabShardedFit:
         """Every rank ends up with the full slab level (one broadcast per slab from its owner)."""
         if self.world == 1:
             return
+        self.check_sync()
         p = self._flat(self.model.level_tensors()[self.slab_level])
         for owner in range(self.world):
             dist.broadcast(p[self.bounds[owner]:self.bounds[owner + 1]], src=owner)
