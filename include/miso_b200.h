@@ -363,7 +363,7 @@ int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64_t n, float
  * the neighbour's memory (pointer from miso_ipc_import) once everything enqueued before it on `stream` is complete;
  * miso_peer_wait(sync) holds `stream` until sync[0] (the counter the peer bumps) has reached sync[1], then increments
  * sync[1] (the number of waits so far).  sync: 4 device uint32 {counter, waits, error, -}, zero-initialised; the wait
- * gives up after ~4 s and sets sync[2] instead of hanging the device. */
+ * gives up after ~30 s and sets sync[2] instead of hanging the device. */
 int miso_peer_signal(uint32_t* flag_peer, miso_stream_t stream);
 int miso_peer_wait(uint32_t* sync, miso_stream_t stream);
 

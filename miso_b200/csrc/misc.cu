@@ -471,7 +471,7 @@ extern "C" int miso_adam_step_halo(float* p, float* g, float* m, float* v, int64
 // Neighbour-to-neighbour ordering without a collective (slab-sharded fit): after its boundary-plane Adam a rank bumps a
 // counter in the LOWER neighbour's memory; before its next step kernel that neighbour waits until the counter has reached
 // the number of steps it has taken.  sync = {flag (written by the peer), expected, error, -}.  The wait gives up after
-// ~4 s (error word set, checked by the host) instead of hanging the GPU.
+// ~30 s (error word set, checked by the host) instead of hanging the GPU.
 __global__ void peer_signal_kernel(unsigned* flag_peer) {
   __threadfence_system();
   atomicAdd_system(flag_peer, 1u);
@@ -481,7 +481,7 @@ __global__ void peer_wait_kernel(unsigned* sync) {
   sync[1] = want + 1u;
   const long long t0 = clock64();
   while (*reinterpret_cast<volatile unsigned*>(sync) < want) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (clock64() - t0 > 60000000000LL) {
       sync[2] = 1u;
       break;
     }
