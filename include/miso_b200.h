@@ -278,7 +278,11 @@ int miso_atlas_features(const miso_field_t* fields, int32_t num_fields, const in
  * (S,6) through the transforms and the closed-form derivative of Exp; (3) torch.optim.Adam on (w_s, tau_s),
  * s >= 1 (submap 0 fixed, base.py:104-108), state in exp_avg / exp_avg_sq (S,6), step = ++*iter_counter.
  * w_ptrs / tau_ptrs are DEVICE arrays of S device pointers to the (1,3) / (3,1) correction tensors, which are
- * updated in place.  A multi-GPU run all-reduces `grads` between (2) and (3).  Rt (S,12) = [R row-major, t]. */
+ * updated in place.  A multi-GPU run all-reduces `grads` (and `contrib`) between (2) and (3).  Rt (S,12) = [R row-major, t].
+ * contrib (S floats, optional): number of pairs that gave submap s a gradient this iteration; with it and
+ * submap_steps (S int32, zero-initialised) the Adam kernel skips submaps with contrib == 0 -- no moment decay, no step
+ * increment -- as torch.optim.Adam skips a parameter whose .grad is None (a submap none of whose pairs intersects any
+ * more stops moving, base.py:112-146), and bias-corrects with the submap's own step count. */
 int miso_align_compose_poses(const float* R0, const float* t0, float* const* w_ptrs, float* const* tau_ptrs,
                              int32_t num_submaps, const int32_t* src, const int32_t* dst, int32_t num_pairs,
                              float* poses24, float* Rt_out, miso_stream_t stream);
@@ -286,10 +290,10 @@ int miso_align_pose_grads(const float* R0, const float* t0, float* const* w_ptrs
                           int32_t num_submaps, const int32_t* src, const int32_t* dst, int32_t num_pairs,
                           const double* align_out, const float* poses24, const float* Rt, int32_t channels_used,
                           float align_weight, float* grads, float* loss_hist, int32_t* iter_counter,
-                          float* pair_loss, miso_stream_t stream);
+                          float* pair_loss, float* contrib, miso_stream_t stream);
 int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t num_submaps, const float* grads,
                          float* exp_avg, float* exp_avg_sq, int32_t* iter_counter, float lr, float beta1,
-                         float beta2, float eps, miso_stream_t stream);
+                         float beta2, float eps, const float* contrib, int32_t* submap_steps, miso_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Helpers around the path.

@@ -265,6 +265,9 @@ class FusedPoseAligner:
         self.Rt = torch.zeros((S, 12), dtype=torch.float32, device=dev)
         self.out = torch.zeros((max(self.P, 1), _lib.MISO_ALIGN_OUT), dtype=torch.float64, device=dev)
         self.grads = torch.zeros((S, 6), dtype=torch.float32, device=dev)
+        # pairs that gave each submap a gradient this iteration; a submap with none is skipped by Adam (grad None in torch)
+        self.contrib = torch.zeros(S, dtype=torch.float32, device=dev)
+        self.submap_steps = torch.zeros(S, dtype=torch.int32, device=dev)
         self.exp_avg = torch.zeros((S, 6), dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros((S, 6), dtype=torch.float32, device=dev)
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -297,13 +300,15 @@ class FusedPoseAligner:
                 self.R0.data_ptr(), self.t0.data_ptr(), self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S,
                 self.src.data_ptr(), self.dst.data_ptr(), self.P, self.out.data_ptr(), self.poses24.data_ptr(),
                 self.Rt.data_ptr(), b.norm_channels, self.align_weight, self.grads.data_ptr(), self.loss_hist.data_ptr(),
-                self.iter_counter.data_ptr(), self.pair_loss.data_ptr(), stream), "align_pose_grads")
+                self.iter_counter.data_ptr(), self.pair_loss.data_ptr(), self.contrib.data_ptr(), stream),
+                "align_pose_grads")
             if self.allreduce is not None:
-                self.allreduce([self.grads])
+                self.allreduce([self.grads, self.contrib])
             _lib.check(lib.miso_align_pose_adam(
                 self.w_ptrs.data_ptr(), self.tau_ptrs.data_ptr(), self.S, self.grads.data_ptr(),
                 self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.iter_counter.data_ptr(), self.lr,
-                float(self.betas[0]), float(self.betas[1]), self.eps, stream), "align_pose_adam")
+                float(self.betas[0]), float(self.betas[1]), self.eps, self.contrib.data_ptr(),
+                self.submap_steps.data_ptr(), stream), "align_pose_adam")
 
     def run(self, num_iters: int, use_cuda_graph: bool = True):
         """`num_iters` iterations; returns the per-iteration total losses (device tensor).  With a CUDA graph the

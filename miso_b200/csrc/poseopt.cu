@@ -93,10 +93,13 @@ __global__ void __launch_bounds__(256)
                       const double* __restrict__ out, const float* __restrict__ poses24, const float* __restrict__ Rt, int K,
                       float align_weight,
                       float* __restrict__ grads /* (S,6): dw, dtau */, float* __restrict__ loss_hist,
-                      int32_t* __restrict__ iter_counter, float* __restrict__ pair_loss /* optional (P) */) {
+                      int32_t* __restrict__ iter_counter, float* __restrict__ pair_loss /* optional (P) */,
+                      float* __restrict__ contrib /* optional (S): pairs that gave submap s a gradient */) {
   __shared__ double dR[kMaxSubmaps][9];
   __shared__ double dt[kMaxSubmaps][3];
+  __shared__ int nc[kMaxSubmaps];
   __shared__ double total;
+  for (int i = threadIdx.x; i < T.S; i += blockDim.x) nc[i] = 0;
   for (int i = threadIdx.x; i < T.S * 9; i += blockDim.x) dR[i / 9][i % 9] = 0.0;
   for (int i = threadIdx.x; i < T.S * 3; i += blockDim.x) dt[i / 3][i % 3] = 0.0;
   if (threadIdx.x == 0) total = 0.0;
@@ -119,6 +122,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < 9; ++i) A2[i] = (double)A2f[i];
     const int s = src[p], d = dst[p];
+    atomicAdd(&nc[s], 1);
+    atomicAdd(&nc[d], 1);
     // dA1 = A2^T G2 s ; db1 = A2^T G0 s ; dA2 = G1 s ; db2 = G0 s
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -193,22 +198,30 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) grads[s * 6 + 3 + i] = (float)dt[s][i];     // t = t0 + tau
+    if (contrib) contrib[s] = (float)nc[s];
   }
   if (threadIdx.x == 0 && loss_hist && iter_counter) loss_hist[*iter_counter] = (float)total;
 }
 
 // torch.optim.Adam (single-tensor semantics, no amsgrad / weight decay) on (w_s, tau_s) of submaps 1..S-1.
+// With `contrib` / `submap_steps`: a submap no pair gave a gradient to in this iteration (contrib[s] == 0) is skipped --
+// no moment decay, no step increment, no momentum drift -- exactly like a parameter whose .grad is None in
+// torch.optim.Adam (the reference's loss simply does not depend on it then), and bias correction uses the submap's own
+// step count.
 __global__ void __launch_bounds__(256)
     pose_adam_kernel(PoseTables T, const float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v,
-                     int32_t* __restrict__ iter_counter, float lr, float b1, float b2, float eps) {
-  const int step = *iter_counter + 1;
-  const double bc1 = 1.0 - pow((double)b1, (double)step);
-  const double bc2 = 1.0 - pow((double)b2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+                     int32_t* __restrict__ iter_counter, float lr, float b1, float b2, float eps,
+                     const float* __restrict__ contrib, int32_t* __restrict__ submap_steps) {
+  const int global_step = *iter_counter + 1;
   for (int i = threadIdx.x; i < T.S * 6; i += blockDim.x) {
     const int s = i / 6, c = i % 6;
     if (s == 0) continue;                       // submap 0 stays fixed (base.py:104-108)
+    if (contrib && contrib[s] == 0.f) continue;
+    const int step = submap_steps ? submap_steps[s] + 1 : global_step;
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
     float* p = c < 3 ? &T.w[s][c] : &T.tau[s][c - 3];
     const float g = grads[i];
     const float mi = m[i] + (g - m[i]) * (1.f - b1);
@@ -219,7 +232,10 @@ __global__ void __launch_bounds__(256)
     v[i] = vi;
   }
   __syncthreads();
-  if (threadIdx.x == 0) *iter_counter = step;
+  if (submap_steps)
+    for (int s = 1 + threadIdx.x; s < T.S; s += blockDim.x)
+      if (!contrib || contrib[s] != 0.f) submap_steps[s] += 1;
+  if (threadIdx.x == 0) *iter_counter = global_step;
 }
 
 }  // namespace miso
@@ -246,23 +262,25 @@ extern "C" int miso_align_pose_grads(const float* R0, const float* t0, float* co
                                      int32_t num_submaps, const int32_t* src, const int32_t* dst, int32_t num_pairs,
                                      const double* align_out, const float* poses24, const float* Rt, int32_t channels_used,
                                      float align_weight, float* grads, float* loss_hist, int32_t* iter_counter,
-                                     float* pair_loss, miso_stream_t stream) {
+                                     float* pair_loss, float* contrib, miso_stream_t stream) {
   if (int e = check_tables(num_submaps, R0, t0, w_ptrs, tau_ptrs)) return e;
   MISO_REQUIRE(grads && Rt && (num_pairs == 0 || (src && dst && align_out && poses24)), "align_pose_grads: null argument");
   MISO_REQUIRE(channels_used > 0, "align_pose_grads: channels_used must be positive");
   PoseTables T{R0, t0, w_ptrs, tau_ptrs, num_submaps};
   pose_grads_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(T, src, dst, num_pairs, align_out, poses24, Rt, channels_used,
-                                                       align_weight, grads, loss_hist, iter_counter, pair_loss);
+                                                       align_weight, grads, loss_hist, iter_counter, pair_loss, contrib);
   return check_launch("align_pose_grads");
 }
 
 extern "C" int miso_align_pose_adam(float* const* w_ptrs, float* const* tau_ptrs, int32_t num_submaps,
                                     const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* iter_counter,
-                                    float lr, float beta1, float beta2, float eps, miso_stream_t stream) {
+                                    float lr, float beta1, float beta2, float eps, const float* contrib,
+                                    int32_t* submap_steps, miso_stream_t stream) {
   MISO_REQUIRE(num_submaps >= 1 && num_submaps <= kMaxSubmaps, "align_pose_adam: num_submaps %d not in [1,%d]",
                num_submaps, kMaxSubmaps);
   MISO_REQUIRE(w_ptrs && tau_ptrs && grads && exp_avg && exp_avg_sq && iter_counter, "align_pose_adam: null argument");
   PoseTables T{nullptr, nullptr, w_ptrs, tau_ptrs, num_submaps};
-  pose_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(T, grads, exp_avg, exp_avg_sq, iter_counter, lr, beta1, beta2, eps);
+  pose_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(T, grads, exp_avg, exp_avg_sq, iter_counter, lr, beta1, beta2, eps,
+                                                        contrib, submap_steps);
   return check_launch("align_pose_adam");
 }

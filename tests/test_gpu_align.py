@@ -254,3 +254,47 @@ def test_intersection_counts_lattice_path_equals_per_vertex_path():
         q = G.transfrom_points_from(G.transform_points_to(v, Rs, ts), Rd, td)
         ref = int(G.coords_in_bound(q, atlas.get_submap(d).bound.cuda()).sum())
         assert abs(int(counts[0][i]) - ref) <= max(4, ref // 20000), (s, d, int(counts[0][i]), ref)
+
+
+def test_pose_adam_skips_submaps_without_a_gradient():
+    """A submap none of whose pairs gave a gradient this iteration has .grad None in the reference's loop (its loss does
+    not depend on the submap), so torch.optim.Adam leaves it alone: no moment decay, no step increment, no momentum
+    drift.  miso_align_pose_adam with `contrib` / `submap_steps` against torch.optim.Adam with per-iteration None
+    gradients (submap 2 contributes in iterations 0 and 2 only, submap 3 never; submap 0 is fixed)."""
+    from miso_b200 import _lib
+    lib = _lib.load()
+    S, iters = 4, 4
+    g = torch.Generator().manual_seed(3)
+    w0 = [torch.randn(1, 3, generator=g) * 0.1 for _ in range(S)]
+    t0 = [torch.randn(3, 1, generator=g) * 0.1 for _ in range(S)]
+    grads = torch.randn(iters, S, 6, generator=g)
+    contrib = torch.tensor([[2, 3, 1, 0], [2, 2, 0, 0], [1, 1, 1, 0], [1, 1, 0, 0]], dtype=torch.float32)
+    # reference semantics
+    pw = [torch.nn.Parameter(x.clone()) for x in w0]
+    pt = [torch.nn.Parameter(x.clone()) for x in t0]
+    opt = torch.optim.Adam(pw[1:] + pt[1:], lr=1e-2)
+    for it in range(iters):
+        for s in range(1, S):
+            has = contrib[it, s] > 0
+            pw[s].grad = grads[it, s, :3].reshape(1, 3).clone() if has else None
+            pt[s].grad = grads[it, s, 3:].reshape(3, 1).clone() if has else None
+        opt.step()
+    # kernel
+    dw = [x.clone().cuda() for x in w0]
+    dt = [x.clone().cuda() for x in t0]
+    w_ptrs = torch.tensor([x.data_ptr() for x in dw], dtype=torch.int64, device="cuda")
+    t_ptrs = torch.tensor([x.data_ptr() for x in dt], dtype=torch.int64, device="cuda")
+    m = torch.zeros(S, 6, device="cuda")
+    v = torch.zeros(S, 6, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    steps = torch.zeros(S, dtype=torch.int32, device="cuda")
+    for it in range(iters):
+        gi, ci = grads[it].contiguous().cuda(), contrib[it].contiguous().cuda()
+        _lib.check(lib.miso_align_pose_adam(w_ptrs.data_ptr(), t_ptrs.data_ptr(), S, gi.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                            counter.data_ptr(), 1e-2, 0.9, 0.999, 1e-8, ci.data_ptr(), steps.data_ptr(),
+                                            _lib.stream_ptr(torch.device("cuda", 0))), "align_pose_adam")
+    torch.cuda.synchronize()
+    assert int(counter.item()) == iters and steps.tolist() == [0, 4, 2, 0]
+    for s in range(S):
+        assert rel_err(dw[s], pw[s]) < 1e-6 and rel_err(dt[s], pt[s]) < 1e-6, s
+    assert torch.equal(dw[3].cpu(), w0[3]) and torch.equal(dw[0].cpu(), w0[0])
