@@ -42,7 +42,7 @@ struct Tc2Smem {
   alignas(128) unsigned char w1j_hi[16 * tc::kK * 4];   // Jacobian product: canonical [16][64], row i = W1[:, i] (rows >= F zero)
   alignas(128) unsigned char w1j_lo[16 * tc::kK * 4];
   alignas(16) float2 ep[H];       // {b2, W3}
-  alignas(16) float b3[4];        // {b3, a scale, eikonal scale, -}
+  alignas(16) float b3[4];        // {b3, a scale, eikonal scale, mode 4: sample count as int bits}
   uint64_t bar[G];
   uint32_t tmem_base;
   float ppx[G * 256];             // partial sdf of each thread, read by its partner
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(G * 256, 1)
     s->b3[1] = (1.0f / n_den) * m.cfg.grad_scale;                                       // a scale
     s->b3[2] = m.cfg.weight_eik * m.cfg.grad_scale * 2.f * (1.0f / n_eik);              // eikonal scale
     s->b3[3] = 0.f;
+    if constexpr (kMode == 4) s->b3[3] = __int_as_float(min((int)m.N, *m.cfg.n_device));   // device-side sample count
   }
   const bool poses_in_smem = fr.ids != nullptr && fr.num_frames <= kTc2MaxSmemPoses;
   if (poses_in_smem) {
@@ -408,17 +409,20 @@ __global__ void __launch_bounds__(G * 256, 1)
 
   float acc_sdf = 0.f, acc_fs = 0.f, acc_eik = 0.f;
   const int tile_stride = (int)gridDim.x * G;   // 32-bit point indices: the host routes N >= 2^31 - 2^24 elsewhere
-  // device-side sample count (batch compacted by miso_slab_select): the launch is sized for m.N, tiles past it exit
-  // (kMode 4; mode 0 keeps the count in the constant bank -- one more live register spills in this 64-register kernel)
-  int N32 = (int)m.N;
-  if constexpr (kMode == 4) N32 = min(N32, *m.cfg.n_device);
+  // device-side sample count (batch compacted by miso_slab_select): the launch is sized for m.N, tiles past it exit.
+  // Mode 0 reads the count from the constant bank; mode 4 re-reads it from shared memory (the spare word of b3, staged
+  // with the decoder) at each of its three uses per tile instead of keeping it live in this 64-register kernel.
+  auto n_limit = [&]() -> int {
+    if constexpr (kMode == 4) return __float_as_int(*reinterpret_cast<volatile float*>(&s->b3[3]));
+    else return (int)m.N;
+  };
   // Point work (load, frame->world, normalise) is done ONCE per point, by half 1, one tile ahead: the result is
   // parked in the idle A_lo operand and picked up by both halves after the next group barrier, so the dependent
   // id -> pose -> transform chain and its global-load latency are off the tile's critical path.
   auto stage_point = [&](int t2) {
     const int n2 = t2 * 128 + pt;
     float p[3] = {0.f, 0.f, 0.f};
-    if (n2 < N32) {
+    if (n2 < n_limit()) {
       // finite-difference passes (miso_mapping_step_fd) run over 6 N "virtual" points: virtual index k N + i is
       // sample i displaced by +eps (k even) / -eps (k odd) along axis k / 2, in world coordinates (diff.py:18-26)
       int nb = n2, k = -1;
@@ -448,9 +452,9 @@ __global__ void __launch_bounds__(G * 256, 1)
   };
   if (half == 1) stage_point((int)blockIdx.x * G + grp);
   group_barrier(grp);
-  for (int tile = (int)blockIdx.x * G + grp; tile * 128 < N32; tile += tile_stride) {
+  for (int tile = (int)blockIdx.x * G + grp; tile * 128 < n_limit(); tile += tile_stride) {
     const int n = tile * 128 + pt;
-    const bool active = n < N32;
+    const bool active = n < n_limit();
     float xn[3];
     {
       const float4 q = xnbuf[pt];   // normalised coordinates, produced one tile ahead by half 1 (see below)
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(G * 256, 1)
       stage_point(tile + tile_stride);
     } else {
       const int n3 = n + 2 * tile_stride * 128;   // two tiles ahead: pull the per-point inputs towards this SM
-      if (n3 < N32 && !kVirt) {
+      if (n3 < n_limit() && !kVirt) {
         prefetch_l1(m.x + 3 * (int64_t)n3);
         prefetch_l1(m.x + 3 * (int64_t)n3 + 2);
         if (fr.ids) prefetch_l1(fr.ids + n3);
