@@ -632,6 +632,38 @@ def test_graphed_train_step_equals_eager_steps():
         assert rel_err(out[1][1][l], o2.features[l]) < TOL_G
 
 
+def test_graphed_train_step_with_trainable_decoder():
+    """decoder.fix: False under the CUDA-graph trainer: the decoder-gradient pass and the decoder's Adam launches are
+    captured with the step; six graph launches equal six eager steps (losses, grids, decoder weights)."""
+    from miso_b200.loss import MisoLossMapping
+    from miso_b200.trainer import GridTrainer
+    mi, gt, (R, t) = _batch(5000, seed=13)
+    dmi, dgt = _to_cuda(mi), _to_cuda(gt)
+    mk = lambda: MisoLossMapping(loss_type="L2", weight_sdf=1.0, weight_eik=0.5, weight_fs=0.1, trunc_dist=0.15,
+                                 grad_method="autograd", eik_trunc_dist=None)
+    out = []
+    for graph in (False, True):
+        net, _, _ = make_pair(fix=False)
+        for k in range(R.shape[0]):
+            net.set_initial_kf_pose(k, R[k], t[k], kf_key=f"KF{k}")
+        net.unlock_feature()
+        net.lock_pose()
+        tr = GridTrainer({"learning_rate": 1e-3, "grid_training_mode": "joint", "cuda_graph": graph}, net, mk(), None,
+                         device="cuda")
+        step = (lambda: tr.graphed_train_step(dmi, dgt)) if graph else (lambda: tr.train_step(dmi, dgt))
+        losses = [step().clone() for _ in range(6)]
+        out.append((torch.stack(losses), [p.detach().clone() for p in net.level_tensors()],
+                    [p.detach().clone() for p in net.decoder.parameters()]))
+    w0 = list(synth.decoder_weights(8, seed=0).values())
+    assert rel_err(out[1][0], out[0][0]) < 1e-5
+    for a, b in zip(out[1][1], out[0][1]):
+        assert rel_err(a, b) < 1e-5
+    for a, b, c in zip(out[1][2], out[0][2], w0):
+        assert rel_err(a, b) < 1e-5
+        if c.numel() > 1:
+            assert rel_err(a, c) > 1e-3      # and the decoder was trained
+
+
 def test_nan_total_skips_the_update_on_the_device():
     """grid_opt/trainer.py:214-217 (`if not isnan(total): backward(); step()`): a step whose total is NaN (here: a
     keyframe without a pose poisons it) leaves parameters, moments and the Adam step counter untouched and clears the
