@@ -117,7 +117,8 @@ class SlabShardedFit:
         if halo not in ("auto", "p2p", "nccl"):
             raise ValueError(f"halo must be 'auto', 'p2p' or 'nccl', not {halo!r}")
         live = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        self.p2p = halo == "p2p" or (halo == "auto" and live and f.is_cuda and dist.get_backend() == "nccl")
+        self.p2p = halo == "p2p" or (halo == "auto" and live and f.is_cuda and dist.get_backend() == "nccl"
+                                     and self._one_node())
         if self.p2p and not (live and self.world == dist.get_world_size() and self.rank == dist.get_rank()):
             raise RuntimeError("halo='p2p' needs an initialised process group whose ranks are the slab owners")
         self._peer, self._side, self._side2, self._flat_buf = None, None, None, None
@@ -132,6 +133,14 @@ class SlabShardedFit:
         self.other = FusedAdam([p for l, p in enumerate(feats) if l != self.slab_level and p.requires_grad],
                                lr=lr, betas=betas, eps=eps, device_step=True)
         self._bufs = None
+
+    @staticmethod
+    def _one_node() -> bool:
+        """True when every rank of the process group runs on this host (CUDA IPC peer mappings need that).  Collective."""
+        import socket
+        names = [None] * dist.get_world_size()
+        dist.all_gather_object(names, socket.gethostname())
+        return len(set(names)) == 1
 
     # ---- slabs ---------------------------------------------------------------------------------------
     def _configure_axis(self, axis: int):
