@@ -17,8 +17,13 @@ that lets the per-rank terms and gradients sum.  Two splits are implemented:
     level starts in its planes (`miso_slab_select`, device-side compaction, no host sync), runs the fused step on
     them with the GLOBAL batch size as denominator, and owns the Adam update of its planes.  A sample touches planes
     [z, z+1], so what crosses ranks per step is ONE plane of gradients up and one plane of parameters down per
-    neighbour (0.8 MB for the NCD quad grid instead of 324 MB), plus an all_reduce of the small replicated levels'
-    gradients and of the four loss terms.  Slab boundaries balance the sample count (`calibrate`).
+    neighbour (0.8 MB for the NCD quad grid instead of 324 MB), plus ONE all_reduce of the small replicated levels'
+    gradients and the four loss terms.  On one node (`halo="p2p"`) the two planes do not travel as messages at all:
+    the boundary plane's Adam kernel (`miso_adam_step_halo`) reads the neighbour's gradient plane and writes the
+    neighbour's parameter plane directly over NVLink peer memory (buffers mapped with CUDA IPC), the interior planes'
+    Adam overlaps it on a second stream, and the neighbour is released by a counter in peer memory
+    (`miso_peer_signal` / `miso_peer_wait`) instead of a second collective; `halo="nccl"` keeps batched isend/irecv.
+    Slab boundaries come from a two-phase cost model (`calibrate`): max samples per rank + c * max parameters per rank.
 
 Both reproduce the single-GPU step up to the order of the float32 atomics.  `gather_model` re-assembles the full level
 on every rank (checkpointing / meshing).
