@@ -93,3 +93,26 @@ def test_calibrate_picks_the_cheaper_axis_for_a_skewed_batch():
         assert fits[r].calibrate(mi, voxel_cost=vc) == bounds
         fits[r].restore_layout()
     assert fits[0].axis == 2 and net.level_tensors()[fits[0].slab_level].stride(2) > net.level_tensors()[fits[0].slab_level].stride(3)
+
+
+def test_replicated_gradients_and_loss_terms_share_one_buffer():
+    """p2p mode sums the replicated levels' gradients and the 4 loss terms with ONE all_reduce: their storage is one
+    flat buffer, each .grad a strided view of it with the parameter's own layout, existing gradient values kept."""
+    net, _ = _model_and_batch(n=16)
+    fit = sf.SlabShardedFit(net, MisoLossMapping(loss_type="L2", weight_eik=0.0), rank=0, world=1)
+    feats = net.level_tensors()
+    coarse = [f for l, f in enumerate(feats) if l != fit.slab_level][0]
+    coarse.grad = torch.arange(coarse.numel(), dtype=torch.float32).reshape(coarse.shape).contiguous(
+        memory_format=torch.channels_last_3d) if coarse.stride(1) == 1 else torch.ones_like(coarse)
+    before = coarse.grad.clone()
+    terms = fit._pack_replicated_grads(feats)
+    key, flat, total = fit._flat_buf
+    assert terms.numel() == 4 and total == coarse.numel() and flat.numel() == total + 4
+    assert terms.data_ptr() == flat.data_ptr() + 4 * total
+    assert coarse.grad.data_ptr() == flat.data_ptr() and coarse.grad.stride() == coarse.stride()
+    assert torch.equal(coarse.grad, before)
+    coarse.grad.add_(1.0)
+    terms.fill_(7.0)
+    assert float(flat[:total].sum()) == float((before + 1.0).sum()) and flat[total:].tolist() == [7.0] * 4
+    assert fit._pack_replicated_grads(feats).data_ptr() == terms.data_ptr()      # cached: same buffer on the next step
+    assert feats[fit.slab_level].grad is None                                     # the slab level is not replicated
